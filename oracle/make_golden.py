@@ -1,0 +1,152 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container.
+
+TEST INFRASTRUCTURE ONLY (see oracle/clip_oracle.py header).  Usage, from the repo root, in the
+build container where /root/reference is mounted:
+
+    python oracle/make_golden.py
+
+It imports ``src.models.components.loss`` (ClipLoss, gather_features) and
+``src.models.components.base_encoder`` (Normalize, LearnableLogitScaling) from /root/reference,
+runs them in float64 / float32 / bfloat16 on bf16-valued synthetic inputs (single process and
+2-rank gloo) and stores inputs + outputs.  Nothing at test or bench time reads /root/reference;
+the fixtures are the pin for oracle/clip_oracle.py.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REF = os.environ.get("ONEPROT_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def _ref():
+    sys.path.insert(0, REF)
+    from src.models.components.loss import ClipLoss, gather_features  # noqa: F401
+    from src.models.components.base_encoder import Normalize, LearnableLogitScaling  # noqa: F401
+    return ClipLoss, gather_features, Normalize, LearnableLogitScaling
+
+
+def bf16_bits(t: torch.Tensor) -> np.ndarray:
+    return t.to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+
+
+def single_process_cases():
+    from oracle.clip_oracle import synthetic_pair
+    ClipLoss, _, _, _ = _ref()
+    out = {}
+    cases = [
+        # name, n, d, correlated, temperature_into_b, logit_scale (None => python float 1.0)
+        ("n25_d64_train", 25, 64, True, True, None),
+        ("n96_d128_uncorr", 96, 128, False, True, None),
+        ("n100_d72_scale", 100, 72, True, False, 1.0 / 0.07),
+        ("n256_d512_train", 256, 512, True, True, None),          # BASELINE configs[0] shape
+        ("n256_d512_scale", 256, 512, True, False, 1.0 / 0.07),
+    ]
+    for name, n, d, corr, t_in_b, s in cases:
+        a, b = synthetic_pair(n, d, seed=1234, pair_id=0, rank=0, correlated=corr,
+                              temperature_into_b=t_in_b, dtype="bf16")
+        rec = {"A_bf16": bf16_bits(a), "B_bf16": bf16_bits(b),
+               "scale": np.float64(1.0 if s is None else s), "scale_is_tensor": np.bool_(s is not None)}
+        for tag, td in (("f64", torch.float64), ("f32", torch.float32), ("bf16", torch.bfloat16)):
+            A = a.to(td).requires_grad_(True)
+            B = b.to(td).requires_grad_(True)
+            if s is None:
+                ls = 1.0
+            else:
+                ls = torch.tensor(s, dtype=td, requires_grad=True)
+            loss = ClipLoss(world_size=1)(A, B, ls)
+            loss.backward()
+            rec[f"loss_{tag}"] = np.float64(loss.detach().double().item())
+            if tag == "f64":
+                # the second 256x512 case keeps only the first 8 gradient rows (fixture size)
+                keep = 8 if name == "n256_d512_scale" else n
+                rec["dA_f64"] = A.grad.numpy()[:keep].astype(np.float32)
+                rec["dB_f64"] = B.grad.numpy()[:keep].astype(np.float32)
+                rec["dscale_f64"] = np.float64(0.0 if s is None else ls.grad.item())
+            if tag == "bf16":
+                rec["loss_bf16_dtype"] = np.bytes_(str(loss.dtype))
+        out[name] = rec
+    for name, rec in out.items():
+        np.savez_compressed(os.path.join(OUT, f"clip_single_{name}.npz"), **rec)
+        print("wrote", name, {k: v for k, v in rec.items() if np.ndim(v) == 0})
+
+
+def _dist_worker(rank, world, port, n, d, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    ClipLoss, _, _, _ = _ref()
+    from oracle.clip_oracle import synthetic_pair
+    a, b = synthetic_pair(n, d, seed=4321, pair_id=0, rank=rank, correlated=True,
+                          temperature_into_b=False, dtype="bf16")
+    rec = {"A_bf16": bf16_bits(a), "B_bf16": bf16_bits(b)}
+    for local_loss in (False, True):
+        for gwg in (False, True):
+            A = a.double().requires_grad_(True)
+            B = b.double().requires_grad_(True)
+            ls = torch.tensor(1.0 / 0.07, dtype=torch.float64, requires_grad=True)
+            loss = ClipLoss(local_loss=local_loss, gather_with_grad=gwg, cache_labels=True,
+                            rank=rank, world_size=world)(A, B, ls)
+            # distinct upstream gradient per rank exercises the reduce-scatter convention
+            (loss * (1.0 + 0.5 * rank)).backward()
+            tag = f"ll{int(local_loss)}_gwg{int(gwg)}"
+            rec[f"loss_{tag}"] = np.float64(loss.item())
+            rec[f"dA_{tag}"] = A.grad.numpy().copy()
+            rec[f"dB_{tag}"] = B.grad.numpy().copy()
+            rec[f"dscale_{tag}"] = np.float64(ls.grad.item())
+    results[rank] = rec
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def distributed_cases():
+    world, n, d = 2, 12, 32
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_dist_worker, args=(world, 29611, n, d, results), nprocs=world, join=True)
+    flat = {"world": np.int64(world), "n": np.int64(n), "d": np.int64(d),
+            "scale": np.float64(1.0 / 0.07), "grad_outputs": np.array([1.0, 1.5])}
+    for r in range(world):
+        for k, v in results[r].items():
+            flat[f"r{r}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "clip_dist_w2_n12_d32.npz"), **flat)
+    print("wrote distributed", {k: float(v) for k, v in flat.items() if k.startswith("r") and "loss" in k})
+
+
+def epilogue_cases():
+    _, _, Normalize, LearnableLogitScaling = _ref()
+    g = torch.Generator().manual_seed(77)
+    x = (3.0 * torch.randn(8, 64, generator=g)).to(torch.bfloat16)
+    x[3] = 0  # exercises the eps clamp of F.normalize
+    gy = torch.randn(8, 64, generator=g).to(torch.bfloat16)
+    X = x.double().requires_grad_(True)
+    y = Normalize(dim=-1)(X)
+    y.backward(gy.double())
+    scl = LearnableLogitScaling(logit_scale_init=1 / 0.07, learnable=True)
+    ys = scl(y.detach().float())
+    big = LearnableLogitScaling(logit_scale_init=250.0, learnable=False)   # clipped to 100
+    yb = big(y.detach().float())
+    np.savez_compressed(os.path.join(OUT, "epilogue_normalize_scale.npz"),
+                        x_bf16=bf16_bits(x), gy_bf16=bf16_bits(gy),
+                        y_f64=y.detach().numpy(), gx_f64=X.grad.numpy(),
+                        log_logit_scale=np.float64(scl.log_logit_scale.item()),
+                        ys_f32=ys.detach().numpy(),
+                        log_logit_scale_big=np.float64(big.log_logit_scale.item()),
+                        yb_f32=yb.detach().numpy())
+    print("wrote epilogue")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    single_process_cases()
+    distributed_cases()
+    epilogue_cases()

@@ -1,0 +1,91 @@
+"""CPU: pins oracle/clip_oracle.py against fixtures generated from the unmodified reference
+(oracle/make_golden.py).  The reference's own tests hold no golden vector for this path
+(SURVEY.md section 4), so these reference-generated fixtures are the pin."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as oc
+from tests.helpers import GOLDEN, bf16_from_bits, cosine, load_golden, rel_err
+
+SINGLE = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "clip_single_*.npz")))
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_closed_form_matches_reference_single(name):
+    g = load_golden(name)
+    A = bf16_from_bits(g["A_bf16"]).double().numpy()
+    B = bf16_from_bits(g["B_bf16"]).double().numpy()
+    res = oc.clip_loss_closed_form(A, B, float(g["scale"]))
+    assert rel_err(res.loss, g["loss_f64"]) < 1e-12
+    keep = g["dA_f64"].shape[0]
+    np.testing.assert_allclose(res.dA[:keep], g["dA_f64"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(res.dB[:keep], g["dB_f64"], rtol=2e-6, atol=1e-9)
+    if bool(g["scale_is_tensor"]):
+        assert rel_err(res.dscale, g["dscale_f64"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_port_matches_reference_single(name):
+    g = load_golden(name)
+    a = bf16_from_bits(g["A_bf16"])
+    b = bf16_from_bits(g["B_bf16"])
+    s = float(g["scale"])
+    for tag, td, tol in (("f64", torch.float64, 1e-12), ("f32", torch.float32, 1e-6)):
+        ls = torch.tensor(s, dtype=td) if bool(g["scale_is_tensor"]) else 1.0
+        loss, dA, dB = oc.clip_loss_port_fwd_bwd(a.to(td), b.to(td), ls)
+        assert rel_err(loss.item(), g[f"loss_{tag}"]) < tol
+        if tag == "f64":
+            keep = g["dA_f64"].shape[0]
+            assert cosine(dA[:keep].numpy(), g["dA_f64"]) > 1 - 1e-10
+            assert cosine(dB[:keep].numpy(), g["dB_f64"]) > 1 - 1e-10
+    # the reference returns a bf16 scalar for bf16 inputs; the port does too
+    ls = torch.tensor(s, dtype=torch.bfloat16) if bool(g["scale_is_tensor"]) else 1.0
+    lb = oc.clip_loss_port(a, b, ls)
+    assert lb.dtype == torch.bfloat16
+    assert float(lb) == float(g["loss_bf16"])
+
+
+def test_closed_form_matches_reference_distributed_conventions():
+    g = load_golden("clip_dist_w2_n12_d32.npz")
+    W = int(g["world"])
+    A_all = np.concatenate([bf16_from_bits(g[f"r{r}_A_bf16"]).double().numpy() for r in range(W)])
+    B_all = np.concatenate([bf16_from_bits(g[f"r{r}_B_bf16"]).double().numpy() for r in range(W)])
+    for ll in (False, True):
+        for gwg in (False, True):
+            tag = f"ll{int(ll)}_gwg{int(gwg)}"
+            for r in range(W):
+                res = oc.clip_loss_closed_form(A_all, B_all, float(g["scale"]), rank=r, world_size=W,
+                                               local_loss=ll, gather_with_grad=gwg,
+                                               grad_outputs=g["grad_outputs"])
+                assert rel_err(res.loss, g[f"r{r}_loss_{tag}"]) < 1e-12, tag
+                np.testing.assert_allclose(res.dA, g[f"r{r}_dA_{tag}"], rtol=1e-9, atol=1e-13, err_msg=tag)
+                np.testing.assert_allclose(res.dB, g[f"r{r}_dB_{tag}"], rtol=1e-9, atol=1e-13, err_msg=tag)
+                assert rel_err(res.dscale, g[f"r{r}_dscale_{tag}"]) < 1e-9, tag
+
+
+def test_epilogue_closed_forms():
+    g = load_golden("epilogue_normalize_scale.npz")
+    x = bf16_from_bits(g["x_bf16"]).double().numpy()
+    gy = bf16_from_bits(g["gy_bf16"]).double().numpy()
+    np.testing.assert_allclose(oc.normalize_closed_form(x), g["y_f64"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(oc.normalize_backward_closed_form(x, gy), g["gx_f64"], rtol=1e-9, atol=1e-12)
+    y = g["y_f64"].astype(np.float32).astype(np.float64)
+    ys, s = oc.logit_scaling_closed_form(y, float(g["log_logit_scale"]))
+    np.testing.assert_allclose(ys, g["ys_f32"], rtol=1e-6)
+    yb, sb = oc.logit_scaling_closed_form(y, float(g["log_logit_scale_big"]))
+    assert sb == 100.0
+    np.testing.assert_allclose(yb, g["yb_f32"], rtol=1e-6)
+
+
+def test_synthetic_generator_is_deterministic():
+    a1, b1 = oc.synthetic_pair(16, 32, seed=5, rank=1)
+    a2, b2 = oc.synthetic_pair(16, 32, seed=5, rank=1)
+    assert torch.equal(a1, a2) and torch.equal(b1, b2)
+    assert a1.dtype == torch.bfloat16
+    # unit-norm anchor, temperature folded into B
+    assert abs(a1.float().norm(dim=-1).mean().item() - 1.0) < 1e-2
+    assert abs(b1.float().norm(dim=-1).mean().item() - 1 / 0.07) < 0.2

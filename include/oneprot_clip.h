@@ -1,0 +1,133 @@
+/* oneprot_clip.h - C ABI of the B200-native ClipLoss hot path (liboneprot_clip.so).
+ *
+ * The reference (klemens-floege/oneprot) has no FFI for this path: the boundary is the Python
+ * class ClipLoss (src/models/components/loss.py:49-114) plus gather_features (loss.py:19-46) and
+ * the Normalize / LearnableLogitScaling epilogue (src/models/components/base_encoder.py:6-33).
+ * Each entry point below states which reference lines it replaces.  All pointers are raw device
+ * pointers owned by the caller (PyTorch's caching allocator in the Python host); the library
+ * allocates no device memory and keeps no state besides a thread-local error string.  Every
+ * function returns 0 on success and a non-zero code otherwise (oneprot_last_error() describes
+ * it); nothing throws across this boundary.  `stream` is a cudaStream_t passed as void*.
+ *
+ * Notation: n = rows held by this rank, N = global rows (= world_size * n), d = feature dim,
+ * row_offset = rank * n, A = first positional feature tensor (n x d, row-major, bf16),
+ * B_all = second positional feature tensor gathered over ranks (N x d, row-major, bf16).
+ *   x_ij = c * <a_i, b_j>,  c = logit_scale * log2(e)   (logits in log2 units, fp32 accumulators)
+ *   e_ij = 2^(x_ij - G),    G = max(0, |c| * max|a| * max|b| - 100)  (one global reference)
+ */
+#ifndef ONEPROT_CLIP_H
+#define ONEPROT_CLIP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONEPROT_ABI_VERSION 1
+
+/* error codes */
+#define ONEPROT_OK 0
+#define ONEPROT_ERR_ARG 1      /* bad argument (null pointer, misaligned, unsupported shape) */
+#define ONEPROT_ERR_CUDA 2     /* CUDA runtime / driver error */
+#define ONEPROT_ERR_DEVICE 3   /* device is not sm_100 (no tcgen05 / TMEM) */
+
+int oneprot_abi_version(void);
+const char* oneprot_last_error(void);
+/* 0 iff `device` exists and is compute capability 10.x */
+int oneprot_device_check(int device);
+/* number of kernel launches issued by this library on the calling thread since the last reset */
+long long oneprot_launch_count(void);
+void oneprot_launch_count_reset(void);
+
+/* ---- gradient / value conventions --------------------------------- */
+#define ONEPROT_MODE_GLOBAL 0  /* local_loss = False : value = global loss                    */
+#define ONEPROT_MODE_LOCAL 1   /* local_loss = True  : value = mean over this rank's rows/cols */
+
+/* ---- forward ------------------------------------------------------------------------------ */
+
+/* Row statistics: diag[i] = <a_i, b_{row_offset+i}> (fp32), stats[0] = max_i |a_i|^2,
+ * stats[1] = max_j |b_j|^2 over B_all (atomic max; caller zero-initialises stats[0..1]).
+ * Replaces nothing 1:1 - it supplies the label logits that F.cross_entropy gathers
+ * (loss.py:109-112 with labels from get_ground_truth, loss.py:72-83). */
+int oneprot_clip_rowstats(const void* A, const void* B_all, int n, int N, int d, int row_offset,
+                          float* diag, float* stats, void* stream);
+
+/* Bytes of scratch oneprot_clip_fwd_sums needs for a (n x N) logit panel. */
+size_t oneprot_clip_fwd_scratch_bytes(int n, int N);
+
+/* Fused logit GEMM + exp-sum epilogue (tcgen05/TMEM/TMA): for the row panel
+ * Z[row_offset : row_offset+n, 0:N] computes, without ever storing a logit,
+ *   rowsum[i] = sum_j e_ij (complete for this rank's rows)  and
+ *   colsum[j] = sum_{i in panel} e_ij (partial over ranks; sum them across ranks).
+ * Replaces get_logits (loss.py:85-101) + the log_softmax half of F.cross_entropy (loss.py:109-112).
+ * scale_dev: device pointer to the fp32 logit_scale; stats: as written by rowstats (after a
+ * cross-rank max when world_size > 1). */
+int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
+                          const float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
+                          void* stream);
+
+/* Loss value + softmax normalisers from complete sums (all length N, global index order):
+ *   loss_out[0] = this rank's return value (MODE_GLOBAL: mean over all N; MODE_LOCAL: mean over
+ *   rows/cols [row_offset, row_offset+n)), fp32;  inv_rowsum/inv_colsum[k] = 1/sum;
+ *   flag[0] |= 1 if any sum left the validated fp32 window (result then not trustworthy).
+ * Replaces the nll half of F.cross_entropy and the /2 (loss.py:109-112). */
+int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N,
+                               int n, int row_offset, int mode, const float* scale_dev, const float* stats,
+                               float* loss_out, float* inv_rowsum, float* inv_colsum, int* flag, void* stream);
+
+/* ---- backward ----------------------------------------------------------------------------- */
+
+/* Per-row / per-column / diagonal coefficients of dL/dZ for the panel of this rank:
+ *   Wz_ij = e_ij * (wr[i] + wc[j]) - [i == j] * dg[i]      (already multiplied by logit_scale)
+ * gvec_dev[world] holds the upstream gradient of every rank (device fp32; world = 1: one value).
+ * use_gsum != 0 applies the reduce-scatter-SUM convention of torch.distributed.nn.all_gather's
+ * backward (loss.py:32-33): coefficients carry sum_r g_r (MODE_GLOBAL) or g_owner (MODE_LOCAL).
+ * part: 0 = both softmax directions, 1 = row-softmax part only, 2 = column-softmax part only
+ * (the two halves of the local_loss=True, gather_with_grad=False convention). */
+int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, int N, int n, int row_offset,
+                             int mode, int use_gsum, int part, int world, int rank, const float* gvec_dev,
+                             const float* scale_dev, float* wr, float* wc, float* dg, void* stream);
+
+/* Recompute logit tiles for rows [r0, r0+rows) of this rank's panel and write
+ * Wz (bf16, row-major, leading dimension ldw >= N, multiple of 8) - the bounded dL/dZ panel.
+ * A_rows points at row r0 of A; wr/dg point at element r0.  grow0 = row_offset + r0 (global row
+ * of the first panel row, for the diagonal).  Replaces the autograd backward of
+ * F.cross_entropy (loss.py:109-112). */
+int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0,
+                          const float* scale_dev, const float* stats, const float* wr, const float* wc,
+                          const float* dg, void* Wz, int ldw, void* stream);
+
+/* C[M x Nc] = op(A) * op(B) with bf16 operands, fp32 accumulation in TMEM.
+ *   a_mn = 0: A is M x K row-major (lda >= K);  a_mn = 1: A is K x M row-major (lda >= M)
+ *   b_mn = 0: B is Nc x K row-major (ldb >= K); b_mn = 1: B is K x Nc row-major (ldb >= Nc)
+ * value = acc + (acc_in ? acc_in[m*ldc+n] : 0); stored to acc_out (fp32) and/or out_bf16 (bf16),
+ * whichever is non-null, both with leading dimension ldc.  Replaces the autograd backward of
+ * the logits matmul (loss.py:92-99): dA = Wz * B_all (a_mn=0,b_mn=1), dB = Wz^T * A (a_mn=1,b_mn=1). */
+int oneprot_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
+                      const float* acc_in, float* acc_out, void* out_bf16, int ldc, void* stream);
+
+/* ---- L2-normalise / logit-scale epilogue (base_encoder.py:6-33) -------------------------- */
+
+/* y = scale * x / max(|x|_2, eps) row-wise; x, y: rows x d bf16 (or fp32 when is_fp32);
+ * inv_norm[rows] (fp32) is saved for the backward.  scale_dev may be NULL (scale = 1).
+ * Replaces Normalize.forward (base_encoder.py:11-12) fused with
+ * LearnableLogitScaling.forward (base_encoder.py:29-30; the clip(exp(log_s), max) is computed by
+ * the caller into scale_dev). */
+int oneprot_l2norm_scale_fwd(const void* x, void* y, float* inv_norm, int rows, int d, int is_fp32,
+                             const float* scale_dev, float eps, void* stream);
+/* gx = scale * inv_norm * (gy - yhat * <yhat, gy>), yhat = x * inv_norm;
+ * dscale_partial[row] = <yhat, gy> (sum over rows = d loss / d scale), may be NULL. */
+int oneprot_l2norm_scale_bwd(const void* x, const void* gy, const float* inv_norm, void* gx, float* dscale_partial,
+                             int rows, int d, int is_fp32, const float* scale_dev, float eps, void* stream);
+
+/* Split fp32 rows into bf16 limbs for the fp32-accurate path: out is rows x (terms*d) bf16 with
+ * the limb order given by `pattern`, so that the bf16 GEMM over the
+ * concatenated K reproduces the fp32 dot product. */
+int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int terms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONEPROT_CLIP_H */

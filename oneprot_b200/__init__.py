@@ -1,0 +1,17 @@
+"""oneprot_b200 - B200-native (sm_100a) implementation of OneProt's ClipLoss hot path.
+
+Public surface mirrors the reference (klemens-floege/oneprot, src/models/components/loss.py and
+base_encoder.py): ``ClipLoss``, ``gather_features``, ``Normalize``, ``LearnableLogitScaling``.
+"""
+__version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # lazy: importing the package must not import torch-heavy modules for `build()`
+    if name in ("ClipLoss", "gather_features"):
+        from . import clip_loss
+        return getattr(clip_loss, name)
+    if name in ("Normalize", "LearnableLogitScaling", "NormalizeAndScale"):
+        from . import epilogue
+        return getattr(epilogue, name)
+    raise AttributeError(name)

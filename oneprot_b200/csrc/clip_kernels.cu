@@ -1,0 +1,1018 @@
+// B200 (sm_100a) kernels + C ABI for the OneProt ClipLoss hot path.  See include/oneprot_clip.h for
+// the contract of every entry point and DESIGN.md for the data layout and rooflines.
+//
+// One warp-specialised mainloop serves every tensor-core kernel here:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 4-stage smem ring, SWIZZLE_128B)
+//   warp 1      UMMA issuer    (tcgen05.mma cta_group::1, M=128 x N=256 x K=16, fp32 accum in TMEM)
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers; thread = one accumulator row)
+// The epilogues differ: exp-sum (forward), dL/dZ panel (backward), plain store (dA / dB GEMMs).
+#include "ptx.cuh"
+#include "../../include/oneprot_clip.h"
+
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+
+namespace op {
+
+constexpr int BM = 128;            // accumulator rows  (TMEM lanes)
+constexpr int BN = 256;            // accumulator cols  (TMEM columns per buffer)
+constexpr int BK = 64;             // bf16 elements per smem row = 128 B = one swizzle atom
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float G_MARGIN = 100.0f;   // e_ij <= 2^100 guaranteed by the Cauchy-Schwarz bound
+
+struct __align__(16) SmemTail {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+  alignas(16) float colvec[BN];   // read back as float4
+};
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + sizeof(SmemTail);
+
+// ------------------------------------------------------------------------------------------
+// mainloop pieces
+// ------------------------------------------------------------------------------------------
+template <int A_MN, int B_MN>
+__device__ __forceinline__ void load_stage(uint8_t* sa, uint8_t* sb, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                           uint64_t* bar, int m0, int n0, int k0) {
+  mbar_arrive_expect_tx(bar, STAGE_BYTES);
+  if (A_MN == 0) {
+    tma_load_2d(sa, mapA, bar, k0, m0);                       // box {64 k, 128 rows}
+  } else {
+#pragma unroll
+    for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, mapA, bar, m0 + c * 64, k0);  // box {64 m, 64 k}
+  }
+  if (B_MN == 0) {
+    tma_load_2d(sb, mapB, bar, k0, n0);                       // box {64 k, 256 rows}
+  } else {
+#pragma unroll
+    for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, mapB, bar, n0 + c * 64, k0);
+  }
+}
+
+template <int A_MN, int B_MN>
+__device__ __forceinline__ void mma_stage(uint32_t sa, uint32_t sb, uint32_t tmem_d, bool first) {
+  constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+#pragma unroll
+  for (int k = 0; k < BK / 16; ++k) {
+    const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+    const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+    umma_bf16(tmem_d, da, db, idesc, (first && k == 0) ? 0u : 1u);
+  }
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+};
+
+struct Smem {
+  uint8_t* stages;
+  SmemTail* tail;
+};
+
+__device__ __forceinline__ Smem carve_smem(uint8_t* raw) {
+  uintptr_t p = (reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023);
+  Smem s;
+  s.stages = reinterpret_cast<uint8_t*>(p);
+  s.tail = reinterpret_cast<SmemTail*>(p + STAGES * STAGE_BYTES);
+  return s;
+}
+
+// Common prologue: barrier init, TMEM alloc.  Returns the TMEM base address.
+__device__ __forceinline__ uint32_t kernel_prologue(const Smem& s, const CUtensorMap* mapA, const CUtensorMap* mapB) {
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 && lane_id() == 0) {
+    prefetch_tmap(mapA);
+    prefetch_tmap(mapB);
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.tail->full[i], 1);
+      mbar_init(&s.tail->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tail->tfull[i], 1);
+      mbar_init(&s.tail->tempty[i], EPI_THREADS / 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&s.tail->tmem_base, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return s.tail->tmem_base;
+}
+
+__device__ __forceinline__ void kernel_epilogue_dealloc(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Butterfly transposing reduction: every lane holds v[0..31] (one value per column, for its
+// own row); afterwards lane l holds in v[0] the sum over the 32 lanes of column l.
+__device__ __forceinline__ void warp_transpose_sum32(float (&v)[32]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; ++k) {
+      const float keep = up ? v[k + o] : v[k];
+      const float send = up ? v[k] : v[k + o];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// S-kernels: logits tile = A_rows(128 x d) . B_all(256 x d)^T, both K-major.
+// Work item = (column block j, chunk of CI row blocks); rows sweep inside an item so that the
+// per-column accumulators stay in registers.
+// ------------------------------------------------------------------------------------------
+struct SParams {
+  int rows;        // rows of A in this launch
+  int N;           // columns = rows of B_all
+  int nK;          // ceil(d / 64)
+  int nI, nJ;      // row blocks (128), column blocks (256)
+  int CI;          // row blocks per work item
+  int nChunks;     // ceil(nI / CI)
+  int grow0;       // global row index of row 0 (diagonal)
+  const float* scale;   // device scalar
+  const float* stats;   // [maxA2, maxB2]
+  // forward
+  float* rowpart;  // [2*nJ][ldr]
+  float* colpart;  // [4*nChunks][ldc]
+  int ldr, ldc;
+  // dz
+  const float* wr;
+  const float* wc;
+  const float* dg;
+  __nv_bfloat16* Wz;
+  int ldw;
+};
+
+__device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& negG) {
+  const float s = __ldg(p.scale);
+  c = s * LOG2E;
+  const float U = fabsf(c) * sqrtf(__ldg(p.stats) * __ldg(p.stats + 1));
+  negG = -fmaxf(0.f, U - G_MARGIN);
+}
+
+enum { EPI_FWD = 0, EPI_DZ = 1 };
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem s = carve_smem(smem_raw);
+  const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
+  const int warp = threadIdx.x >> 5;
+  const int items = p.nJ * p.nChunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    reg_dealloc<56>();   // the 4 control warps hand registers to the 8 epilogue warps
+    if (lane_id() == 0) {
+      PipeState ps;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int jb = item / p.nChunks, ch = item % p.nChunks;
+        const int ib1 = min(p.nI, (ch + 1) * p.CI);
+        for (int ib = ch * p.CI; ib < ib1; ++ib) {
+          for (int kb = 0; kb < p.nK; ++kb) {
+            mbar_wait(&s.tail->empty[ps.stage], ps.phase ^ 1);
+            uint8_t* sa = s.stages + ps.stage * STAGE_BYTES;
+            load_stage<0, 0>(sa, sa + A_STAGE_BYTES, &mapA, &mapB, &s.tail->full[ps.stage], ib * BM, jb * BN, kb * BK);
+            ps.advance();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ UMMA issuer
+    reg_dealloc<56>();
+    if (lane_id() == 0) {
+      PipeState ps;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int ch = item % p.nChunks;
+        const int ib1 = min(p.nI, (ch + 1) * p.CI);
+        for (int ib = ch * p.CI; ib < ib1; ++ib) {
+          mbar_wait(&s.tail->tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int kb = 0; kb < p.nK; ++kb) {
+            mbar_wait(&s.tail->full[ps.stage], ps.phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(s.stages + ps.stage * STAGE_BYTES);
+            mma_stage<0, 0>(sa, sa + A_STAGE_BYTES, tmem_d, kb == 0);
+            umma_commit(&s.tail->empty[ps.stage]);
+            ps.advance();
+          }
+          umma_commit(&s.tail->tfull[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    reg_dealloc<56>();
+  } else {
+    // ------------------------------------------------ epilogue (8 warps)
+    reg_alloc<224>();
+    const int ew = warp - EPI_WARP0;
+    const int q = ew & 3;        // TMEM lane quadrant (== warp % 4)
+    const int h = ew >> 2;       // column half of the 256-wide tile
+    const int lane = lane_id();
+    const int r = q * 32 + lane; // row inside the tile
+    float c, negG;
+    load_c_and_G(p, c, negG);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    float colacc[EPI == EPI_FWD ? 128 : 1];
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int jb = item / p.nChunks, ch = item % p.nChunks;
+      const int ib1 = min(p.nI, (ch + 1) * p.CI);
+      const int j0 = jb * BN + h * 128;   // first column this thread sees
+      if (EPI == EPI_FWD) {
+#pragma unroll
+        for (int k = 0; k < 128; ++k) colacc[k] = 0.f;
+      } else {
+        // stage the per-column weights of this item's 256 columns
+        named_bar_sync(1, EPI_THREADS);
+        const int t = threadIdx.x - EPI_WARP0 * 32;
+        const int jj = jb * BN + t;
+        s.tail->colvec[t] = (jj < p.N) ? __ldg(p.wc + jj) : 0.f;
+        named_bar_sync(1, EPI_THREADS);
+      }
+      for (int ib = ch * p.CI; ib < ib1; ++ib) {
+        const int i = ib * BM + r;
+        const bool rowok = i < p.rows;
+        const bool edge = (ib * BM + BM > p.rows) || (jb * BN + BN > p.N);
+        float wr_i = 0.f, dg_i = 0.f;
+        bool diag_tile = false;
+        if (EPI == EPI_DZ) {
+          if (rowok) { wr_i = __ldg(p.wr + i); dg_i = __ldg(p.dg + i); }
+          const int g0 = p.grow0 + ib * BM;       // global rows [g0, g0+128)
+          diag_tile = (g0 < j0 + 128) && (j0 < g0 + BM);
+        }
+        mbar_wait(&s.tail->tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
+        float rsum = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+          tmem_ld_32x32(taddr + cc * 32, v);
+          tmem_ld_wait();
+          if (cc == 3) {
+            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
+          }
+          if (EPI == EPI_FWD) {
+            if (!edge) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float e = ex2(fmaf(v[k], c, negG));
+                rsum += e;
+                colacc[cc * 32 + k] += e;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const bool ok = rowok && (j0 + cc * 32 + k < p.N);
+                const float e = ok ? ex2(fmaf(v[k], c, negG)) : 0.f;
+                rsum += e;
+                colacc[cc * 32 + k] += e;
+              }
+            }
+          } else {
+            const float4* cv = reinterpret_cast<const float4*>(&s.tail->colvec[h * 128 + cc * 32]);
+            uint32_t packed[16];
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 w4 = cv[k4];
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+              float dz[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int k = k4 * 4 + u;
+                const float e = ex2(fmaf(v[k], c, negG));
+                dz[u] = e * (wr_i + wv[u]);
+              }
+              if (diag_tile) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (p.grow0 + i == j0 + cc * 32 + k4 * 4 + u) dz[u] -= dg_i;
+              }
+              packed[k4 * 2] = pack_bf16x2(dz[0], dz[1]);
+              packed[k4 * 2 + 1] = pack_bf16x2(dz[2], dz[3]);
+            }
+            if (rowok) {
+              __nv_bfloat16* dst = p.Wz + static_cast<size_t>(i) * p.ldw + j0 + cc * 32;
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                if (j0 + cc * 32 + v4 * 8 < p.ldw)
+                  *reinterpret_cast<uint4*>(dst + v4 * 8) =
+                      make_uint4(packed[v4 * 4], packed[v4 * 4 + 1], packed[v4 * 4 + 2], packed[v4 * 4 + 3]);
+              }
+            }
+          }
+        }
+        if (EPI == EPI_FWD) {
+          p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (EPI == EPI_FWD) {
+        // flush column sums of this item: reduce over the 32 rows of the warp, one slot per (chunk, quadrant)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = colacc[cc * 32 + k];
+          warp_transpose_sum32(v);
+          p.colpart[static_cast<size_t>(ch * 4 + q) * p.ldc + j0 + cc * 32 + lane] = v[0];  // ldc covers nJ*256
+        }
+      }
+    }
+  }
+  kernel_epilogue_dealloc(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic GEMM: C[M x Nc] = op(A) op(B), tile 128 x 256, full K per tile.
+// ------------------------------------------------------------------------------------------
+struct GParams {
+  int M, Nc, nK;
+  int nMb, nNb;
+  const float* acc_in;
+  float* acc_out;
+  __nv_bfloat16* out;
+  int ldc;
+};
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const Smem s = carve_smem(smem_raw);
+  const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
+  const int warp = threadIdx.x >> 5;
+  const int tiles = p.nMb * p.nNb;
+
+  if (warp == 0) {
+    reg_dealloc<56>();
+    if (lane_id() == 0) {
+      PipeState ps;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int mb = t / p.nNb, nb = t % p.nNb;
+        for (int kb = 0; kb < p.nK; ++kb) {
+          mbar_wait(&s.tail->empty[ps.stage], ps.phase ^ 1);
+          uint8_t* sa = s.stages + ps.stage * STAGE_BYTES;
+          load_stage<A_MN, B_MN>(sa, sa + A_STAGE_BYTES, &mapA, &mapB, &s.tail->full[ps.stage], mb * BM, nb * BN,
+                                 kb * BK);
+          ps.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    reg_dealloc<56>();
+    if (lane_id() == 0) {
+      PipeState ps;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(&s.tail->tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.nK; ++kb) {
+          mbar_wait(&s.tail->full[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s.stages + ps.stage * STAGE_BYTES);
+          mma_stage<A_MN, B_MN>(sa, sa + A_STAGE_BYTES, tmem_d, kb == 0);
+          umma_commit(&s.tail->empty[ps.stage]);
+          ps.advance();
+        }
+        umma_commit(&s.tail->tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    reg_dealloc<56>();
+  } else {
+    reg_alloc<224>();
+    const int ew = warp - EPI_WARP0;
+    const int q = ew & 3, h = ew >> 2;
+    const int lane = lane_id();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int mb = t / p.nNb, nb = t % p.nNb;
+      const int m = mb * BM + q * 32 + lane;
+      const int n0 = nb * BN + h * 128;
+      mbar_wait(&s.tail->tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tmem_ld_32x32(taddr + cc * 32, v);
+        tmem_ld_wait();
+        if (cc == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
+        }
+        if (m < p.M) {
+          const size_t base = static_cast<size_t>(m) * p.ldc + n0 + cc * 32;
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            const int n = n0 + cc * 32 + v8 * 8;
+            if (n < p.Nc) {       // Nc % 8 == 0 is required by the host wrapper
+              float x[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) x[u] = v[v8 * 8 + u];
+              if (p.acc_in) {
+                const float4 a0 = *reinterpret_cast<const float4*>(p.acc_in + base + v8 * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(p.acc_in + base + v8 * 8 + 4);
+                x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
+                x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
+              }
+              if (p.acc_out) {
+                *reinterpret_cast<float4*>(p.acc_out + base + v8 * 8) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(p.acc_out + base + v8 * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              }
+              if (p.out) {
+                *reinterpret_cast<uint4*>(p.out + base + v8 * 8) =
+                    make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                               pack_bf16x2(x[6], x[7]));
+              }
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  kernel_epilogue_dealloc(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Small HBM-bound kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// one warp per row index; rows of A (n) and of B_all (N) share the index space
+__global__ void rowstats_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int n, int N,
+                                int d, int row_offset, float* __restrict__ diag, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int total = max(n, N);
+  float maxa = 0.f, maxb = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < total; row += gridDim.x * wpb) {
+    float sa = 0.f, sb = 0.f, sab = 0.f;
+    const bool has_a = row < n, has_b = row < N;
+    const __nv_bfloat16* ap = A + static_cast<size_t>(has_a ? row : 0) * d;
+    const __nv_bfloat16* bp = B + static_cast<size_t>(has_b ? row : 0) * d;
+    const __nv_bfloat16* bd = B + static_cast<size_t>(has_a ? row_offset + row : 0) * d;  // label column of row
+    for (int k = lane * 8; k < d; k += 256) {      // d % 8 == 0
+      float fa[8], fb[8], fd[8];
+      if (has_a) {
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(ap + k), fa);
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(bd + k), fd);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { sa = fmaf(fa[u], fa[u], sa); sab = fmaf(fa[u], fd[u], sab); }
+      }
+      if (has_b) {
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(bp + k), fb);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sb = fmaf(fb[u], fb[u], sb);
+      }
+    }
+    sa = warp_sum(sa); sb = warp_sum(sb); sab = warp_sum(sab);
+    if (has_a) { maxa = fmaxf(maxa, sa); if (lane == 0) diag[row] = sab; }
+    if (has_b) maxb = fmaxf(maxb, sb);
+  }
+  if (lane == 0) {
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned int*>(stats), __float_as_uint(maxa));
+    atomicMax(reinterpret_cast<unsigned int*>(stats + 1), __float_as_uint(maxb));
+  }
+}
+
+// out[k] = sum_s part[s*ld + k], fixed order (deterministic)
+__global__ void reduce_slots_kernel(const float* __restrict__ part, int slots, int ld, int count, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  float acc = 0.f;
+  for (int s = 0; s < slots; ++s) acc += part[static_cast<size_t>(s) * ld + k];
+  out[k] = acc;
+}
+
+// single block: loss value, reciprocal sums, hazard flag
+__global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum,
+                                     const float* __restrict__ diag, int N, int n, int row_offset, int mode,
+                                     const float* __restrict__ scale, const float* __restrict__ stats,
+                                     float* __restrict__ loss_out, float* __restrict__ inv_rs, float* __restrict__ inv_cs,
+                                     int* __restrict__ flag) {
+  __shared__ double red[32];
+  __shared__ int bad_s;
+  const float s = *scale;
+  const float c = s * LOG2E;
+  const float U = fabsf(c) * sqrtf(stats[0] * stats[1]);
+  const float G = fmaxf(0.f, U - G_MARGIN);
+  if (threadIdx.x == 0) bad_s = 0;
+  __syncthreads();
+  const int lo = (mode == ONEPROT_MODE_LOCAL) ? row_offset : 0;
+  const int hi = (mode == ONEPROT_MODE_LOCAL) ? row_offset + n : N;
+  double acc = 0.0;
+  int bad = 0;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const float rs = rowsum[k], cs = colsum[k];
+    // validated window: sums must be finite and not have lost their leading terms to flush-to-zero
+    if (!(rs >= 1e-24f && rs <= 3e38f) || !(cs >= 1e-24f && cs <= 3e38f)) bad = 1;
+    inv_rs[k] = 1.f / rs;
+    inv_cs[k] = 1.f / cs;
+    if (k >= lo && k < hi) {
+      const float zd = s * diag[k];
+      acc += static_cast<double>(LN2 * (G + log2f(rs)) - zd) + static_cast<double>(LN2 * (G + log2f(cs)) - zd);
+    }
+  }
+  if (bad) bad_s = 1;
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    loss_out[0] = static_cast<float>(t / (2.0 * (hi - lo)));
+    if (bad_s) atomicOr(flag, 1);
+  }
+}
+
+__global__ void bwd_weights_kernel(const float* __restrict__ inv_rs, const float* __restrict__ inv_cs, int N, int n,
+                                   int row_offset, int mode, int use_gsum, int part, int world, int rank,
+                                   const float* __restrict__ gvec, const float* __restrict__ scale,
+                                   float* __restrict__ wr, float* __restrict__ wc, float* __restrict__ dg) {
+  const float s = *scale;
+  float gsum = 0.f;
+  for (int r = 0; r < world; ++r) gsum += gvec[r];
+  const float g_own = gvec[rank];
+  const float fr = (part == 2) ? 0.f : 1.f;   // row-softmax half enabled
+  const float fc = (part == 1) ? 0.f : 1.f;   // column-softmax half enabled
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == ONEPROT_MODE_GLOBAL) {
+    const float coef = s * (use_gsum ? gsum : g_own) / (2.f * N);
+    if (k < n) {
+      wr[k] = fr * coef * inv_rs[row_offset + k];
+      dg[k] = (fr + fc) * coef;
+    }
+    if (k < N) wc[k] = fc * coef * inv_cs[k];
+  } else {
+    const int npr = N / world;   // rows per rank
+    if (k < n) {
+      const float coef = s * g_own / (2.f * n);
+      wr[k] = fr * coef * inv_rs[row_offset + k];
+      dg[k] = (fr + fc) * coef;
+    }
+    if (k < N) {
+      const int owner = k / npr;
+      // without gather_with_grad only this rank's own columns carry gradient
+      const float g = use_gsum ? gvec[owner] : (owner == rank ? g_own : 0.f);
+      wc[k] = fc * s * g / (2.f * n) * inv_cs[k];
+    }
+  }
+}
+
+// ---- L2 normalise (+ logit scale) ---------------------------------------------------------
+template <bool FP32>
+__device__ __forceinline__ void load8(const void* base, size_t idx, float (&f)[8]) {
+  if (FP32) {
+    const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + idx), f);
+  }
+}
+template <bool FP32>
+__device__ __forceinline__ void store8(void* base, size_t idx, const float (&f)[8]) {
+  if (FP32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + idx) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
+// one warp per row; the row is read once (kept in registers for d <= 2048) and written once
+template <bool FP32>
+__global__ void l2norm_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, float* __restrict__ inv_norm,
+                                  int rows, int d, const float* __restrict__ scale, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float sc = scale ? *scale : 1.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    float ss = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float f[8];
+      load8<FP32>(x, base + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ss = fmaf(f[u], f[u], ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+    const float m = inv * sc;
+    for (int k = lane * 8; k < d; k += 256) {   // second read hits L1/L2 (row <= 8 KiB)
+      float f[8];
+      load8<FP32>(x, base + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] *= m;
+      store8<FP32>(y, base + k, f);
+    }
+  }
+}
+
+template <bool FP32>
+__global__ void l2norm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ gy,
+                                  const float* __restrict__ inv_norm, void* __restrict__ gx,
+                                  float* __restrict__ dscale_partial, int rows, int d, const float* __restrict__ scale,
+                                  float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float sc = scale ? *scale : 1.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    const float inv = inv_norm[row];
+    float dot = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fg[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(gy, base + k, fg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dot = fmaf(fx[u] * inv, fg[u], dot);
+    }
+    dot = warp_sum(dot);                      // <yhat, gy>
+    if (lane == 0 && dscale_partial) dscale_partial[row] = dot;
+    // below the eps clamp F.normalize is x / eps: the projection term vanishes
+    const bool clamped = inv >= 1.f / eps;
+    const float proj = clamped ? 0.f : dot;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fg[8], o[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(gy, base + k, fg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = sc * inv * (fg[u] - fx[u] * inv * proj);
+      store8<FP32>(gx, base + k, o);
+    }
+  }
+}
+
+// fp32 -> bf16 limbs: x = h + m + l (each bf16).  side 0 (left operand):  [h h m | h m l]
+//                                                   side 1 (right operand): [h m h | l m h]
+// terms = 3 keeps the first three limb products (h.h + h.m + m.h), terms = 6 all six of order <= 2.
+__global__ void split_fp32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int d,
+                                  int side, int terms) {
+  const size_t total = static_cast<size_t>(rows) * d;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = idx / d, col = idx % d;
+    const float v = x[idx];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    const __nv_bfloat16 L[6] = {h, h, m, h, m, l};
+    const __nv_bfloat16 R[6] = {h, m, h, l, m, h};
+    __nv_bfloat16* o = out + row * static_cast<size_t>(terms) * d + col;
+    for (int t = 0; t < terms; ++t) o[static_cast<size_t>(t) * d] = side ? R[t] : L[t];
+  }
+}
+
+}  // namespace op
+
+// ==========================================================================================
+// Host side: C ABI
+// ==========================================================================================
+namespace {
+
+thread_local std::string g_err;
+thread_local long long g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define OP_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(ONEPROT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements,
+// box {64, box_outer}, 128-byte swizzle, out-of-bounds elements read as zero.
+int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(ONEPROT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(ONEPROT_ERR_ARG, "tensor base must be 16-byte aligned and the row pitch a multiple of 8 elements");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ONEPROT_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return ONEPROT_OK;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <typename K>
+int prep_kernel(K kernel) {
+  static thread_local const void* done[8] = {nullptr};
+  for (auto& p : done) {
+    if (p == reinterpret_cast<const void*>(kernel)) return ONEPROT_OK;
+  }
+  OP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, op::SMEM_BYTES));
+  for (auto& p : done) {
+    if (!p) { p = reinterpret_cast<const void*>(kernel); break; }
+  }
+  return ONEPROT_OK;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// choose the row-chunk length of an S-kernel work item: >= 4 waves of items when possible
+void s_schedule(int rows, int N, op::SParams& p) {
+  p.nI = cdiv(rows, op::BM);
+  p.nJ = cdiv(N, op::BN);
+  const int sms = num_sms();
+  int ci = p.nI;
+  // shrink the chunk until there are at least ~6 items per SM (or chunks are 8 row blocks long)
+  while (ci > 8 && static_cast<long long>(p.nJ) * cdiv(p.nI, ci) < 6LL * sms) ci = cdiv(ci, 2);
+  // small problems: make sure every SM gets work even if chunks become short
+  while (ci > 1 && static_cast<long long>(p.nJ) * cdiv(p.nI, ci) < sms) ci = cdiv(ci, 2);
+  p.CI = ci;
+  p.nChunks = cdiv(p.nI, ci);
+}
+
+}  // namespace
+
+extern "C" {
+
+int oneprot_abi_version(void) { return ONEPROT_ABI_VERSION; }
+const char* oneprot_last_error(void) { return g_err.c_str(); }
+long long oneprot_launch_count(void) { return g_launches; }
+void oneprot_launch_count_reset(void) { g_launches = 0; }
+
+int oneprot_device_check(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(ONEPROT_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  if (prop.major != 10) return fail(ONEPROT_ERR_DEVICE, "device is not compute capability 10.x (needs tcgen05/TMEM)");
+  return ONEPROT_OK;
+}
+
+int oneprot_clip_rowstats(const void* A, const void* B_all, int n, int N, int d, int row_offset, float* diag,
+                          float* stats, void* stream) {
+  if (!A || !B_all || !diag || !stats || n <= 0 || N <= 0 || d <= 0) return fail(ONEPROT_ERR_ARG, "rowstats: bad argument");
+  if (d % 8) return fail(ONEPROT_ERR_ARG, "rowstats: d must be a multiple of 8");
+  if (row_offset < 0 || row_offset + n > N) return fail(ONEPROT_ERR_ARG, "rowstats: row_offset out of range");
+  const int total = n > N ? n : N;
+  const int blocks = std::min(cdiv(total, 8), num_sms() * 8);
+  op::rowstats_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(B_all), n, N, d, row_offset, diag, stats);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+size_t oneprot_clip_fwd_scratch_bytes(int n, int N) {
+  op::SParams p{};
+  s_schedule(n, N, p);
+  const size_t ldr = static_cast<size_t>(p.nI) * op::BM, ldc = static_cast<size_t>(p.nJ) * op::BN;
+  return sizeof(float) * (2 * static_cast<size_t>(p.nJ) * ldr + 4 * static_cast<size_t>(p.nChunks) * ldc);
+}
+
+int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
+                          const float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
+                          void* stream) {
+  if (!A || !B_all || !scale_dev || !stats || !rowsum || !colsum || !scratch) return fail(ONEPROT_ERR_ARG, "fwd_sums: null pointer");
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "fwd_sums: need n, N > 0 and d a positive multiple of 8");
+  if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "fwd_sums: scratch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  op::SParams p{};
+  s_schedule(n, N, p);
+  p.rows = n; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = 0;
+  p.scale = scale_dev; p.stats = stats;
+  p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
+  p.rowpart = static_cast<float*>(scratch);
+  p.colpart = p.rowpart + 2 * static_cast<size_t>(p.nJ) * p.ldr;
+  CUtensorMap mapA, mapB;
+  int rc;
+  if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD>))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, op::SMEM_BYTES, st>>>(mapA, mapB, p);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  op::reduce_slots_kernel<<<cdiv(n, 256), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
+  op::reduce_slots_kernel<<<cdiv(N, 256), 256, 0, st>>>(p.colpart, 4 * p.nChunks, p.ldc, N, colsum);
+  g_launches += 2;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N, int n,
+                               int row_offset, int mode, const float* scale_dev, const float* stats, float* loss_out,
+                               float* inv_rowsum, float* inv_colsum, int* flag, void* stream) {
+  if (!rowsum_all || !colsum_all || !diag_all || !scale_dev || !stats || !loss_out || !inv_rowsum || !inv_colsum || !flag)
+    return fail(ONEPROT_ERR_ARG, "loss_finalize: null pointer");
+  if (N <= 0 || n <= 0 || row_offset < 0 || row_offset + n > N) return fail(ONEPROT_ERR_ARG, "loss_finalize: bad sizes");
+  op::loss_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      rowsum_all, colsum_all, diag_all, N, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum, inv_colsum, flag);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, int N, int n, int row_offset, int mode,
+                             int use_gsum, int part, int world, int rank, const float* gvec_dev,
+                             const float* scale_dev, float* wr, float* wc, float* dg, void* stream) {
+  if (!inv_rowsum || !inv_colsum || !gvec_dev || !scale_dev || !wr || !wc || !dg) return fail(ONEPROT_ERR_ARG, "bwd_weights: null pointer");
+  if (world <= 0 || rank < 0 || rank >= world || N % world || n <= 0 || row_offset + n > N)
+    return fail(ONEPROT_ERR_ARG, "bwd_weights: bad sizes");
+  op::bwd_weights_kernel<<<cdiv(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      inv_rowsum, inv_colsum, N, n, row_offset, mode, use_gsum, part, world, rank, gvec_dev, scale_dev, wr, wc, dg);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0,
+                          const float* scale_dev, const float* stats, const float* wr, const float* wc, const float* dg,
+                          void* Wz, int ldw, void* stream) {
+  if (!A_rows || !B_all || !scale_dev || !stats || !wr || !wc || !dg || !Wz) return fail(ONEPROT_ERR_ARG, "dz_panel: null pointer");
+  if (rows <= 0 || N <= 0 || d <= 0 || d % 8 || ldw < N || ldw % 8) return fail(ONEPROT_ERR_ARG, "dz_panel: bad sizes");
+  if (reinterpret_cast<uintptr_t>(Wz) & 15) return fail(ONEPROT_ERR_ARG, "dz_panel: Wz must be 16-byte aligned");
+  op::SParams p{};
+  s_schedule(rows, N, p);
+  p.rows = rows; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = grow0;
+  p.scale = scale_dev; p.stats = stats;
+  p.wr = wr; p.wc = wc; p.dg = dg;
+  p.Wz = static_cast<__nv_bfloat16*>(Wz); p.ldw = ldw;
+  CUtensorMap mapA, mapB;
+  int rc;
+  if ((rc = make_map(&mapA, A_rows, d, rows, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, op::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, p);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
+                      const float* acc_in, float* acc_out, void* out_bf16, int ldc, void* stream) {
+  if (!A || !B || (!acc_out && !out_bf16)) return fail(ONEPROT_ERR_ARG, "gemm: null pointer");
+  if (M <= 0 || Nc <= 0 || K <= 0 || Nc % 8 || ldc % 8 || ldc < Nc) return fail(ONEPROT_ERR_ARG, "gemm: need Nc, ldc multiples of 8, ldc >= Nc");
+  if (lda < (a_mn ? M : K) || ldb < (b_mn ? Nc : K)) return fail(ONEPROT_ERR_ARG, "gemm: leading dimension too small");
+  op::GParams p{};
+  p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
+  p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
+  p.acc_in = acc_in; p.acc_out = acc_out; p.out = static_cast<__nv_bfloat16*>(out_bf16); p.ldc = ldc;
+  CUtensorMap mapA, mapB;
+  int rc;
+  if (a_mn) rc = make_map(&mapA, A, M, K, lda, 64); else rc = make_map(&mapA, A, K, M, lda, op::BM);
+  if (rc) return rc;
+  if (b_mn) rc = make_map(&mapB, B, Nc, K, ldb, 64); else rc = make_map(&mapB, B, K, Nc, ldb, op::BN);
+  if (rc) return rc;
+  const int grid = std::min(num_sms(), p.nMb * p.nNb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LAUNCH_GEMM(AM, BMJ)                                                                       \
+  do {                                                                                             \
+    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ>))) return rc;                                   \
+    op::gemm_kernel<AM, BMJ><<<grid, op::NUM_THREADS, op::SMEM_BYTES, st>>>(mapA, mapB, p);        \
+  } while (0)
+  if (!a_mn && !b_mn) LAUNCH_GEMM(0, 0);
+  else if (!a_mn && b_mn) LAUNCH_GEMM(0, 1);
+  else if (a_mn && !b_mn) LAUNCH_GEMM(1, 0);
+  else LAUNCH_GEMM(1, 1);
+#undef LAUNCH_GEMM
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_l2norm_scale_fwd(const void* x, void* y, float* inv_norm, int rows, int d, int is_fp32,
+                             const float* scale_dev, float eps, void* stream) {
+  if (!x || !y || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "l2norm_fwd: need d a positive multiple of 8");
+  const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) op::l2norm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, y, inv_norm, rows, d, scale_dev, eps);
+  else op::l2norm_fwd_kernel<false><<<blocks, 256, 0, st>>>(x, y, inv_norm, rows, d, scale_dev, eps);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_l2norm_scale_bwd(const void* x, const void* gy, const float* inv_norm, void* gx, float* dscale_partial,
+                             int rows, int d, int is_fp32, const float* scale_dev, float eps, void* stream) {
+  if (!x || !gy || !inv_norm || !gx || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "l2norm_bwd: bad argument");
+  const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) op::l2norm_bwd_kernel<true><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
+  else op::l2norm_bwd_kernel<false><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int terms, void* stream) {
+  if (!x || !out || rows <= 0 || d <= 0 || (terms != 3 && terms != 6) || (side != 0 && side != 1))
+    return fail(ONEPROT_ERR_ARG, "split_fp32: bad argument");
+  const size_t total = static_cast<size_t>(rows) * d;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  op::split_fp32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(out), rows, d, side, terms);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+}  // extern "C"

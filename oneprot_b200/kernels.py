@@ -1,0 +1,139 @@
+"""Tensor-level wrappers over the C ABI (include/oneprot_clip.h).
+
+PyTorch is used here only for device memory and the current CUDA stream; every computation is a
+call into liboneprot_clip.so.  No fallbacks: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+MODE_GLOBAL = 0
+MODE_LOCAL = 1
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.OneProtKernelError("oneprot_b200 kernels need CUDA tensors (no CPU fallback exists)")
+
+
+def _need(t, dtype, what):
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{what}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+
+
+def launch_count() -> int:
+    return int(_lib.load().oneprot_launch_count())
+
+
+def launch_count_reset():
+    _lib.load().oneprot_launch_count_reset()
+
+
+def rowstats(A, B_all, row_offset: int, diag, stats):
+    """diag[i] = <a_i, b_{row_offset+i}>, stats[0:2] = max |a|^2, max |b|^2 (atomic max)."""
+    _need_cuda(A, B_all, diag, stats)
+    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
+    _need(diag, torch.float32, "diag"); _need(stats, torch.float32, "stats")
+    n, d = A.shape
+    N = B_all.shape[0]
+    check(_lib.load().oneprot_clip_rowstats(ptr(A), ptr(B_all), n, N, d, row_offset, ptr(diag), ptr(stats),
+                                            _stream()), "oneprot_clip_rowstats")
+
+
+def fwd_scratch_bytes(n: int, N: int) -> int:
+    return int(_lib.load().oneprot_clip_fwd_scratch_bytes(n, N))
+
+
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None):
+    """rowsum[i] = sum_j e_ij, colsum[j] = sum_i e_ij for the n x N logit panel (never stored)."""
+    _need_cuda(A, B_all, scale_dev, stats, rowsum, colsum)
+    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
+    n, d = A.shape
+    N = B_all.shape[0]
+    need = fwd_scratch_bytes(n, N)
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=A.device)
+    check(_lib.load().oneprot_clip_fwd_sums(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(stats), ptr(rowsum),
+                                            ptr(colsum), ptr(scratch), scratch.numel() * scratch.element_size(),
+                                            _stream()), "oneprot_clip_fwd_sums")
+    return scratch
+
+
+def loss_finalize(rowsum_all, colsum_all, diag_all, n: int, row_offset: int, mode: int, scale_dev, stats,
+                  loss_out, inv_rowsum, inv_colsum, flag):
+    _need_cuda(rowsum_all, colsum_all, diag_all, loss_out, inv_rowsum, inv_colsum, flag)
+    N = rowsum_all.numel()
+    check(_lib.load().oneprot_clip_loss_finalize(ptr(rowsum_all), ptr(colsum_all), ptr(diag_all), N, n, row_offset,
+                                                 mode, ptr(scale_dev), ptr(stats), ptr(loss_out), ptr(inv_rowsum),
+                                                 ptr(inv_colsum), ptr(flag), _stream()),
+          "oneprot_clip_loss_finalize")
+
+
+def bwd_weights(inv_rowsum, inv_colsum, n: int, row_offset: int, mode: int, use_gsum: bool, part: int, world: int,
+                rank: int, gvec, scale_dev, wr, wc, dg):
+    _need_cuda(inv_rowsum, inv_colsum, gvec, scale_dev, wr, wc, dg)
+    N = inv_rowsum.numel()
+    check(_lib.load().oneprot_clip_bwd_weights(ptr(inv_rowsum), ptr(inv_colsum), N, n, row_offset, mode,
+                                               int(use_gsum), part, world, rank, ptr(gvec), ptr(scale_dev), ptr(wr),
+                                               ptr(wc), ptr(dg), _stream()), "oneprot_clip_bwd_weights")
+
+
+def dz_panel(A_rows, B_all, grow0: int, scale_dev, stats, wr, wc, dg, Wz):
+    """Wz[i, j] = e_ij (wr[i] + wc[j]) - [grow0+i == j] dg[i]  (bf16 panel, rows x ldw)."""
+    _need_cuda(A_rows, B_all, wr, wc, dg, Wz)
+    _need(A_rows, torch.bfloat16, "A_rows"); _need(B_all, torch.bfloat16, "B_all"); _need(Wz, torch.bfloat16, "Wz")
+    rows, d = A_rows.shape
+    N = B_all.shape[0]
+    if Wz.shape[0] < rows:
+        raise ValueError("Wz panel has fewer rows than A_rows")
+    check(_lib.load().oneprot_clip_dz_panel(ptr(A_rows), ptr(B_all), rows, N, d, grow0, ptr(scale_dev), ptr(stats),
+                                            ptr(wr), ptr(wc), ptr(dg), ptr(Wz), Wz.stride(0), _stream()),
+          "oneprot_clip_dz_panel")
+
+
+def gemm_bf16(A, a_mn: bool, B, b_mn: bool, M: int, Nc: int, K: int, *, acc_in=None, acc_out=None, out=None):
+    """C[M x Nc] = op(A) op(B); see oneprot_gemm_bf16 in include/oneprot_clip.h."""
+    _need_cuda(A, B, acc_in, acc_out, out)
+    if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16:
+        raise ValueError("gemm_bf16 needs bf16 operands")
+    if A.stride(1) != 1 or B.stride(1) != 1:
+        raise ValueError("gemm_bf16 operands must be row-major (unit inner stride)")
+    ref = out if out is not None else acc_out
+    ldc = ref.stride(0)
+    for t in (acc_in, acc_out, out):
+        if t is not None and (t.stride(0) != ldc or t.stride(1) != 1):
+            raise ValueError("gemm_bf16 outputs must share one row-major leading dimension")
+    check(_lib.load().oneprot_gemm_bf16(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), M, Nc, K,
+                                        ptr(acc_in), ptr(acc_out), ptr(out), ldc, _stream()), "oneprot_gemm_bf16")
+
+
+def l2norm_scale_fwd(x, y, inv_norm, scale_dev=None, eps: float = 1e-12):
+    _need_cuda(x, y, inv_norm, scale_dev)
+    rows, d = x.shape
+    check(_lib.load().oneprot_l2norm_scale_fwd(ptr(x), ptr(y), ptr(inv_norm), rows, d,
+                                               int(x.dtype == torch.float32), ptr(scale_dev), eps, _stream()),
+          "oneprot_l2norm_scale_fwd")
+
+
+def l2norm_scale_bwd(x, gy, inv_norm, gx, dscale_partial=None, scale_dev=None, eps: float = 1e-12):
+    _need_cuda(x, gy, inv_norm, gx, dscale_partial, scale_dev)
+    rows, d = x.shape
+    check(_lib.load().oneprot_l2norm_scale_bwd(ptr(x), ptr(gy), ptr(inv_norm), ptr(gx), ptr(dscale_partial), rows, d,
+                                               int(x.dtype == torch.float32), ptr(scale_dev), eps, _stream()),
+          "oneprot_l2norm_scale_bwd")
+
+
+def split_fp32(x, out, side: int, terms: int):
+    _need_cuda(x, out)
+    rows, d = x.shape
+    check(_lib.load().oneprot_split_fp32(ptr(x), ptr(out), rows, d, side, terms, _stream()), "oneprot_split_fp32")

@@ -85,10 +85,15 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
  * use_gsum != 0 applies the reduce-scatter-SUM convention of torch.distributed.nn.all_gather's
  * backward (loss.py:32-33): coefficients carry sum_r g_r (MODE_GLOBAL) or g_owner (MODE_LOCAL).
  * part: 0 = both softmax directions, 1 = row-softmax part only, 2 = column-softmax part only
- * (the two halves of the local_loss=True, gather_with_grad=False convention). */
+ * (the two halves of the local_loss=True, gather_with_grad=False convention).
+ * MODE_GLOBAL writes a unit-gradient panel description and the upstream gradients go to
+ * out_scale_a[n] (multiplies the rows of dA) and out_scale_b[N] (multiplies the rows of the
+ * partial dB): g_own resp. g_owner(j) without, sum_r g_r with use_gsum.  MODE_LOCAL folds the
+ * gradients into wr/wc and writes ones. */
 int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, int N, int n, int row_offset,
                              int mode, int use_gsum, int part, int world, int rank, const float* gvec_dev,
-                             const float* scale_dev, float* wr, float* wc, float* dg, void* stream);
+                             const float* scale_dev, float* wr, float* wc, float* dg, float* out_scale_a,
+                             float* out_scale_b, void* stream);
 
 /* Recompute logit tiles for rows [r0, r0+rows) of this rank's panel and write
  * Wz (bf16, row-major, leading dimension ldw >= N, multiple of 8) - the bounded dL/dZ panel.
@@ -108,6 +113,23 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
 int oneprot_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
                       const float* acc_in, float* acc_out, void* out_bf16, int ldc, void* stream);
 
+/* Same GEMM with two optional epilogue extras:
+ *   row_scale[M]  : stored value = row_scale[m] * (acc + acc_in)
+ *   dot_mat (bf16, M x Nc, leading dimension ld_dot) + rowdot_part: per-row dot products of the
+ *   UNSCALED value with dot_mat, one partial per 128-column slab:
+ *   rowdot_part[(slab) * ldd + m], ldd = ceil(M/128)*128, slabs = 2*ceil(Nc/256)
+ *   (oneprot_gemm_rowdot_scratch_bytes gives the size).  Used for d logit_scale =
+ *   (1/scale) * sum_i <a_i, dA_i>  (backward of the `logit_scale *` in loss.py:92-99). */
+size_t oneprot_gemm_rowdot_scratch_bytes(int M, int Nc);
+int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
+                         const float* acc_in, float* acc_out, void* out_bf16, int ldc, const float* row_scale,
+                         const void* dot_mat, int ld_dot, float* rowdot_part, void* stream);
+
+/* out[i] = <x_i, y_i> over d bf16 elements (leading dimensions ldx, ldy; multiples of 8). */
+int oneprot_rowdot_bf16(const void* x, int ldx, const void* y, int ldy, int rows, int d, float* out, void* stream);
+/* out[0] = sum of v[0..count) in a fixed order (deterministic). */
+int oneprot_sum_f32(const float* v, int count, float* out, void* stream);
+
 /* ---- L2-normalise / logit-scale epilogue (base_encoder.py:6-33) -------------------------- */
 
 /* y = scale * x / max(|x|_2, eps) row-wise; x, y: rows x d bf16 (or fp32 when is_fp32);
@@ -121,6 +143,12 @@ int oneprot_l2norm_scale_fwd(const void* x, void* y, float* inv_norm, int rows, 
  * dscale_partial[row] = <yhat, gy> (sum over rows = d loss / d scale), may be NULL. */
 int oneprot_l2norm_scale_bwd(const void* x, const void* gy, const float* inv_norm, void* gx, float* dscale_partial,
                              int rows, int d, int is_fp32, const float* scale_dev, float eps, void* stream);
+
+/* y = scale * x over rows x d elements (bf16, or fp32 when is_fp32).  Replaces the multiply of
+ * LearnableLogitScaling.forward (base_encoder.py:29-30) when it is used without Normalize. */
+int oneprot_scale_rows(const void* x, void* y, int rows, int d, int is_fp32, const float* scale_dev, void* stream);
+/* out[row] = <x_row, y_row> for contiguous rows (bf16 or fp32): d scale = sum_rows <x, gy>. */
+int oneprot_rowdot(const void* x, const void* y, int rows, int d, int is_fp32, float* out, void* stream);
 
 /* Split fp32 rows into bf16 limbs for the fp32-accurate path: out is rows x (terms*d) bf16 with
  * the limb order given by `pattern`, so that the bf16 GEMM over the

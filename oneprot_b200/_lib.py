@@ -24,11 +24,17 @@ SIGNATURES = {
     "oneprot_clip_fwd_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_clip_fwd_sums": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _sz, _vp]),
     "oneprot_clip_loss_finalize": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _ip, _vp]),
-    "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "oneprot_clip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _vp]),
+    "oneprot_gemm_rowdot_scratch_bytes": (_sz, [_i, _i]),
+    "oneprot_gemm_bf16_ex": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _fp, _vp, _i, _fp, _vp]),
+    "oneprot_rowdot_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _fp, _vp]),
+    "oneprot_sum_f32": (_i, [_fp, _i, _fp, _vp]),
     "oneprot_l2norm_scale_fwd": (_i, [_vp, _vp, _fp, _i, _i, _i, _fp, _f, _vp]),
     "oneprot_l2norm_scale_bwd": (_i, [_vp, _vp, _fp, _vp, _fp, _i, _i, _i, _fp, _f, _vp]),
+    "oneprot_scale_rows": (_i, [_vp, _vp, _i, _i, _i, _fp, _vp]),
+    "oneprot_rowdot": (_i, [_vp, _vp, _i, _i, _i, _fp, _vp]),
     "oneprot_split_fp32": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
 }
 

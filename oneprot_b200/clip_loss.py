@@ -1,0 +1,483 @@
+"""Drop-in ``ClipLoss`` / ``gather_features`` for OneProt on B200.
+
+Mirrors the reference interface (klemens-floege/oneprot ``src/models/components/loss.py``):
+``ClipLoss(local_loss, gather_with_grad, cache_labels, rank, world_size, use_horovod)`` and
+``forward(modality_features, sequence_features, logit_scale=1.0, output_dict=False)``
+(loss.py:49-114), plus ``gather_features`` (loss.py:19-46).  The module registers no parameters or
+buffers and touches no process group in ``__init__`` (the reference builds it before DDP
+initialises, ``src/models/oneprot_module.py:48-56`` / ``src/train.py:44,88``).
+
+What runs where
+  * every floating-point operation on the path is a kernel of ``liboneprot_clip.so`` reached through
+    the C ABI in ``include/oneprot_clip.h`` (tcgen05/TMEM/TMA for the contractions);
+  * PyTorch supplies device memory, the current stream, autograd bookkeeping and
+    ``torch.distributed`` collectives (all-gather of the second operand, a 3N-float all-reduce of
+    the softmax sums, reduce-scatter of the partial gradient) - the reference's own exchange steps
+    (loss.py:32-38) without its W-fold redundant N x N compute (loss.py:95).
+There is no CPU or eager fallback: without the CUDA library the forward raises.
+
+Sharding: rank r owns rows [r n, (r+1) n) of the logit matrix.  It computes
+the row panel Z[r, :] tile by tile, which gives its row sums exactly and partial column sums;
+one small all-reduce completes the column sums.  Backward recomputes the panel into a bounded
+bf16 dL/dZ workspace (``panel_bytes``), dA_r is complete locally and the partial dB is
+reduce-scattered.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import kernels as _cuda_kernels
+
+try:  # same guard as the reference (loss.py:5-11)
+    import torch.distributed as dist
+    has_distributed = dist.is_available()
+except ImportError:  # pragma: no cover
+    dist = None
+    has_distributed = False
+
+# Kernel provider.  Tests of the host-side sharding logic (CPU, gloo) swap this for an emulation
+# that lives under tests/; the product never does.
+_KERNELS = _cuda_kernels
+
+DEFAULT_PANEL_BYTES = 1 << 30   # bound of the bf16 dL/dZ panel workspace
+
+_SCALE_CACHE = {}               # (device, python float) -> 1-element fp32 device tensor
+
+
+def _float_scale_on(device, value: float) -> torch.Tensor:
+    key = (str(device), float(value))
+    t = _SCALE_CACHE.get(key)
+    if t is None:
+        if len(_SCALE_CACHE) > 64:
+            _SCALE_CACHE.clear()
+        t = torch.full((1,), float(value), dtype=torch.float32, device=device)
+        _SCALE_CACHE[key] = t
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# collectives (plumbing only)
+# ---------------------------------------------------------------------------------------------
+def _all_gather_rows(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
+    """Concatenation over ranks of the contiguous (n x d) tensor, gathered straight into one
+    (W n x d) buffer (the reference builds W tensors and ``torch.cat``s them, loss.py:32-44)."""
+    out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def _reduce_scatter_rows(full: torch.Tensor, rank: int, world_size: int, group=None) -> torch.Tensor:
+    """SUM-reduce-scatter of a (W n x d) tensor along rows; the backward of an all-gather
+    (torch/distributed/nn/functional.py:_AllGather.backward)."""
+    n = full.shape[0] // world_size
+    out = torch.empty((n,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    else:  # gloo has no reduce-scatter
+        tmp = full.contiguous().clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out.copy_(tmp[rank * n:(rank + 1) * n])
+    return out
+
+
+class _AllGatherWithGrad(torch.autograd.Function):
+    """all-gather whose backward is a reduce-scatter SUM (``torch.distributed.nn.all_gather``)."""
+
+    @staticmethod
+    def forward(ctx, x, rank, world_size, group):
+        ctx.rank, ctx.world_size, ctx.group = rank, world_size, group
+        return _all_gather_rows(x, world_size, group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _reduce_scatter_rows(g, ctx.rank, ctx.world_size, ctx.group), None, None, None
+
+
+class _InsertLocalRows(torch.autograd.Function):
+    """Gathered tensor (no grad) whose rows of this rank are the grad-carrying local tensor -
+    the ``gathered[rank] = features`` of loss.py:39-42 without the list + cat."""
+
+    @staticmethod
+    def forward(ctx, gathered, local, rank):
+        ctx.rank, ctx.n = rank, local.shape[0]
+        return gathered
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n], None
+
+
+def gather_features(modality_features, sequence_features, local_loss=False, gather_with_grad=False, rank=0,
+                    world_size=1, use_horovod=False):
+    """Same contract as the reference ``gather_features`` (loss.py:19-46): returns the two feature
+    tensors concatenated over ranks.  ``use_horovod`` is accepted and ignored, as in the reference."""
+    assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+    if gather_with_grad:
+        all_m = _AllGatherWithGrad.apply(modality_features, rank, world_size, None)
+        all_s = _AllGatherWithGrad.apply(sequence_features, rank, world_size, None)
+    else:
+        with torch.no_grad():
+            all_m = _all_gather_rows(modality_features, world_size)
+            all_s = _all_gather_rows(sequence_features, world_size)
+        if not local_loss:
+            all_m = _InsertLocalRows.apply(all_m, modality_features, rank)
+            all_s = _InsertLocalRows.apply(all_s, sequence_features, rank)
+    return all_m, all_s
+
+
+# ---------------------------------------------------------------------------------------------
+# operand preparation
+# ---------------------------------------------------------------------------------------------
+def _prep_side(x: torch.Tensor, side: int):
+    """bf16 GEMM operand of one feature tensor -> (operand, d_padded, split).
+
+    bf16 inputs are used as they are.  fp32 / fp16 inputs are split into bf16 limbs x = h + m (+ l)
+    laid out along K so that one bf16 GEMM reproduces the fp32 dot product:
+    left (side 0) operand [h | h | m], right (side 1) operand [h | m | h] => <l, r> = hh + hm + mh
+    (error 2^-16 per product instead of 2^-8).  Feature dims that are not a multiple of 8 are
+    zero-padded (TMA needs 16-byte row pitches; zero columns change no dot product)."""
+    x = x.detach()
+    d = x.shape[1]
+    pad = (-d) % 8
+    if pad:
+        x = torch.nn.functional.pad(x, (0, pad))
+        d += pad
+    if x.dtype == torch.bfloat16:
+        return x.contiguous(), d, False
+    out = torch.empty(x.shape[0], 3 * d, dtype=torch.bfloat16, device=x.device)
+    _KERNELS.split_fp32(x.float().contiguous(), out, side, 3)
+    return out, d, True
+
+
+class _Operands:
+    """The prepared (A, B) pair of one ClipLoss call."""
+
+    def __init__(self, A: torch.Tensor, B: torch.Tensor):
+        self.in_dtype = A.dtype
+        self.n, self.d_in = A.shape
+        self.A, self.d, self.split = _prep_side(A, 0)
+        self.B, _, _ = _prep_side(B, 1)
+        self.pad = self.d - self.d_in
+        self.dk = self.A.shape[1]          # contraction length seen by the kernels
+
+    # column blocks whose sum reconstructs the fp32 operand (for the gradient GEMMs)
+    def b_pieces(self, B_all):
+        d = self.d
+        return [B_all[:, 0:d], B_all[:, d:2 * d]] if self.split else [B_all]
+
+    def a_pieces(self, A_rows):
+        d = self.d
+        return [A_rows[:, d:2 * d], A_rows[:, 2 * d:3 * d]] if self.split else [A_rows]
+
+    def a_head(self, A_rows):
+        return A_rows[:, 0:self.d] if self.split else A_rows
+
+
+class _GemmChain:
+    """Sum of several GEMM terms into one output: fp32 accumulator chained through acc_in /
+    acc_out, the last term applies the row scale and writes the final dtype."""
+
+    def __init__(self, M, Nc, out: torch.Tensor, row_scale, n_terms: int):
+        self.M, self.Nc, self.out, self.row_scale, self.n_terms = M, Nc, out, row_scale, n_terms
+        self.done = 0
+        self.acc = None
+        if n_terms > 1 and out.dtype != torch.float32:
+            self.acc = torch.empty(M, out.stride(0), dtype=torch.float32, device=out.device)[:, :Nc]
+
+    def add(self, A, a_mn, B, b_mn, K, dot_mat=None, rowdot_part=None):
+        Kn = _KERNELS
+        first, last = self.done == 0, self.done == self.n_terms - 1
+        f32_out = self.out.dtype == torch.float32
+        acc = self.out if f32_out else self.acc
+        kw = dict(dot_mat=dot_mat, rowdot_part=rowdot_part)
+        if last:
+            kw["row_scale"] = self.row_scale
+            if f32_out:
+                Kn.gemm_bf16(A, a_mn, B, b_mn, self.M, self.Nc, K, acc_in=None if first else acc, acc_out=self.out, **kw)
+            else:
+                Kn.gemm_bf16(A, a_mn, B, b_mn, self.M, self.Nc, K, acc_in=None if first else acc, out=self.out, **kw)
+        else:
+            Kn.gemm_bf16(A, a_mn, B, b_mn, self.M, self.Nc, K, acc_in=None if first else acc, acc_out=acc, **kw)
+        self.done += 1
+
+
+# ---------------------------------------------------------------------------------------------
+# the autograd function
+# ---------------------------------------------------------------------------------------------
+class _ClipLossFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, A, B, scale_t, cfg):
+        K = _KERNELS
+        W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
+        dev = A.device
+        ops = _Operands(A, B)
+        n, off = ops.n, rank * ops.n
+        N = W * n
+        B_all = _all_gather_rows(ops.B, W, group) if W > 1 else ops.B
+        scale_dev = scale_t.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+
+        stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        sums = torch.zeros(3 * N, dtype=torch.float32, device=dev)     # [colsum | rowsum | diag], global order
+        colsum, rowsum_all, diag_all = sums[0:N], sums[N:2 * N], sums[2 * N:3 * N]
+        K.rowstats(ops.A, B_all, off, diag_all[off:off + n], stats)
+        if W > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=group)   # one reference G on every rank
+        K.fwd_sums(ops.A, B_all, scale_dev, stats, rowsum_all[off:off + n], colsum)
+        if W > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+
+        out = torch.empty(1 + 2 * N, dtype=torch.float32, device=dev)
+        loss32, inv_rs, inv_cs = out[0:1], out[1:1 + N], out[1 + N:]
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        mode = K.MODE_LOCAL if (W > 1 and cfg["local_loss"]) else K.MODE_GLOBAL
+        K.loss_finalize(rowsum_all, colsum, diag_all, n, off, mode, scale_dev, stats, loss32, inv_rs, inv_cs, flag)
+
+        ctx.cfg, ctx.ops, ctx.mode = cfg, ops, mode
+        ctx.B_all, ctx.scale_dev, ctx.stats, ctx.inv_rs, ctx.inv_cs = B_all, scale_dev, stats, inv_rs, inv_cs
+        ctx.scale_needs_grad = scale_t.requires_grad
+        ctx.scale_meta = (scale_t.dtype, scale_t.device, scale_t.shape)
+        ctx.set_materialize_grads(False)
+        loss_dtype = cfg["loss_dtype"] or ops.in_dtype
+        loss_out = loss32.reshape(()).to(loss_dtype)
+        loss_f32 = loss32.reshape(()).clone()
+        ctx.mark_non_differentiable(loss_f32, flag)
+        return loss_out, loss_f32, flag
+
+    @staticmethod
+    def backward(ctx, g_loss, _g32, _gflag):
+        K = _KERNELS
+        cfg, ops, mode = ctx.cfg, ctx.ops, ctx.mode
+        W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
+        n, d, dk = ops.n, ops.d, ops.dk
+        N, off = W * n, rank * n
+        dev = ops.A.device
+        B_all = ctx.B_all
+        need_a, need_b, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.scale_needs_grad
+
+        g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
+               else g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1))
+        gvec = _all_gather_rows(g32, W, group) if W > 1 else g32
+        local = mode == K.MODE_LOCAL
+        gwg = cfg["gather_with_grad"]
+        # cross-rank gradient only flows where the reference's graph has it
+        exchange_b = W > 1
+        if local and not gwg:
+            passes = [(1, need_a or need_s, False), (2, False, need_b or need_s)]
+        elif local and need_s:
+            passes = [(1, True, True), (2, True, True)]
+        else:
+            passes = [(0, need_a or need_s, need_b or (W > 1))]
+        # collectives must be entered by every rank: with W > 1 the partial dB is always exchanged
+        grad_dtype = torch.float32 if ops.split else torch.bfloat16
+        ldw = (N + 63) // 64 * 64
+        rows_cap = max(128, (cfg["panel_bytes"] // (2 * ldw)) // 128 * 128)
+        panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
+        Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
+
+        vec = torch.empty(3 * n + 2 * N, dtype=torch.float32, device=dev)
+        wr, dg, sA = vec[0:n], vec[n:2 * n], vec[2 * n:3 * n]
+        wc, sB = vec[3 * n:3 * n + N], vec[3 * n + N:]
+
+        dA_total = dB_total = None
+        ds_terms = []      # 1-element tensors whose sum is scale * d(value)/d(scale) * g  (this rank's part)
+        b_pieces, n_bp = ops.b_pieces(B_all), (2 if ops.split else 1)
+        for part, want_a, want_b in passes:
+            K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
+                          wr, wc, dg, sA, sB)
+            dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
+            dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
+            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp) if want_b else None
+            rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
+            for r0, rows in panels:
+                A_rows = ops.A[r0:r0 + rows]
+                K.dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc, dg[r0:r0 + rows], Wz)
+                Wp = Wz[:rows]
+                if want_a:
+                    chain_a = _GemmChain(rows, d, dA[r0:r0 + rows], sA[r0:r0 + rows], n_bp)
+                    for bi, Bp in enumerate(b_pieces):
+                        if rd_global and bi == n_bp - 1:   # last piece: the accumulated (unscaled) value
+                            part_buf = torch.empty(K.gemm_rowdot_scratch_floats(rows, d), dtype=torch.float32, device=dev)
+                            chain_a.add(Wp, False, Bp, True, N, dot_mat=ops.a_head(A_rows), rowdot_part=part_buf)
+                            t = torch.empty(1, dtype=torch.float32, device=dev)
+                            # rows >= `rows` of a slab are never written: sum only the valid part
+                            K.sum_f32(_valid_rowdot(part_buf, rows, d), t)
+                            ds_terms.append(("unit", t))
+                        else:
+                            chain_a.add(Wp, False, Bp, True, N)
+                if want_b:
+                    for Ap in ops.a_pieces(A_rows):
+                        chain_b.add(Wp, True, Ap, True, rows)
+            if want_b and exchange_b:
+                dBp = _reduce_scatter_rows(dBp, rank, W, group)
+            if local and need_s:
+                # local loss: d value_r / d scale = (sum_i <a_i, dA^P_i> + sum_j <b_j, dB^Q_j>) / scale
+                if part == 1 and dA is not None:
+                    ds_terms.append(("scaled", _rowdot_sum(ops.a_head(ops.A), dA)))
+                if part == 2 and dBp is not None:
+                    ds_terms.append(("scaled", _rowdot_sum(ops.B[:, 0:d], dBp)))
+            if local and not gwg:
+                dA_total = dA if part == 1 else dA_total
+                dB_total = dBp if part == 2 else dB_total
+            else:
+                dA_total = dA if dA_total is None else (dA_total + dA if dA is not None else dA_total)
+                dB_total = dBp if dB_total is None else (dB_total + dBp if dBp is not None else dB_total)
+
+        grad_a = _finish_grad(dA_total, ops, need_a)
+        grad_b = _finish_grad(dB_total, ops, need_b)
+        grad_s = None
+        if need_s:
+            tot = torch.zeros(1, dtype=torch.float32, device=dev)
+            for kind, t in ds_terms:
+                tot = tot + t
+            if not local:
+                # unit-gradient partial of this rank's rows -> all ranks' rows, times this rank's upstream g
+                if W > 1:
+                    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+                tot = tot * g32
+            grad_s = tot / ctx.scale_dev
+            sdt, sdev, sshape = ctx.scale_meta
+            grad_s = grad_s.reshape(sshape).to(device=sdev, dtype=sdt)
+        return grad_a, grad_b, grad_s, None
+
+
+def _valid_rowdot(part_buf, rows, d):
+    """The written entries of the rowdot partial buffer: [slabs, ldd] -> [:, :rows]."""
+    ldd = (rows + 127) // 128 * 128
+    slabs = part_buf.numel() // ldd
+    return part_buf.view(slabs, ldd)[:, :rows].contiguous()
+
+
+def _rowdot_sum(X, G):
+    """sum_i <x_i, g_i> with the rowdot + sum kernels (G in bf16 or fp32 -> bf16 view for the dot)."""
+    K = _KERNELS
+    Gb = G if G.dtype == torch.bfloat16 else G.to(torch.bfloat16)
+    rows, d = Gb.shape
+    tmp = torch.empty(rows, dtype=torch.float32, device=G.device)
+    K.rowdot_bf16(X[:, :d] if X.shape[1] != d else X, Gb, tmp)
+    t = torch.empty(1, dtype=torch.float32, device=G.device)
+    K.sum_f32(tmp, t)
+    return t
+
+
+def _finish_grad(g, ops, needed):
+    if not needed or g is None:
+        return None
+    if ops.pad:
+        g = g[:, :ops.d_in]
+    return g.to(ops.in_dtype) if g.dtype != ops.in_dtype else g
+
+
+# ---------------------------------------------------------------------------------------------
+# the module
+# ---------------------------------------------------------------------------------------------
+class ClipLoss(nn.Module):
+    """B200-native drop-in for the reference ``ClipLoss`` (loss.py:49-114).
+
+    Extra keyword-only arguments (all optional, defaults keep reference behaviour):
+      loss_dtype   dtype of the returned scalar; default = input dtype like the reference
+                   (bf16 in -> bf16 out).  The fp32 value is always kept in ``last_loss_fp32``.
+      panel_bytes  bound of the bf16 dL/dZ panel workspace used by the backward.
+      group        process group for the collectives (default: the world group).
+    """
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
+                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None):
+        super().__init__()
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self.loss_dtype = loss_dtype
+        self.panel_bytes = int(panel_bytes)
+        self.group = group
+        # cache state (same attributes as the reference, loss.py:68-70)
+        self.prev_num_logits = 0
+        self.labels = {}
+        # diagnostics of the last call (device tensors, no host sync)
+        self.last_loss_fp32 = None
+        self.last_hazard_flag = None
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        """Labels of the reference (loss.py:72-83).  The fused kernels use the diagonal implicitly;
+        this stays for API parity."""
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = torch.arange(num_logits, device=device, dtype=torch.long)
+            if self.world_size > 1 and self.local_loss:
+                labels = labels + num_logits * self.rank
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def get_logits(self, modality_features, sequence_features, logit_scale):
+        """Materialised logits as in loss.py:85-101 - DEBUG ONLY (the loss path never forms
+        them).  Contraction on the tcgen05 GEMM kernel, fp32 accumulators, scale applied in fp32."""
+        K = _KERNELS
+        A, B = modality_features, sequence_features
+        if self.world_size > 1:
+            A_all, B_all = gather_features(A, B, self.local_loss, self.gather_with_grad, self.rank, self.world_size,
+                                           self.use_horovod)
+        else:
+            A_all, B_all = A, B
+
+        def mm(x, y):
+            xo, _, _ = _prep_side(x, 0)
+            yo, _, _ = _prep_side(y, 1)
+            M, Nc, Kd = xo.shape[0], yo.shape[0], xo.shape[1]
+            ld = (Nc + 7) // 8 * 8
+            out = torch.empty(M, ld, dtype=torch.float32, device=x.device)[:, :Nc]
+            K.gemm_bf16(xo, False, yo, False, M, Nc, Kd, acc_out=out)
+            sc = logit_scale.to(device=x.device, dtype=torch.float32) if torch.is_tensor(logit_scale) else float(logit_scale)
+            return (out * sc).to(x.dtype)
+
+        with torch.no_grad():
+            if self.world_size > 1 and self.local_loss:
+                return mm(A, B_all), mm(B, A_all)
+            z = mm(A_all, B_all)
+            return z, z.T
+
+    def forward(self, modality_features, sequence_features, logit_scale=1.0, output_dict=False):
+        A, B = modality_features, sequence_features
+        if A.dim() != 2 or B.dim() != 2 or A.shape != B.shape:
+            raise ValueError(f"ClipLoss expects two (n, d) tensors of equal shape, got {tuple(A.shape)} and {tuple(B.shape)}")
+        if A.dtype != B.dtype or A.device != B.device:
+            raise ValueError("ClipLoss expects both feature tensors on one device with one dtype")
+        if A.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+            raise ValueError(f"unsupported feature dtype {A.dtype}")
+        if self.world_size > 1:
+            assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+            if not dist.is_initialized():
+                raise RuntimeError("ClipLoss(world_size > 1) needs an initialised torch.distributed process group")
+            if dist.get_world_size(self.group) != self.world_size:
+                raise RuntimeError("ClipLoss world_size does not match the process group")
+        if torch.is_tensor(logit_scale):
+            if logit_scale.numel() != 1:
+                raise ValueError("logit_scale must be a scalar")
+            scale_t = logit_scale
+        else:
+            scale_t = _float_scale_on(A.device, logit_scale)   # cached: no host-to-device copy per call
+        cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
+                   gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
+                   panel_bytes=self.panel_bytes)
+        total_loss, loss32, flag = _ClipLossFunction.apply(A, B, scale_t, cfg)
+        self.last_loss_fp32, self.last_hazard_flag = loss32, flag
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+    def check_last_call(self):
+        """Host-side check (synchronises) that the last forward stayed inside the validated fp32
+        window of the single-reference exp-sum ('numerical window')."""
+        if self.last_hazard_flag is not None and int(self.last_hazard_flag.item()) != 0:
+            raise FloatingPointError(
+                "ClipLoss: logits left the validated exp2 window (|logit_scale| * max|a| * max|b| is huge and the "
+                "row/column maxima are more than ~100 log2 units apart); normalise the features or lower logit_scale")

@@ -371,6 +371,8 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // Generic GEMM: C[M x Nc] = op(A) op(B), tile 128 x 256, full K per tile.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]);
+
 struct GParams {
   int M, Nc, nK;
   int nMb, nNb;
@@ -378,6 +380,10 @@ struct GParams {
   float* acc_out;
   __nv_bfloat16* out;
   int ldc;
+  const float* row_scale;        // optional: value *= row_scale[m] (applied after acc_in is added)
+  const __nv_bfloat16* dot_mat;  // optional: rowdot_part[(nb*2+h)*ldd + m] = <unscaled value row, dot_mat row>
+  float* rowdot_part;
+  int ld_dot, ldd;
 };
 
 template <int A_MN, int B_MN>
@@ -439,6 +445,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       const int mb = t / p.nNb, nb = t % p.nNb;
       const int m = mb * BM + q * 32 + lane;
       const int n0 = nb * BN + h * 128;
+      const float rs = (p.row_scale && m < p.M) ? __ldg(p.row_scale + m) : 1.f;
+      float rdot = 0.f;
       mbar_wait(&s.tail->tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
@@ -467,6 +475,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
                 x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
               }
+              if (p.dot_mat) {
+                float fd[8];
+                bf16x8_to_float(*reinterpret_cast<const uint4*>(p.dot_mat + static_cast<size_t>(m) * p.ld_dot + n), fd);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) rdot = fmaf(x[u], fd[u], rdot);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) x[u] *= rs;
               if (p.acc_out) {
                 *reinterpret_cast<float4*>(p.acc_out + base + v8 * 8) = make_float4(x[0], x[1], x[2], x[3]);
                 *reinterpret_cast<float4*>(p.acc_out + base + v8 * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
@@ -480,6 +496,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           }
         }
       }
+      if (p.rowdot_part && m < p.M) p.rowdot_part[static_cast<size_t>(nb * 2 + h) * p.ldd + m] = rdot;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -595,7 +612,8 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
 __global__ void bwd_weights_kernel(const float* __restrict__ inv_rs, const float* __restrict__ inv_cs, int N, int n,
                                    int row_offset, int mode, int use_gsum, int part, int world, int rank,
                                    const float* __restrict__ gvec, const float* __restrict__ scale,
-                                   float* __restrict__ wr, float* __restrict__ wc, float* __restrict__ dg) {
+                                   float* __restrict__ wr, float* __restrict__ wc, float* __restrict__ dg,
+                                   float* __restrict__ out_scale_a, float* __restrict__ out_scale_b) {
   const float s = *scale;
   float gsum = 0.f;
   for (int r = 0; r < world; ++r) gsum += gvec[r];
@@ -603,26 +621,66 @@ __global__ void bwd_weights_kernel(const float* __restrict__ inv_rs, const float
   const float fr = (part == 2) ? 0.f : 1.f;   // row-softmax half enabled
   const float fc = (part == 1) ? 0.f : 1.f;   // column-softmax half enabled
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npr = N / world;                  // rows per rank
   if (mode == ONEPROT_MODE_GLOBAL) {
-    const float coef = s * (use_gsum ? gsum : g_own) / (2.f * N);
+    // unit-gradient panel; the upstream gradients are applied to the GEMM outputs:
+    //   dA_r *= (use_gsum ? sum_r g_r : g_own),  dB_partial[j] *= (use_gsum ? sum_r g_r : g_owner(j))
+    const float coef = s / (2.f * N);
     if (k < n) {
       wr[k] = fr * coef * inv_rs[row_offset + k];
       dg[k] = (fr + fc) * coef;
+      out_scale_a[k] = use_gsum ? gsum : g_own;
     }
-    if (k < N) wc[k] = fc * coef * inv_cs[k];
+    if (k < N) {
+      wc[k] = fc * coef * inv_cs[k];
+      out_scale_b[k] = use_gsum ? gsum : gvec[k / npr];
+    }
   } else {
-    const int npr = N / world;   // rows per rank
+    // local loss: row i of rank r carries g_r (row softmax), column j carries g_owner(j)
     if (k < n) {
       const float coef = s * g_own / (2.f * n);
       wr[k] = fr * coef * inv_rs[row_offset + k];
       dg[k] = (fr + fc) * coef;
+      out_scale_a[k] = 1.f;
     }
     if (k < N) {
-      const int owner = k / npr;
-      // without gather_with_grad only this rank's own columns carry gradient
-      const float g = use_gsum ? gvec[owner] : (owner == rank ? g_own : 0.f);
-      wc[k] = fc * s * g / (2.f * n) * inv_cs[k];
+      wc[k] = fc * s * gvec[k / npr] / (2.f * n) * inv_cs[k];
+      out_scale_b[k] = 1.f;
     }
+  }
+}
+
+// rowdot[i] = <x_i, y_i> for bf16 matrices (one warp per row)
+__global__ void rowdot_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ y, int ldy,
+                              int rows, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    float acc = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fy[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + k), fx);
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(y + static_cast<size_t>(row) * ldy + k), fy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(fx[u], fy[u], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
+// out[0] = sum_k v[k] (single block, fixed order => deterministic)
+__global__ void sum_kernel(const float* __restrict__ v, int count, float* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < count; k += blockDim.x) acc += v[k];
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    out[0] = static_cast<float>(t);
   }
 }
 
@@ -710,6 +768,42 @@ __global__ void l2norm_bwd_kernel(const void* __restrict__ x, const void* __rest
       for (int u = 0; u < 8; ++u) o[u] = sc * inv * (fg[u] - fx[u] * inv * proj);
       store8<FP32>(gx, base + k, o);
     }
+  }
+}
+
+// y = scale * x, flat over rows*d elements (8 per thread per step)
+template <bool FP32>
+__global__ void scale_kernel(const void* __restrict__ x, void* __restrict__ y, size_t total8,
+                             const float* __restrict__ scale) {
+  const float sc = *scale;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8<FP32>(x, i * 8, f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] *= sc;
+    store8<FP32>(y, i * 8, f);
+  }
+}
+
+// out[row] = <x_row, y_row>, contiguous rows of d elements
+template <bool FP32>
+__global__ void rowdot_dense_kernel(const void* __restrict__ x, const void* __restrict__ y, int rows, int d,
+                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    float acc = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fy[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(y, base + k, fy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(fx[u], fy[u], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
   }
 }
 
@@ -913,12 +1007,15 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
 
 int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, int N, int n, int row_offset, int mode,
                              int use_gsum, int part, int world, int rank, const float* gvec_dev,
-                             const float* scale_dev, float* wr, float* wc, float* dg, void* stream) {
-  if (!inv_rowsum || !inv_colsum || !gvec_dev || !scale_dev || !wr || !wc || !dg) return fail(ONEPROT_ERR_ARG, "bwd_weights: null pointer");
+                             const float* scale_dev, float* wr, float* wc, float* dg, float* out_scale_a,
+                             float* out_scale_b, void* stream) {
+  if (!inv_rowsum || !inv_colsum || !gvec_dev || !scale_dev || !wr || !wc || !dg || !out_scale_a || !out_scale_b)
+    return fail(ONEPROT_ERR_ARG, "bwd_weights: null pointer");
   if (world <= 0 || rank < 0 || rank >= world || N % world || n <= 0 || row_offset + n > N)
     return fail(ONEPROT_ERR_ARG, "bwd_weights: bad sizes");
   op::bwd_weights_kernel<<<cdiv(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      inv_rowsum, inv_colsum, N, n, row_offset, mode, use_gsum, part, world, rank, gvec_dev, scale_dev, wr, wc, dg);
+      inv_rowsum, inv_colsum, N, n, row_offset, mode, use_gsum, part, world, rank, gvec_dev, scale_dev, wr, wc, dg,
+      out_scale_a, out_scale_b);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -950,13 +1047,29 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
 
 int oneprot_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
                       const float* acc_in, float* acc_out, void* out_bf16, int ldc, void* stream) {
+  return oneprot_gemm_bf16_ex(A, lda, a_mn, B, ldb, b_mn, M, Nc, K, acc_in, acc_out, out_bf16, ldc, nullptr, nullptr, 0,
+                              nullptr, stream);
+}
+
+size_t oneprot_gemm_rowdot_scratch_bytes(int M, int Nc) {
+  return sizeof(float) * 2 * static_cast<size_t>(cdiv(Nc, op::BN)) * static_cast<size_t>(cdiv(M, op::BM) * op::BM);
+}
+
+int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
+                         const float* acc_in, float* acc_out, void* out_bf16, int ldc, const float* row_scale,
+                         const void* dot_mat, int ld_dot, float* rowdot_part, void* stream) {
   if (!A || !B || (!acc_out && !out_bf16)) return fail(ONEPROT_ERR_ARG, "gemm: null pointer");
+  if ((dot_mat != nullptr) != (rowdot_part != nullptr) || (dot_mat && (ld_dot < Nc || ld_dot % 8)))
+    return fail(ONEPROT_ERR_ARG, "gemm: dot_mat and rowdot_part go together, ld_dot >= Nc and a multiple of 8");
   if (M <= 0 || Nc <= 0 || K <= 0 || Nc % 8 || ldc % 8 || ldc < Nc) return fail(ONEPROT_ERR_ARG, "gemm: need Nc, ldc multiples of 8, ldc >= Nc");
   if (lda < (a_mn ? M : K) || ldb < (b_mn ? Nc : K)) return fail(ONEPROT_ERR_ARG, "gemm: leading dimension too small");
   op::GParams p{};
   p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
   p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
   p.acc_in = acc_in; p.acc_out = acc_out; p.out = static_cast<__nv_bfloat16*>(out_bf16); p.ldc = ldc;
+  p.row_scale = row_scale;
+  p.dot_mat = static_cast<const __nv_bfloat16*>(dot_mat); p.ld_dot = ld_dot;
+  p.rowdot_part = rowdot_part; p.ldd = p.nMb * op::BM;
   CUtensorMap mapA, mapB;
   int rc;
   if (a_mn) rc = make_map(&mapA, A, M, K, lda, 64); else rc = make_map(&mapA, A, K, M, lda, op::BM);
@@ -975,6 +1088,24 @@ int oneprot_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, 
   else if (a_mn && !b_mn) LAUNCH_GEMM(1, 0);
   else LAUNCH_GEMM(1, 1);
 #undef LAUNCH_GEMM
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_rowdot_bf16(const void* x, int ldx, const void* y, int ldy, int rows, int d, float* out, void* stream) {
+  if (!x || !y || !out || rows <= 0 || d <= 0 || d % 8 || ldx % 8 || ldy % 8) return fail(ONEPROT_ERR_ARG, "rowdot: bad argument");
+  const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
+  op::rowdot_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(y), ldy, rows, d, out);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_sum_f32(const float* v, int count, float* out, void* stream) {
+  if (!v || !out || count <= 0) return fail(ONEPROT_ERR_ARG, "sum: bad argument");
+  op::sum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(v, count, out);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -999,6 +1130,29 @@ int oneprot_l2norm_scale_bwd(const void* x, const void* gy, const float* inv_nor
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_fp32) op::l2norm_bwd_kernel<true><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
   else op::l2norm_bwd_kernel<false><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_scale_rows(const void* x, void* y, int rows, int d, int is_fp32, const float* scale_dev, void* stream) {
+  if (!x || !y || !scale_dev || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "scale_rows: need d a positive multiple of 8");
+  const size_t total8 = static_cast<size_t>(rows) * d / 8;
+  const int blocks = static_cast<int>(std::min<size_t>((total8 + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) op::scale_kernel<true><<<blocks, 256, 0, st>>>(x, y, total8, scale_dev);
+  else op::scale_kernel<false><<<blocks, 256, 0, st>>>(x, y, total8, scale_dev);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_rowdot(const void* x, const void* y, int rows, int d, int is_fp32, float* out, void* stream) {
+  if (!x || !y || !out || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "rowdot: need d a positive multiple of 8");
+  const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) op::rowdot_dense_kernel<true><<<blocks, 256, 0, st>>>(x, y, rows, d, out);
+  else op::rowdot_dense_kernel<false><<<blocks, 256, 0, st>>>(x, y, rows, d, out);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

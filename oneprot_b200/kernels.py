@@ -80,12 +80,13 @@ def loss_finalize(rowsum_all, colsum_all, diag_all, n: int, row_offset: int, mod
 
 
 def bwd_weights(inv_rowsum, inv_colsum, n: int, row_offset: int, mode: int, use_gsum: bool, part: int, world: int,
-                rank: int, gvec, scale_dev, wr, wc, dg):
-    _need_cuda(inv_rowsum, inv_colsum, gvec, scale_dev, wr, wc, dg)
+                rank: int, gvec, scale_dev, wr, wc, dg, out_scale_a, out_scale_b):
+    _need_cuda(inv_rowsum, inv_colsum, gvec, scale_dev, wr, wc, dg, out_scale_a, out_scale_b)
     N = inv_rowsum.numel()
     check(_lib.load().oneprot_clip_bwd_weights(ptr(inv_rowsum), ptr(inv_colsum), N, n, row_offset, mode,
                                                int(use_gsum), part, world, rank, ptr(gvec), ptr(scale_dev), ptr(wr),
-                                               ptr(wc), ptr(dg), _stream()), "oneprot_clip_bwd_weights")
+                                               ptr(wc), ptr(dg), ptr(out_scale_a), ptr(out_scale_b), _stream()),
+          "oneprot_clip_bwd_weights")
 
 
 def dz_panel(A_rows, B_all, grow0: int, scale_dev, stats, wr, wc, dg, Wz):
@@ -101,9 +102,14 @@ def dz_panel(A_rows, B_all, grow0: int, scale_dev, stats, wr, wc, dg, Wz):
           "oneprot_clip_dz_panel")
 
 
-def gemm_bf16(A, a_mn: bool, B, b_mn: bool, M: int, Nc: int, K: int, *, acc_in=None, acc_out=None, out=None):
-    """C[M x Nc] = op(A) op(B); see oneprot_gemm_bf16 in include/oneprot_clip.h."""
-    _need_cuda(A, B, acc_in, acc_out, out)
+def gemm_rowdot_scratch_floats(M: int, Nc: int) -> int:
+    return int(_lib.load().oneprot_gemm_rowdot_scratch_bytes(M, Nc)) // 4
+
+
+def gemm_bf16(A, a_mn: bool, B, b_mn: bool, M: int, Nc: int, K: int, *, acc_in=None, acc_out=None, out=None,
+              row_scale=None, dot_mat=None, rowdot_part=None):
+    """C[M x Nc] = op(A) op(B); see oneprot_gemm_bf16(_ex) in include/oneprot_clip.h."""
+    _need_cuda(A, B, acc_in, acc_out, out, row_scale, dot_mat, rowdot_part)
     if A.dtype != torch.bfloat16 or B.dtype != torch.bfloat16:
         raise ValueError("gemm_bf16 needs bf16 operands")
     if A.stride(1) != 1 or B.stride(1) != 1:
@@ -113,8 +119,26 @@ def gemm_bf16(A, a_mn: bool, B, b_mn: bool, M: int, Nc: int, K: int, *, acc_in=N
     for t in (acc_in, acc_out, out):
         if t is not None and (t.stride(0) != ldc or t.stride(1) != 1):
             raise ValueError("gemm_bf16 outputs must share one row-major leading dimension")
-    check(_lib.load().oneprot_gemm_bf16(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), M, Nc, K,
-                                        ptr(acc_in), ptr(acc_out), ptr(out), ldc, _stream()), "oneprot_gemm_bf16")
+    ld_dot = 0
+    if dot_mat is not None:
+        if dot_mat.dtype != torch.bfloat16 or dot_mat.stride(1) != 1:
+            raise ValueError("dot_mat must be row-major bf16")
+        ld_dot = dot_mat.stride(0)
+    check(_lib.load().oneprot_gemm_bf16_ex(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), M, Nc, K,
+                                           ptr(acc_in), ptr(acc_out), ptr(out), ldc, ptr(row_scale), ptr(dot_mat),
+                                           ld_dot, ptr(rowdot_part), _stream()), "oneprot_gemm_bf16_ex")
+
+
+def rowdot_bf16(x, y, out):
+    _need_cuda(x, y, out)
+    rows, d = x.shape
+    check(_lib.load().oneprot_rowdot_bf16(ptr(x), x.stride(0), ptr(y), y.stride(0), rows, d, ptr(out), _stream()),
+          "oneprot_rowdot_bf16")
+
+
+def sum_f32(v, out):
+    _need_cuda(v, out)
+    check(_lib.load().oneprot_sum_f32(ptr(v), v.numel(), ptr(out), _stream()), "oneprot_sum_f32")
 
 
 def l2norm_scale_fwd(x, y, inv_norm, scale_dev=None, eps: float = 1e-12):
@@ -137,3 +161,17 @@ def split_fp32(x, out, side: int, terms: int):
     _need_cuda(x, out)
     rows, d = x.shape
     check(_lib.load().oneprot_split_fp32(ptr(x), ptr(out), rows, d, side, terms, _stream()), "oneprot_split_fp32")
+
+
+def scale_rows(x, y, scale_dev):
+    _need_cuda(x, y, scale_dev)
+    rows, d = x.shape
+    check(_lib.load().oneprot_scale_rows(ptr(x), ptr(y), rows, d, int(x.dtype == torch.float32), ptr(scale_dev),
+                                         _stream()), "oneprot_scale_rows")
+
+
+def rowdot(x, y, out):
+    _need_cuda(x, y, out)
+    rows, d = x.shape
+    check(_lib.load().oneprot_rowdot(ptr(x), ptr(y), rows, d, int(x.dtype == torch.float32), ptr(out), _stream()),
+          "oneprot_rowdot")

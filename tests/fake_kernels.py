@@ -1,0 +1,158 @@
+"""CPU emulation of oneprot_b200.kernels for HOST-LOGIC tests only (gloo, world_size 2).
+
+Test infrastructure: lives under tests/, is injected by monkeypatching
+``oneprot_b200.clip_loss._KERNELS`` and is never importable from the product package.  Each
+function restates the contract of the C entry point of the same name (include/oneprot_clip.h) in
+plain torch float64 so that the sharding / collective / gradient-convention logic of
+``ClipLoss`` can be exercised without a GPU.
+"""
+import math
+
+import torch
+
+MODE_GLOBAL = 0
+MODE_LOCAL = 1
+LOG2E = 1.4426950408889634
+CALLS = []
+
+
+def launch_count():
+    return len(CALLS)
+
+
+def launch_count_reset():
+    CALLS.clear()
+
+
+def _G(scale_dev, stats):
+    c = float(scale_dev[0]) * LOG2E
+    U = abs(c) * math.sqrt(float(stats[0]) * float(stats[1]))
+    return c, max(0.0, U - 100.0)
+
+
+def rowstats(A, B_all, row_offset, diag, stats):
+    CALLS.append("rowstats")
+    n = A.shape[0]
+    a, b = A.double(), B_all.double()
+    diag.copy_((a * b[row_offset:row_offset + n]).sum(-1).float())
+    stats[0] = max(float(stats[0]), float((a * a).sum(-1).max()))
+    stats[1] = max(float(stats[1]), float((b * b).sum(-1).max()))
+
+
+def fwd_scratch_bytes(n, N):
+    return 16
+
+
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None):
+    CALLS.append("fwd_sums")
+    c, G = _G(scale_dev, stats)
+    E = torch.exp2(c * (A.double() @ B_all.double().T) - G)
+    rowsum.copy_(E.sum(1).float())
+    colsum.copy_(E.sum(0).float())
+    return scratch
+
+
+def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum,
+                  inv_colsum, flag):
+    CALLS.append("loss_finalize")
+    c, G = _G(scale_dev, stats)
+    s = float(scale_dev[0])
+    N = rowsum_all.numel()
+    lo, hi = (row_offset, row_offset + n) if mode == MODE_LOCAL else (0, N)
+    rl = (G + torch.log2(rowsum_all.double())) / LOG2E
+    cl = (G + torch.log2(colsum_all.double())) / LOG2E
+    zd = s * diag_all.double()
+    loss_out[0] = float(((rl - zd)[lo:hi].sum() + (cl - zd)[lo:hi].sum()) / (2 * (hi - lo)))
+    inv_rowsum.copy_((1.0 / rowsum_all.double()).float())
+    inv_colsum.copy_((1.0 / colsum_all.double()).float())
+    bad = (~torch.isfinite(rowsum_all)).any() or (~torch.isfinite(colsum_all)).any() \
+        or (rowsum_all < 1e-24).any() or (colsum_all < 1e-24).any()
+    if bool(bad):
+        flag[0] = int(flag[0]) | 1
+
+
+def bwd_weights(inv_rowsum, inv_colsum, n, row_offset, mode, use_gsum, part, world, rank, gvec, scale_dev, wr, wc, dg,
+                out_scale_a, out_scale_b):
+    CALLS.append("bwd_weights")
+    N = inv_rowsum.numel()
+    s = float(scale_dev[0])
+    g = gvec.double()
+    gsum, g_own = float(g.sum()), float(g[rank])
+    fr = 0.0 if part == 2 else 1.0
+    fc = 0.0 if part == 1 else 1.0
+    npr = N // world
+    owner = torch.arange(N) // npr
+    if mode == MODE_GLOBAL:
+        coef = s / (2.0 * N)
+        wr.copy_((fr * coef * inv_rowsum[row_offset:row_offset + n].double()).float())
+        dg.fill_((fr + fc) * coef)
+        out_scale_a.fill_(gsum if use_gsum else g_own)
+        wc.copy_((fc * coef * inv_colsum.double()).float())
+        out_scale_b.copy_((torch.full((N,), gsum, dtype=torch.float64) if use_gsum else g[owner]).float())
+    else:
+        coef = s * g_own / (2.0 * n)
+        wr.copy_((fr * coef * inv_rowsum[row_offset:row_offset + n].double()).float())
+        dg.fill_((fr + fc) * coef)
+        out_scale_a.fill_(1.0)
+        wc.copy_((fc * s * g[owner] / (2.0 * n) * inv_colsum.double()).float())
+        out_scale_b.fill_(1.0)
+
+
+def dz_panel(A_rows, B_all, grow0, scale_dev, stats, wr, wc, dg, Wz):
+    CALLS.append("dz_panel")
+    c, G = _G(scale_dev, stats)
+    rows, N = A_rows.shape[0], B_all.shape[0]
+    E = torch.exp2(c * (A_rows.double() @ B_all.double().T) - G)
+    Wd = E * (wr.double()[:, None] + wc.double()[None, :])
+    idx = torch.arange(rows)
+    Wd[idx, grow0 + idx] -= dg.double()
+    Wz[:rows, :N] = Wd.to(torch.bfloat16)
+
+
+def gemm_rowdot_scratch_floats(M, Nc):
+    return 2 * ((Nc + 255) // 256) * ((M + 127) // 128 * 128)
+
+
+def gemm_bf16(A, a_mn, B, b_mn, M, Nc, K, *, acc_in=None, acc_out=None, out=None, row_scale=None, dot_mat=None,
+              rowdot_part=None):
+    CALLS.append("gemm")
+    opA = (A.double().T if a_mn else A.double())[:M, :K]
+    opB = (B.double() if b_mn else B.double().T)[:K, :Nc]
+    val = opA @ opB
+    if acc_in is not None:
+        val = val + acc_in.double()
+    if rowdot_part is not None:
+        ldd = (M + 127) // 128 * 128
+        rp = rowdot_part.view(-1, ldd)
+        rp.zero_()
+        rp[0, :M] = (val * dot_mat.double()[:M, :Nc]).sum(-1).float()
+    if row_scale is not None:
+        val = val * row_scale.double()[:M, None]
+    if acc_out is not None:
+        acc_out.copy_(val.float())
+    if out is not None:
+        out.copy_(val.to(out.dtype))
+
+
+def rowdot_bf16(x, y, out):
+    CALLS.append("rowdot")
+    out.copy_((x.double() * y.double()).sum(-1).float())
+
+
+def sum_f32(v, out):
+    CALLS.append("sum")
+    out[0] = float(v.double().sum())
+
+
+def split_fp32(x, out, side, terms):
+    CALLS.append("split")
+    h = x.to(torch.bfloat16)
+    r1 = x - h.float()
+    m = r1.to(torch.bfloat16)
+    r2 = r1 - m.float()
+    l = r2.to(torch.bfloat16)
+    L = [h, h, m, h, m, l]
+    R = [h, m, h, l, m, h]
+    d = x.shape[1]
+    for t in range(terms):
+        out[:, t * d:(t + 1) * d] = (R if side else L)[t]

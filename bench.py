@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the ClipLoss hot path (fwd+bwd) on B200 - see DESIGN.md 'Measurement'.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line on rank 0.  Workload = BASELINE.json's metric: global batch 32768 x 1024,
+bf16, synthetic unit-norm anchors with the temperature folded into the second operand
+(SURVEY.md C3), ClipLoss(local_loss=False, gather_with_grad=True); at N GPUs each rank holds
+32768 / N rows (strong scaling, as the metric is quoted).
+
+ value      samples/s with inputs resident in HBM (CUDA events, per-step, L2 flushed between steps)
+ e2e        same metric through the public ClipLoss API with pinned HOST inputs: H2D copies of both
+            embeddings and a D2H read of the loss inside the timed region
+ roofline   the dominant tensor-core kernel, timed alone with CUDA events, against
+            MEASURED_PEAKS.json; plus the whole-step algorithmic rate (6 N^2 d / t)
+ cpu_baseline  the oracle's torch-CPU port of the reference ClipLoss on the host cores (N=1 only)
+ --impl reference   times that CPU port only (rank 0), same metric / config / unit
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GLOBAL_N = int(os.environ.get("ONEPROT_BENCH_N", 32768))
+DIM = int(os.environ.get("ONEPROT_BENCH_D", 1024))
+METRIC = "cliploss_fwd_bwd_samples_per_s"
+UNIT = "samples/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_tflops=float(p["bf16_tflops"]), bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", 0)),
+                    hbm_gbs=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi while the timed region runs)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Polls NVML (SM clock, power, clock-event reasons) every few ms while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
+        self.gpu, self.period, self.samples, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:   # pragma: no cover
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception as e:   # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(self.period)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        reasons = set()
+        for _, _, rs in self.samples:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        pmax = max(p for _, p, _ in self.samples)
+        load = [s for s, p, _ in self.samples if p >= 0.6 * pmax] or [s for s, _, _ in self.samples]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": float(self.max_sm), "power_w_max": pmax,
+                "samples": len(self.samples), "samples_under_load": len(load), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference ClipLoss; bounded row-panel sample)
+# ----------------------------------------------------------------------------------------------
+def cpu_panel_step(A, B, m):
+    """fwd+bwd of the reference's W=1 ClipLoss restricted to the first m rows of BOTH logit
+    matrices (loss.py:98-99,109-112).  Cost is m/N of the full step, so full-step throughput =
+    m / t (the N x N work is row-separable; the port's ops and threading are unchanged)."""
+    import torch
+    import torch.nn.functional as F
+    A = A.detach().requires_grad_(True)
+    B = B.detach().requires_grad_(True)
+    z_ab = (1.0 * A[:m]) @ B.T
+    z_ba = (1.0 * B[:m]) @ A.T
+    t = torch.arange(m)
+    loss = (F.cross_entropy(z_ab, t) + F.cross_entropy(z_ba, t)) / 2
+    loss.backward()
+    return float(loss.detach())
+
+
+def cpu_reference(steps, warmup, budget_s_per_step):
+    import torch
+    from oracle import clip_oracle as oc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a, b = oc.synthetic_pair(GLOBAL_N, DIM, seed=1234, dtype="fp32")
+    # probe to size the panel
+    t0 = time.perf_counter(); cpu_panel_step(a, b, 128); cpu_panel_step(a, b, 128)
+    t_probe = (time.perf_counter() - t0) / 2
+    m = 128
+    while m * 2 <= GLOBAL_N and t_probe * (m * 2 / 128) <= budget_s_per_step:
+        m *= 2
+    for _ in range(warmup):
+        cpu_panel_step(a, b, m)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); cpu_panel_step(a, b, m); times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip(); break
+    except OSError:
+        pass
+    return dict(value=m / t, unit=UNIT, cores=cores, kind="port",
+                sample=(f"oracle torch-CPU port of reference ClipLoss (fp32, {cores} threads, {model}): rows [0,{m}) of both "
+                        f"{GLOBAL_N}x{GLOBAL_N} logit matrices per step ({m}/{GLOBAL_N} of a full fwd+bwd), mean of {steps} "
+                        f"steps = {t:.3f} s; full-step throughput = {m}/t"),
+                ms_per_step_full_equiv=1e3 * t * GLOBAL_N / m)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 3))
+    budget = max(0.25, min(2.0, 120.0 / (steps + warmup)))   # whole run within a few minutes
+    cb = cpu_reference(steps, warmup, budget)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step_full_equiv"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"ClipLoss fwd+bwd, global batch {GLOBAL_N} x {DIM}, reference CPU path (W=1)",
+                       "global_batch": GLOBAL_N, "dim": DIM},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oneprot_b200 import ClipLoss, kernels
+    from oracle import clip_oracle as oc   # synthetic generator + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = GLOBAL_N // world
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    a, b = oc.synthetic_pair(n, DIM, seed=1234, pair_id=0, rank=rank, correlated=True, temperature_into_b=True,
+                             dtype="bf16")
+    a_pin, b_pin = a.pin_memory(), b.pin_memory()
+    A = a.to(dev).requires_grad_(True)
+    B = b.to(dev).requires_grad_(True)
+    loss_mod = ClipLoss(local_loss=False, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 2x the 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        A.grad = None; B.grad = None
+        loss = loss_mod(A, B)
+        loss.backward()
+        return loss
+
+    def step_e2e(host_loss):
+        Ad = a_pin.to(dev, non_blocking=True).requires_grad_(True)
+        Bd = b_pin.to(dev, non_blocking=True).requires_grad_(True)
+        loss = loss_mod(Ad, Bd)
+        loss.backward()
+        host_loss.copy_(loss.detach().float(), non_blocking=True)
+        return Ad.grad
+
+    def timed(fn, k):
+        """k steps, each bracketed by its own event pair; the L2 flush sits between the pairs."""
+        evs = []
+        for _ in range(k):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [e0.elapsed_time(e1) for e0, e1 in evs]
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernels.launch_count_reset()
+    barrier()
+    ms = timed(step_device, steps)
+    barrier()
+    launches = kernels.launch_count()
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = float(total_ms.item()) / steps
+    loss_val = float(loss_mod.last_loss_fp32.item())
+    loss_mod.check_last_call()
+
+    # ---- e2e: pinned host inputs -> H2D -> fwd+bwd -> D2H loss
+    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        step_e2e(host_loss)
+    barrier()
+    ms_e2e = timed(lambda: step_e2e(host_loss), max(3, steps // 2))
+    barrier()
+    e2e_ms = torch.tensor([sum(ms_e2e) / len(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+
+    # ---- roofline: the four tensor-core kernels timed alone (rank-local panel), CUDA events
+    roof = kernel_roofline(torch, kernels, A.detach(), B.detach(), n, GLOBAL_N, world, rank, dev, flush) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        peaks = _peaks()
+        flops = 6.0 * GLOBAL_N * GLOBAL_N * DIM
+        step_tflops = flops / world / (ms_per_step * 1e-3) / 1e12        # per GPU, algorithmic
+        dom = max(roof["kernels"], key=lambda k: roof["kernels"][k]["ms"])
+        dk = roof["kernels"][dom]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(dom)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": GLOBAL_N / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ClipLoss fwd+bwd, global batch {GLOBAL_N} x {DIM} bf16, local_loss=False, "
+                                   f"gather_with_grad=True, {GLOBAL_N // world} rows per GPU",
+                       "global_batch": GLOBAL_N, "dim": DIM, "rows_per_gpu": n,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); inputs 128 MiB",
+                       "loss": loss_val},
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": dk["tflops"], "peak": peaks["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": dk["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
+                         "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
+                         "kernels": roof["kernels"],
+                         "step": {"algorithmic_flops": flops / world, "algorithmic_tflops_per_gpu": step_tflops,
+                                  "frac_of_burst_peak": step_tflops / peaks["bf16_tflops"],
+                                  "frac_of_sustained_peak": (step_tflops / peaks["bf16_tflops_sustained"]
+                                                             if peaks["bf16_tflops_sustained"] else None),
+                                  "executed_over_algorithmic": 8.0 / 6.0}},
+            "e2e": {"value": GLOBAL_N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 2 * n * DIM * 2, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(steps=2, warmup=1, budget_s_per_step=6.0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, reps=5):
+    """Times each tensor-core kernel of one rank's panel alone (CUDA events on the launch stream)."""
+    d = A.shape[1]
+    off = rank * n
+    B_all = B if world == 1 else B.repeat(world, 1)       # same shape/values class as the gathered operand
+    scale = torch.ones(1, dtype=torch.float32, device=dev)
+    stats = torch.zeros(2, dtype=torch.float32, device=dev)
+    diag = torch.empty(n, dtype=torch.float32, device=dev)
+    rowsum = torch.empty(n, dtype=torch.float32, device=dev)
+    colsum = torch.empty(N, dtype=torch.float32, device=dev)
+    K.rowstats(A, B_all, off, diag, stats)
+    scratch = K.fwd_sums(A, B_all, scale, stats, rowsum, colsum)
+    ldw = (N + 63) // 64 * 64
+    rows = min(n, max(128, ((1 << 30) // (2 * ldw)) // 128 * 128))
+    Wz = torch.empty(rows, ldw, dtype=torch.bfloat16, device=dev)
+    wr = torch.full((n,), 1e-6, dtype=torch.float32, device=dev)
+    wc = torch.full((N,), 1e-6, dtype=torch.float32, device=dev)
+    dg = torch.full((n,), 1e-3, dtype=torch.float32, device=dev)
+    dA = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+    dB = torch.empty(N, d, dtype=torch.bfloat16, device=dev)
+    runs = {
+        "clip_s_kernel<FWD> (logits + exp-sums)": (lambda: K.fwd_sums(A, B_all, scale, stats, rowsum, colsum, scratch), 2.0 * n * N * d),
+        "clip_s_kernel<DZ> (logits recompute + dL/dZ panel)": (lambda: K.dz_panel(A[:rows], B_all, off, scale, stats, wr, wc, dg, Wz), 2.0 * rows * N * d),
+        "gemm_kernel<K,MN> (dA = Wz . B)": (lambda: K.gemm_bf16(Wz, False, B_all, True, rows, d, N, out=dA), 2.0 * rows * N * d),
+        "gemm_kernel<MN,MN> (dB = Wz^T . A)": (lambda: K.gemm_bf16(Wz, True, A[:rows], True, N, d, rows, out=dB), 2.0 * rows * N * d),
+    }
+    out = {}
+    for name, (fn, fl) in runs.items():
+        fn(); fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sum(ts) / len(ts)
+        out[name] = {"ms": t, "flops": fl, "tflops": fl / (t * 1e-3) / 1e12, "rows": rows if "FWD" not in name else n}
+    return {"kernels": out}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

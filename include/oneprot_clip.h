@@ -37,7 +37,7 @@ int oneprot_abi_version(void);
 const char* oneprot_last_error(void);
 /* 0 iff `device` exists and is compute capability 10.x */
 int oneprot_device_check(int device);
-/* number of kernel launches issued by this library on the calling thread since the last reset */
+/* number of kernel launches issued by this library (all threads) since the last reset */
 long long oneprot_launch_count(void);
 void oneprot_launch_count_reset(void);
 

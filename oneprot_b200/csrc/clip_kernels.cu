@@ -15,6 +15,8 @@
 #include <cstring>
 #include <cmath>
 #include <string>
+#include <atomic>
+#include <algorithm>
 
 namespace op {
 
@@ -837,7 +839,7 @@ __global__ void split_fp32_kernel(const float* __restrict__ x, __nv_bfloat16* __
 namespace {
 
 thread_local std::string g_err;
-thread_local long long g_launches = 0;
+std::atomic<long long> g_launches{0};   // process-wide: backward runs on autograd's thread
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -930,8 +932,8 @@ extern "C" {
 
 int oneprot_abi_version(void) { return ONEPROT_ABI_VERSION; }
 const char* oneprot_last_error(void) { return g_err.c_str(); }
-long long oneprot_launch_count(void) { return g_launches; }
-void oneprot_launch_count_reset(void) { g_launches = 0; }
+long long oneprot_launch_count(void) { return g_launches.load(); }
+void oneprot_launch_count_reset(void) { g_launches.store(0); }
 
 int oneprot_device_check(int device) {
   cudaDeviceProp prop;

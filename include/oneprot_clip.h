@@ -37,6 +37,9 @@ int oneprot_abi_version(void);
 const char* oneprot_last_error(void);
 /* 0 iff `device` exists and is compute capability 10.x */
 int oneprot_device_check(int device);
+/* SM count of the current device (persistent grids launch one CTA per SM; the host sizes dL/dZ
+ * panels so that the dA GEMM's 128 x 256 tiles fill whole waves). */
+int oneprot_num_sms(void);
 /* number of kernel launches issued by this library (all threads) since the last reset */
 long long oneprot_launch_count(void);
 void oneprot_launch_count_reset(void);

@@ -18,6 +18,7 @@ SIGNATURES = {
     "oneprot_abi_version": (_i, []),
     "oneprot_last_error": (C.c_char_p, []),
     "oneprot_device_check": (_i, [_i]),
+    "oneprot_num_sms": (_i, []),
     "oneprot_launch_count": (C.c_longlong, []),
     "oneprot_launch_count_reset": (None, []),
     "oneprot_clip_rowstats": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _vp]),

@@ -277,6 +277,11 @@ class _ClipLossFunction(torch.autograd.Function):
         grad_dtype = torch.float32 if ops.split else torch.bfloat16
         ldw = (N + 63) // 64 * 64
         rows_cap = max(128, (cfg["panel_bytes"] // (2 * ldw)) // 128 * 128)
+        if rows_cap < n:
+            # several panels: make the dA GEMM of every full panel an integer number of waves
+            unit = K.panel_row_unit(d)
+            if rows_cap >= unit:
+                rows_cap = rows_cap // unit * unit
         panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
         Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
 

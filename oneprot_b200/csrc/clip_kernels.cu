@@ -12,6 +12,7 @@
 
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -23,7 +24,7 @@ namespace op {
 constexpr int BM = 128;            // accumulator rows  (TMEM lanes)
 constexpr int BN = 256;            // accumulator cols  (TMEM columns per buffer)
 constexpr int BK = 64;             // bf16 elements per smem row = 128 B = one swizzle atom
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -36,15 +37,19 @@ constexpr float LN2 = 0.6931471805599453f;
 constexpr float G_MARGIN = 100.0f;   // e_ij <= 2^100 guaranteed by the Cauchy-Schwarz bound
 
 struct __align__(16) SmemTail {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
   uint32_t tmem_base;
   uint32_t pad[3];
   alignas(16) float colvec[BN];   // read back as float4
 };
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + sizeof(SmemTail);
+// dynamic smem = [NS operand stages | optional bf16 staging for TMA stores | barriers etc.]
+constexpr int STORE_STAGING_BYTES = 2 * 16384;     // one 16 KiB TMA-store box {64 cols, 128 rows} per epilogue warp group
+constexpr int smem_bytes(int ns, int staging) {
+  return ns * STAGE_BYTES + staging + 1024 /*alignment slack*/ + static_cast<int>(sizeof(SmemTail));
+}
 
 // ------------------------------------------------------------------------------------------
 // mainloop pieces
@@ -78,24 +83,28 @@ __device__ __forceinline__ void mma_stage(uint32_t sa, uint32_t sb, uint32_t tme
   }
 }
 
+template <int NS>
 struct PipeState {
   int stage = 0;
   uint32_t phase = 0;
   __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    if (++stage == NS) { stage = 0; phase ^= 1; }
   }
 };
 
 struct Smem {
   uint8_t* stages;
+  uint8_t* staging;   // valid only when the kernel was launched with staging bytes
   SmemTail* tail;
 };
 
+template <int NS, int STAGING>
 __device__ __forceinline__ Smem carve_smem(uint8_t* raw) {
   uintptr_t p = (reinterpret_cast<uintptr_t>(raw) + 1023) & ~static_cast<uintptr_t>(1023);
   Smem s;
   s.stages = reinterpret_cast<uint8_t*>(p);
-  s.tail = reinterpret_cast<SmemTail*>(p + STAGES * STAGE_BYTES);
+  s.staging = reinterpret_cast<uint8_t*>(p + NS * STAGE_BYTES);
+  s.tail = reinterpret_cast<SmemTail*>(p + NS * STAGE_BYTES + STAGING);
   return s;
 }
 
@@ -107,7 +116,7 @@ __device__ __forceinline__ uint32_t kernel_prologue(const Smem& s, const CUtenso
     prefetch_tmap(mapB);
   }
   if (warp == 1 && lane_id() == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&s.tail->full[i], 1);
       mbar_init(&s.tail->empty[i], 1);
     }
@@ -189,10 +198,19 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
 enum { EPI_FWD = 0, EPI_DZ = 1 };
 
 template <int EPI>
+struct SCfg {
+  static constexpr int NS = 4;                                             // operand ring depth
+  static constexpr int STAGING = (EPI == EPI_DZ) ? STORE_STAGING_BYTES : 0;
+  static constexpr int SMEM = smem_bytes(NS, STAGING);
+};
+
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SParams p) {
+clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+              const __grid_constant__ CUtensorMap mapW, const SParams p) {
+  constexpr int NS = SCfg<EPI>::NS;
   extern __shared__ uint8_t smem_raw[];
-  const Smem s = carve_smem(smem_raw);
+  const Smem s = carve_smem<NS, SCfg<EPI>::STAGING>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
   const int warp = threadIdx.x >> 5;
   const int items = p.nJ * p.nChunks;
@@ -201,7 +219,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     // ------------------------------------------------ TMA producer
     reg_dealloc<56>();   // the 4 control warps hand registers to the 8 epilogue warps
     if (lane_id() == 0) {
-      PipeState ps;
+      PipeState<NS> ps;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int jb = item / p.nChunks, ch = item % p.nChunks;
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
@@ -219,7 +237,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     // ------------------------------------------------ UMMA issuer
     reg_dealloc<56>();
     if (lane_id() == 0) {
-      PipeState ps;
+      PipeState<NS> ps;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -258,6 +276,10 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint32_t acc_phase = 0;
 
     float colacc[EPI == EPI_FWD ? 128 : 1];
+    // DZ: bf16 staging of 64 columns of this warp group's half tile = one SWIZZLE_128B box {64 cols, 128 rows}
+    const uint32_t colvec_s = smem_u32(&s.tail->colvec[0]);
+    const uint32_t stage_s = smem_u32(s.staging) + h * 16384;
+    const bool store_issuer = (q == 0) && (lane == 0);
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int jb = item / p.nChunks, ch = item % p.nChunks;
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
@@ -270,7 +292,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         named_bar_sync(1, EPI_THREADS);
         const int t = threadIdx.x - EPI_WARP0 * 32;
         const int jj = jb * BN + t;
-        s.tail->colvec[t] = (jj < p.N) ? __ldg(p.wc + jj) : 0.f;
+        st_shared_f32(colvec_s + t * 4, (jj < p.N) ? __ldg(p.wc + jj) : 0.f);
         named_bar_sync(1, EPI_THREADS);
       }
       for (int ib = ch * p.CI; ib < ib1; ++ib) {
@@ -317,11 +339,15 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               }
             }
           } else {
-            const float4* cv = reinterpret_cast<const float4*>(&s.tail->colvec[h * 128 + cc * 32]);
+            if ((cc & 1) == 0) {
+              // the previous TMA store must have finished reading the staging box
+              if (store_issuer) bulk_wait_read<0>();
+              named_bar_sync(2 + h, 128);
+            }
             uint32_t packed[16];
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
-              const float4 w4 = cv[k4];
+              const float4 w4 = ld_shared_f4(colvec_s + (h * 128 + cc * 32 + k4 * 4) * 4);
               const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
               float dz[4];
 #pragma unroll
@@ -338,13 +364,19 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               packed[k4 * 2] = pack_bf16x2(dz[0], dz[1]);
               packed[k4 * 2 + 1] = pack_bf16x2(dz[2], dz[3]);
             }
-            if (rowok) {
-              __nv_bfloat16* dst = p.Wz + static_cast<size_t>(i) * p.ldw + j0 + cc * 32;
+            // row r of the box: 128-byte line, 16-byte slots XOR-swizzled by (r % 8)
+            const uint32_t line = stage_s + r * 128;
 #pragma unroll
-              for (int v4 = 0; v4 < 4; ++v4) {
-                if (j0 + cc * 32 + v4 * 8 < p.ldw)
-                  *reinterpret_cast<uint4*>(dst + v4 * 8) =
-                      make_uint4(packed[v4 * 4], packed[v4 * 4 + 1], packed[v4 * 4 + 2], packed[v4 * 4 + 3]);
+            for (int v4 = 0; v4 < 4; ++v4) {
+              const uint32_t slot = static_cast<uint32_t>(((cc & 1) * 4 + v4) ^ (r & 7));
+              st_shared_v4(line + slot * 16, packed[v4 * 4], packed[v4 * 4 + 1], packed[v4 * 4 + 2], packed[v4 * 4 + 3]);
+            }
+            if (cc & 1) {
+              fence_proxy_async();            // generic-proxy smem writes -> visible to the TMA engine
+              named_bar_sync(2 + h, 128);
+              if (store_issuer) {
+                tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
+                bulk_commit();
               }
             }
           }
@@ -366,6 +398,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
       }
     }
+    if (EPI == EPI_DZ && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
   }
   kernel_epilogue_dealloc(tmem_base);
 }
@@ -374,6 +407,9 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 // Generic GEMM: C[M x Nc] = op(A) op(B), tile 128 x 256, full K per tile.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]);
+
+constexpr int GEMM_NS = 4;
+constexpr int GEMM_SMEM = smem_bytes(GEMM_NS, 0);
 
 struct GParams {
   int M, Nc, nK;
@@ -392,7 +428,7 @@ template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const Smem s = carve_smem(smem_raw);
+  const Smem s = carve_smem<GEMM_NS, 0>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
   const int warp = threadIdx.x >> 5;
   const int tiles = p.nMb * p.nNb;
@@ -400,7 +436,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   if (warp == 0) {
     reg_dealloc<56>();
     if (lane_id() == 0) {
-      PipeState ps;
+      PipeState<GEMM_NS> ps;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int mb = t / p.nNb, nb = t % p.nNb;
         for (int kb = 0; kb < p.nK; ++kb) {
@@ -415,7 +451,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   } else if (warp == 1) {
     reg_dealloc<56>();
     if (lane_id() == 0) {
-      PipeState ps;
+      PipeState<GEMM_NS> ps;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -898,12 +934,12 @@ int num_sms() {
 }
 
 template <typename K>
-int prep_kernel(K kernel) {
+int prep_kernel(K kernel, int smem_bytes) {
   static thread_local const void* done[8] = {nullptr};
   for (auto& p : done) {
     if (p == reinterpret_cast<const void*>(kernel)) return ONEPROT_OK;
   }
-  OP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, op::SMEM_BYTES));
+  OP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   for (auto& p : done) {
     if (!p) { p = reinterpret_cast<const void*>(kernel); break; }
   }
@@ -912,18 +948,31 @@ int prep_kernel(K kernel) {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-// choose the row-chunk length of an S-kernel work item: >= 4 waves of items when possible
-void s_schedule(int rows, int N, op::SParams& p) {
+// Row-chunk length CI of an S-kernel work item (item = one 256-column block x CI row blocks).
+// Items are dealt round-robin to one persistent CTA per SM, so the makespan is about
+// ceil(items / SMs) * CI tiles; pick the CI in [ci_min, 16] that minimises it (ties: longer
+// chunks, fewer column flushes; beyond 16 the cold-L2 start gets measurably worse).
+void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
   p.nI = cdiv(rows, op::BM);
   p.nJ = cdiv(N, op::BN);
   const int sms = num_sms();
-  int ci = p.nI;
-  // shrink the chunk until there are at least ~6 items per SM (or chunks are 8 row blocks long)
-  while (ci > 8 && static_cast<long long>(p.nJ) * cdiv(p.nI, ci) < 6LL * sms) ci = cdiv(ci, 2);
-  // small problems: make sure every SM gets work even if chunks become short
-  while (ci > 1 && static_cast<long long>(p.nJ) * cdiv(p.nI, ci) < sms) ci = cdiv(ci, 2);
-  p.CI = ci;
-  p.nChunks = cdiv(p.nI, ci);
+  long long best_cost = -1;
+  int best_ci = 1;
+  for (int ci = std::min(ci_min, p.nI); ci <= std::min(16, p.nI); ++ci) {
+    const int chunks = cdiv(p.nI, ci);
+    const long long items = static_cast<long long>(p.nJ) * chunks;
+    const long long cost = cdiv(static_cast<int>(std::min<long long>(items, 1 << 30)), sms) * static_cast<long long>(ci);
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && ci > best_ci)) {
+      best_cost = cost;
+      best_ci = ci;
+    }
+  }
+  if (const char* e = getenv("ONEPROT_CI")) {   // experiment knob
+    const int v = atoi(e);
+    if (v > 0) best_ci = std::min(v, p.nI);
+  }
+  p.CI = std::max(1, best_ci);
+  p.nChunks = cdiv(p.nI, p.CI);
 }
 
 }  // namespace
@@ -934,6 +983,8 @@ int oneprot_abi_version(void) { return ONEPROT_ABI_VERSION; }
 const char* oneprot_last_error(void) { return g_err.c_str(); }
 long long oneprot_launch_count(void) { return g_launches.load(); }
 void oneprot_launch_count_reset(void) { g_launches.store(0); }
+
+int oneprot_num_sms(void) { return num_sms(); }
 
 int oneprot_device_check(int device) {
   cudaDeviceProp prop;
@@ -959,7 +1010,7 @@ int oneprot_clip_rowstats(const void* A, const void* B_all, int n, int N, int d,
 
 size_t oneprot_clip_fwd_scratch_bytes(int n, int N) {
   op::SParams p{};
-  s_schedule(n, N, p);
+  s_schedule(n, N, 2, p);
   const size_t ldr = static_cast<size_t>(p.nI) * op::BM, ldc = static_cast<size_t>(p.nJ) * op::BN;
   return sizeof(float) * (2 * static_cast<size_t>(p.nJ) * ldr + 4 * static_cast<size_t>(p.nChunks) * ldc);
 }
@@ -972,7 +1023,7 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
   if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "fwd_sums: scratch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   op::SParams p{};
-  s_schedule(n, N, p);
+  s_schedule(n, N, 2, p);
   p.rows = n; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = 0;
   p.scale = scale_dev; p.stats = stats;
   p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
@@ -982,9 +1033,10 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
   int rc;
   if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
   if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
-  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD>))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_FWD>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD>, smem))) return rc;
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
-  op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, op::SMEM_BYTES, st>>>(mapA, mapB, p);
+  op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   op::reduce_slots_kernel<<<cdiv(n, 256), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
@@ -1030,7 +1082,7 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
   if (rows <= 0 || N <= 0 || d <= 0 || d % 8 || ldw < N || ldw % 8) return fail(ONEPROT_ERR_ARG, "dz_panel: bad sizes");
   if (reinterpret_cast<uintptr_t>(Wz) & 15) return fail(ONEPROT_ERR_ARG, "dz_panel: Wz must be 16-byte aligned");
   op::SParams p{};
-  s_schedule(rows, N, p);
+  s_schedule(rows, N, 1, p);
   p.rows = rows; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = grow0;
   p.scale = scale_dev; p.stats = stats;
   p.wr = wr; p.wc = wc; p.dg = dg;
@@ -1039,9 +1091,12 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
   int rc;
   if ((rc = make_map(&mapA, A_rows, d, rows, d, op::BM))) return rc;
   if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
-  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>))) return rc;
+  CUtensorMap mapW;   // store side: boxes {64 cols, 128 rows}; columns >= N and rows >= `rows` are clipped
+  if ((rc = make_map(&mapW, Wz, N, rows, ldw, op::BM))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_DZ>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
-  op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, op::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, p);
+  op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -1082,8 +1137,8 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_GEMM(AM, BMJ)                                                                       \
   do {                                                                                             \
-    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ>))) return rc;                                   \
-    op::gemm_kernel<AM, BMJ><<<grid, op::NUM_THREADS, op::SMEM_BYTES, st>>>(mapA, mapB, p);        \
+    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ>, op::GEMM_SMEM))) return rc;                    \
+    op::gemm_kernel<AM, BMJ><<<grid, op::NUM_THREADS, op::GEMM_SMEM, st>>>(mapA, mapB, p);         \
   } while (0)
   if (!a_mn && !b_mn) LAUNCH_GEMM(0, 0);
   else if (!a_mn && b_mn) LAUNCH_GEMM(0, 1);

@@ -31,6 +31,15 @@ def _need(t, dtype, what):
         raise ValueError(f"{what}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
 
 
+def panel_row_unit(d: int) -> int:
+    """Smallest panel height (rows) whose dA GEMM tile count (128 x 256 tiles) is a multiple of the
+    SM count, i.e. fills whole waves of the persistent grid."""
+    import math
+    sms = int(_lib.load().oneprot_num_sms())
+    n_col_blocks = (d + 255) // 256
+    return 128 * (sms // math.gcd(sms, n_col_blocks))
+
+
 def launch_count() -> int:
     return int(_lib.load().oneprot_launch_count())
 

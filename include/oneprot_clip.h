@@ -153,6 +153,18 @@ int oneprot_scale_rows(const void* x, void* y, int rows, int d, int is_fp32, con
 /* out[row] = <x_row, y_row> for contiguous rows (bf16 or fp32): d scale = sum_rows <x, gy>. */
 int oneprot_rowdot(const void* x, const void* y, int rows, int d, int is_fp32, float* out, void* stream);
 
+/* ---- single-node exchanges through an NVLink multicast (NVLS) mapping -----------------------
+ * The *_mc pointers are multicast aliases of a symmetric buffer (the Python host obtains them
+ * from torch.distributed._symmetric_memory); they replace the collectives of gather_features
+ * (loss.py:32-38) and of its autograd backward on one NVSwitch node.  The caller brackets them
+ * with the symmetric-memory barrier. */
+/* all-gather by push: copy `bytes` from src into every GPU's copy of the buffer behind dst_mc */
+int oneprot_mc_store(const void* src, void* dst_mc, size_t bytes, void* stream);
+/* dst[i] = reduce over GPUs of src_mc[i]; op 0 = fp32 add, 1 = max of non-negative fp32 */
+int oneprot_mc_allreduce_f32(const float* src_mc, float* dst, int count, int op, void* stream);
+/* dst = sum over GPUs of a bf16 buffer (fp32 accumulation in the switch); reduce-scatter by pull */
+int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* stream);
+
 /* Split fp32 rows into bf16 limbs for the fp32-accurate path: out is rows x (terms*d) bf16 with
  * the limb order given by `pattern`, so that the bf16 GEMM over the
  * concatenated K reproduces the fp32 dot product. */

@@ -36,6 +36,9 @@ SIGNATURES = {
     "oneprot_l2norm_scale_bwd": (_i, [_vp, _vp, _fp, _vp, _fp, _i, _i, _i, _fp, _f, _vp]),
     "oneprot_scale_rows": (_i, [_vp, _vp, _i, _i, _i, _fp, _vp]),
     "oneprot_rowdot": (_i, [_vp, _vp, _i, _i, _i, _fp, _vp]),
+    "oneprot_mc_store": (_i, [_vp, _vp, _sz, _vp]),
+    "oneprot_mc_allreduce_f32": (_i, [_fp, _fp, _i, _i, _vp]),
+    "oneprot_mc_reduce_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "oneprot_split_fp32": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
 }
 

@@ -62,27 +62,18 @@ def _float_scale_on(device, value: float) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # collectives (plumbing only)
 # ---------------------------------------------------------------------------------------------
-def _all_gather_rows(x: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
-    """Concatenation over ranks of the contiguous (n x d) tensor, gathered straight into one
-    (W n x d) buffer (the reference builds W tensors and ``torch.cat``s them, loss.py:32-44)."""
-    out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
-    return out
+from .comm import _all_gather_rows, _reduce_scatter_rows, make_comm   # noqa: E402
+
+_COMMS = {}     # (device, group id, world, rank, kernel provider) -> exchange provider (owns the NVLS workspace)
 
 
-def _reduce_scatter_rows(full: torch.Tensor, rank: int, world_size: int, group=None) -> torch.Tensor:
-    """SUM-reduce-scatter of a (W n x d) tensor along rows; the backward of an all-gather
-    (torch/distributed/nn/functional.py:_AllGather.backward)."""
-    n = full.shape[0] // world_size
-    out = torch.empty((n,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
-    backend = dist.get_backend(group)
-    if backend == "nccl":
-        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=group)
-    else:  # gloo has no reduce-scatter
-        tmp = full.contiguous().clone()
-        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
-        out.copy_(tmp[rank * n:(rank + 1) * n])
-    return out
+def _get_comm(world, rank, group, device):
+    key = (str(device), id(group), world, rank, id(_KERNELS))
+    c = _COMMS.get(key)
+    if c is None:
+        c = make_comm(_KERNELS, world, rank, group, device)
+        _COMMS[key] = c
+    return c
 
 
 class _AllGatherWithGrad(torch.autograd.Function):
@@ -219,18 +210,16 @@ class _ClipLossFunction(torch.autograd.Function):
         ops = _Operands(A, B)
         n, off = ops.n, rank * ops.n
         N = W * n
-        B_all = _all_gather_rows(ops.B, W, group) if W > 1 else ops.B
+        comm = _get_comm(W, rank, group, dev)
         scale_dev = scale_t.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
 
-        stats = torch.zeros(2, dtype=torch.float32, device=dev)
-        sums = torch.zeros(3 * N, dtype=torch.float32, device=dev)     # [colsum | rowsum | diag], global order
+        st = comm.begin_forward(ops, rank, W)          # second operand of all ranks + zeroed [colsum | rowsum | diag]
+        B_all, sums = st["B_all"], st["sums"]
+        K.rowstats(ops.A, st["stats_rows"], st["stats_off"], sums[2 * N + off:2 * N + off + n], st["stats"])
+        stats = comm.global_stats(st)                  # one reference G on every rank
+        K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N])
+        sums = comm.complete_sums(st)
         colsum, rowsum_all, diag_all = sums[0:N], sums[N:2 * N], sums[2 * N:3 * N]
-        K.rowstats(ops.A, B_all, off, diag_all[off:off + n], stats)
-        if W > 1:
-            dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=group)   # one reference G on every rank
-        K.fwd_sums(ops.A, B_all, scale_dev, stats, rowsum_all[off:off + n], colsum)
-        if W > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
 
         out = torch.empty(1 + 2 * N, dtype=torch.float32, device=dev)
         loss32, inv_rs, inv_cs = out[0:1], out[1:1 + N], out[1 + N:]
@@ -238,7 +227,7 @@ class _ClipLossFunction(torch.autograd.Function):
         mode = K.MODE_LOCAL if (W > 1 and cfg["local_loss"]) else K.MODE_GLOBAL
         K.loss_finalize(rowsum_all, colsum, diag_all, n, off, mode, scale_dev, stats, loss32, inv_rs, inv_cs, flag)
 
-        ctx.cfg, ctx.ops, ctx.mode = cfg, ops, mode
+        ctx.cfg, ctx.ops, ctx.mode, ctx.comm, ctx.token = cfg, ops, mode, comm, st["token"]
         ctx.B_all, ctx.scale_dev, ctx.stats, ctx.inv_rs, ctx.inv_cs = B_all, scale_dev, stats, inv_rs, inv_cs
         ctx.scale_needs_grad = scale_t.requires_grad
         ctx.scale_meta = (scale_t.dtype, scale_t.device, scale_t.shape)
@@ -257,12 +246,13 @@ class _ClipLossFunction(torch.autograd.Function):
         n, d, dk = ops.n, ops.d, ops.dk
         N, off = W * n, rank * n
         dev = ops.A.device
-        B_all = ctx.B_all
+        comm = ctx.comm
+        B_all = comm.b_all_for_backward(ops, ctx.B_all, ctx.token, rank, W)
         need_a, need_b, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.scale_needs_grad
 
         g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
                else g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1))
-        gvec = _all_gather_rows(g32, W, group) if W > 1 else g32
+        gvec = comm.gather_grad_outputs(g32, rank, W, ctx.token)
         local = mode == K.MODE_LOCAL
         gwg = cfg["gather_with_grad"]
         # cross-rank gradient only flows where the reference's graph has it
@@ -292,11 +282,11 @@ class _ClipLossFunction(torch.autograd.Function):
         dA_total = dB_total = None
         ds_terms = []      # 1-element tensors whose sum is scale * d(value)/d(scale) * g  (this rank's part)
         b_pieces, n_bp = ops.b_pieces(B_all), (2 if ops.split else 1)
-        for part, want_a, want_b in passes:
+        for pi, (part, want_a, want_b) in enumerate(passes):
             K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
                           wr, wc, dg, sA, sB)
             dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
-            dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
+            dBp = comm.db_buffer(N, d, grad_dtype, dev) if want_b else None
             chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp) if want_b else None
             rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
             for r0, rows in panels:
@@ -319,7 +309,7 @@ class _ClipLossFunction(torch.autograd.Function):
                     for Ap in ops.a_pieces(A_rows):
                         chain_b.add(Wp, True, Ap, True, rows)
             if want_b and exchange_b:
-                dBp = _reduce_scatter_rows(dBp, rank, W, group)
+                dBp = comm.reduce_scatter_db(dBp, rank, W, last_pass=(pi == len(passes) - 1))
             if local and need_s:
                 # local loss: d value_r / d scale = (sum_i <a_i, dA^P_i> + sum_j <b_j, dB^Q_j>) / scale
                 if part == 1 and dA is not None:
@@ -342,8 +332,7 @@ class _ClipLossFunction(torch.autograd.Function):
                 tot = tot + t
             if not local:
                 # unit-gradient partial of this rank's rows -> all ranks' rows, times this rank's upstream g
-                if W > 1:
-                    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+                tot = comm.sum_scalar(tot)
                 tot = tot * g32
             grad_s = tot / ctx.scale_dev
             sdt, sdev, sshape = ctx.scale_meta

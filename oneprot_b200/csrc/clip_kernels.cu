@@ -845,6 +845,54 @@ __global__ void rowdot_dense_kernel(const void* __restrict__ x, const void* __re
   }
 }
 
+// ---- NVLink SHARP (multimem) exchanges over a symmetric-memory multicast mapping ---------------
+// dst_mc is the multicast alias of one buffer that exists on every GPU of the node: a
+// multimem.st lands in all copies (all-gather by push), a multimem.ld_reduce returns the
+// reduction over all copies computed in the switch (all-reduce / reduce-scatter by pull).
+__global__ void mc_store_kernel(const uint4* __restrict__ src, uint4* dst_mc, size_t n16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = src[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + i), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+  }
+}
+
+// op 0: fp32 add (4 per thread), op 1: u32 max (bit patterns of non-negative floats)
+__global__ void mc_allreduce_kernel(const float* src_mc, float* __restrict__ dst, int count, int op) {
+  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= count) return;
+  if (op == 0) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(src_mc + i4)
+                 : "memory");
+    *reinterpret_cast<float4*>(dst + i4) = v;          // count is padded to a multiple of 4 by the host
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint32_t r;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.max.u32 %0, [%1];" : "=r"(r) : "l"(src_mc + i4 + u) : "memory");
+      dst[i4 + u] = __uint_as_float(r);
+    }
+  }
+}
+
+// dst[i] = sum over GPUs of the bf16 buffer (fp32 accumulation in the switch), 8 elements per thread
+__global__ void mc_reduce_bf16_kernel(const uint4* src_mc, uint4* __restrict__ dst, size_t n16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(src_mc + i)
+                 : "memory");
+    dst[i] = v;
+  }
+}
+
 // fp32 -> bf16 limbs: x = h + m + l (each bf16).  side 0 (left operand):  [h h m | h m l]
 //                                                   side 1 (right operand): [h m h | l m h]
 // terms = 3 keeps the first three limb products (h.h + h.m + m.h), terms = 6 all six of order <= 2.
@@ -1210,6 +1258,38 @@ int oneprot_rowdot(const void* x, const void* y, int rows, int d, int is_fp32, f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_fp32) op::rowdot_dense_kernel<true><<<blocks, 256, 0, st>>>(x, y, rows, d, out);
   else op::rowdot_dense_kernel<false><<<blocks, 256, 0, st>>>(x, y, rows, d, out);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_mc_store(const void* src, void* dst_mc, size_t bytes, void* stream) {
+  if (!src || !dst_mc || bytes == 0 || bytes % 16 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_mc) & 15))
+    return fail(ONEPROT_ERR_ARG, "mc_store: need 16-byte aligned pointers and size");
+  const size_t n16 = bytes / 16;
+  const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  op::mc_store_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst_mc), n16);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_mc_allreduce_f32(const float* src_mc, float* dst, int count, int op, void* stream) {
+  if (!src_mc || !dst || count <= 0 || count % 4 || (op != 0 && op != 1) || (reinterpret_cast<uintptr_t>(src_mc) & 15) ||
+      (reinterpret_cast<uintptr_t>(dst) & 15))
+    return fail(ONEPROT_ERR_ARG, "mc_allreduce: count must be a multiple of 4, pointers 16-byte aligned");
+  op::mc_allreduce_kernel<<<cdiv(count / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src_mc, dst, count, op);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* stream) {
+  if (!src_mc || !dst || bytes == 0 || bytes % 16 || (reinterpret_cast<uintptr_t>(src_mc) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return fail(ONEPROT_ERR_ARG, "mc_reduce_bf16: need 16-byte aligned pointers and size");
+  const size_t n16 = bytes / 16;
+  const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  op::mc_reduce_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src_mc), static_cast<uint4*>(dst), n16);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

@@ -184,3 +184,21 @@ def rowdot(x, y, out):
     rows, d = x.shape
     check(_lib.load().oneprot_rowdot(ptr(x), ptr(y), rows, d, int(x.dtype == torch.float32), ptr(out), _stream()),
           "oneprot_rowdot")
+
+
+# ---- NVLS (multimem) exchanges; *_mc arguments are raw multicast addresses (int) -------------
+def mc_store(src, dst_mc_addr: int, nbytes: int):
+    _need_cuda(src)
+    check(_lib.load().oneprot_mc_store(ptr(src), C.c_void_p(dst_mc_addr), nbytes, _stream()), "oneprot_mc_store")
+
+
+def mc_allreduce_f32(src_mc_addr: int, dst, count: int, op: int = 0):
+    _need_cuda(dst)
+    check(_lib.load().oneprot_mc_allreduce_f32(C.c_void_p(src_mc_addr), ptr(dst), count, op, _stream()),
+          "oneprot_mc_allreduce_f32")
+
+
+def mc_reduce_bf16(src_mc_addr: int, dst, nbytes: int):
+    _need_cuda(dst)
+    check(_lib.load().oneprot_mc_reduce_bf16(C.c_void_p(src_mc_addr), ptr(dst), nbytes, _stream()),
+          "oneprot_mc_reduce_bf16")

@@ -75,10 +75,14 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
  *   loss_out[0] = this rank's return value (MODE_GLOBAL: mean over all N; MODE_LOCAL: mean over
  *   rows/cols [row_offset, row_offset+n)), fp32;  inv_rowsum/inv_colsum[k] = 1/sum;
  *   flag[0] |= 1 if any sum left the validated fp32 window (result then not trustworthy).
+ * scratch: ONEPROT_FINALIZE_SCRATCH_BYTES bytes, 8-byte aligned, zero-initialised ONCE by the
+ * caller (the kernel leaves it ready for the next call).
  * Replaces the nll half of F.cross_entropy and the /2 (loss.py:109-112). */
+#define ONEPROT_FINALIZE_SCRATCH_BYTES 512
 int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N,
                                int n, int row_offset, int mode, const float* scale_dev, const float* stats,
-                               float* loss_out, float* inv_rowsum, float* inv_colsum, int* flag, void* stream);
+                               float* loss_out, float* inv_rowsum, float* inv_colsum, int* flag, void* scratch,
+                               void* stream);
 
 /* ---- backward ----------------------------------------------------------------------------- */
 
@@ -92,11 +96,13 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
  * MODE_GLOBAL writes a unit-gradient panel description and the upstream gradients go to
  * out_scale_a[n] (multiplies the rows of dA) and out_scale_b[N] (multiplies the rows of the
  * partial dB): g_own resp. g_owner(j) without, sum_r g_r with use_gsum.  MODE_LOCAL folds the
- * gradients into wr/wc and writes ones. */
+ * gradients into wr/wc and writes ones.
+ * what: 0 = write everything, 1 = only wr/wc/dg, 2 = only the output scales (lets the host
+ * overlap the exchange of the upstream gradients with the dL/dZ panel kernel). */
 int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, int N, int n, int row_offset,
                              int mode, int use_gsum, int part, int world, int rank, const float* gvec_dev,
                              const float* scale_dev, float* wr, float* wc, float* dg, float* out_scale_a,
-                             float* out_scale_b, void* stream);
+                             float* out_scale_b, int what, void* stream);
 
 /* Recompute logit tiles for rows [r0, r0+rows) of this rank's panel and write
  * Wz (bf16, row-major, leading dimension ldw >= N, multiple of 8) - the bounded dL/dZ panel.

@@ -24,8 +24,8 @@ SIGNATURES = {
     "oneprot_clip_rowstats": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "oneprot_clip_fwd_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_clip_fwd_sums": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _sz, _vp]),
-    "oneprot_clip_loss_finalize": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _ip, _vp]),
-    "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "oneprot_clip_loss_finalize": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _ip, _vp, _vp]),
+    "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _vp]),
     "oneprot_clip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_rowdot_scratch_bytes": (_sz, [_i, _i]),

@@ -252,9 +252,24 @@ class _ClipLossFunction(torch.autograd.Function):
 
         g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
                else g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1))
-        gvec = comm.gather_grad_outputs(g32, rank, W, ctx.token)
         local = mode == K.MODE_LOCAL
         gwg = cfg["gather_with_grad"]
+        # Overlap (NVLS provider): in the global modes the panel is built for a unit upstream gradient
+        # and g only scales the GEMM outputs, so its exchange runs on a side stream under the dL/dZ
+        # kernel; the pull-reduce of the partial dB runs on the same side stream under the dA GEMM.
+        side = comm.side_stream(dev) if W > 1 else None
+        main = torch.cuda.current_stream() if side is not None else None
+        ev_g = None
+        if side is not None and not local:
+            gvec = torch.zeros((W + 3) // 4 * 4, dtype=torch.float32, device=dev)   # placeholder for `what=1`
+            g_holder = {}
+            ev0 = main.record_event()
+            with torch.cuda.stream(side):
+                side.wait_event(ev0)
+                g_holder["gvec"] = comm.gather_grad_outputs(g32, rank, W, ctx.token)
+        else:
+            gvec = comm.gather_grad_outputs(g32, rank, W, ctx.token)
+            g_holder = None
         # cross-rank gradient only flows where the reference's graph has it
         exchange_b = W > 1
         if local and not gwg:
@@ -283,16 +298,38 @@ class _ClipLossFunction(torch.autograd.Function):
         ds_terms = []      # 1-element tensors whose sum is scale * d(value)/d(scale) * g  (this rank's part)
         b_pieces, n_bp = ops.b_pieces(B_all), (2 if ops.split else 1)
         for pi, (part, want_a, want_b) in enumerate(passes):
-            K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
-                          wr, wc, dg, sA, sB)
+            if g_holder is not None:
+                K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
+                              wr, wc, dg, sA, sB, 1)                     # panel weights: no g needed
+                with torch.cuda.stream(side):
+                    K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, g_holder["gvec"],
+                                  ctx.scale_dev, wr, wc, dg, sA, sB, 2)  # output scales from the gathered g
+                    ev_g = side.record_event()
+            else:
+                K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
+                              wr, wc, dg, sA, sB)
             dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
             dBp = comm.db_buffer(N, d, grad_dtype, dev) if want_b else None
             chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp) if want_b else None
             rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
-            for r0, rows in panels:
+            last_pass = pi == len(passes) - 1
+            ev_rs, dB_async = None, None
+            for qi, (r0, rows) in enumerate(panels):
                 A_rows = ops.A[r0:r0 + rows]
                 K.dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc, dg[r0:r0 + rows], Wz)
                 Wp = Wz[:rows]
+                if ev_g is not None:
+                    main.wait_event(ev_g)        # GEMM epilogues read the output scales
+                    ev_g = None
+                if want_b:                        # dB first: its exchange then hides under the dA GEMM
+                    for Ap in ops.a_pieces(A_rows):
+                        chain_b.add(Wp, True, Ap, True, rows)
+                    if exchange_b and side is not None and qi == len(panels) - 1:
+                        evb = main.record_event()
+                        with torch.cuda.stream(side):
+                            side.wait_event(evb)
+                            dB_async = comm.reduce_scatter_db(dBp, rank, W, last_pass=last_pass)
+                            ev_rs = side.record_event()
                 if want_a:
                     chain_a = _GemmChain(rows, d, dA[r0:r0 + rows], sA[r0:r0 + rows], n_bp)
                     for bi, Bp in enumerate(b_pieces):
@@ -305,11 +342,13 @@ class _ClipLossFunction(torch.autograd.Function):
                             ds_terms.append(("unit", t))
                         else:
                             chain_a.add(Wp, False, Bp, True, N)
-                if want_b:
-                    for Ap in ops.a_pieces(A_rows):
-                        chain_b.add(Wp, True, Ap, True, rows)
             if want_b and exchange_b:
-                dBp = comm.reduce_scatter_db(dBp, rank, W, last_pass=(pi == len(passes) - 1))
+                if dB_async is not None:
+                    main.wait_event(ev_rs)
+                    dB_async.record_stream(main)
+                    dBp = dB_async
+                else:
+                    dBp = comm.reduce_scatter_db(dBp, rank, W, last_pass=last_pass)
             if local and need_s:
                 # local loss: d value_r / d scale = (sum_i <a_i, dA^P_i> + sum_j <b_j, dB^Q_j>) / scale
                 if part == 1 and dA is not None:

@@ -87,6 +87,10 @@ class LocalComm:
     def sum_scalar(self, t):
         return t
 
+    def side_stream(self, dev):
+        """Stream on which exchanges may overlap with compute (None: exchanges are synchronous)."""
+        return None
+
 
 class DistComm(LocalComm):
     """torch.distributed collectives; gathers first, so the row statistics see all of B at once."""
@@ -146,6 +150,7 @@ class NvlsComm(DistComm):
         self.calls = 0
         self.gen = [0, 0]        # generation of the data held in Bg[p]
         self.chan = 0
+        self._side = None
 
     # ---- workspace ----------------------------------------------------------------------
     @staticmethod
@@ -176,7 +181,14 @@ class NvlsComm(DistComm):
 
     def _barrier(self):
         self.hdl.barrier(self.chan)
-        self.chan = (self.chan + 1) % 4
+        self.chan = (self.chan + 1) % 8
+
+    def side_stream(self, dev):
+        if os.environ.get("ONEPROT_NO_OVERLAP"):
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
 
     def _view(self, off, shape, dtype):
         nbytes = dtype.itemsize

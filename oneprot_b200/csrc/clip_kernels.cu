@@ -425,7 +425,7 @@ struct GParams {
 };
 
 template <int A_MN, int B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(128)   // 384 x 128 registers: leaves 16 K registers per SM for a co-resident exchange kernel
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
   extern __shared__ uint8_t smem_raw[];
   const Smem s = carve_smem<GEMM_NS, 0>(smem_raw);
@@ -434,7 +434,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   const int tiles = p.nMb * p.nNb;
 
   if (warp == 0) {
-    reg_dealloc<56>();
+    reg_dealloc<40>();
     if (lane_id() == 0) {
       PipeState<GEMM_NS> ps;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -449,7 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    reg_dealloc<56>();
+    reg_dealloc<40>();
     if (lane_id() == 0) {
       PipeState<GEMM_NS> ps;
       int acc = 0;
@@ -471,9 +471,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       }
     }
   } else if (warp < EPI_WARP0) {
-    reg_dealloc<56>();
+    reg_dealloc<40>();
   } else {
-    reg_alloc<224>();
+    reg_alloc<168>();
     const int ew = warp - EPI_WARP0;
     const int q = ew & 3, h = ew >> 2;
     const int lane = lane_id();
@@ -597,23 +597,35 @@ __global__ void rowstats_kernel(const __nv_bfloat16* __restrict__ A, const __nv_
   }
 }
 
-// out[k] = sum_s part[s*ld + k], fixed order (deterministic)
+// out[k] = sum_s part[s*ld + k]; block = 32 outputs x 8 slot groups, fixed summation order (deterministic)
 __global__ void reduce_slots_kernel(const float* __restrict__ part, int slots, int ld, int count, float* __restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= count) return;
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int s = 0; s < slots; ++s) acc += part[static_cast<size_t>(s) * ld + k];
-  out[k] = acc;
+  if (k < count)
+    for (int s = grp; s < slots; s += 8) acc += part[static_cast<size_t>(s) * ld + k];
+  red[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && k < count) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][lane];
+    out[k] = t;
+  }
 }
 
-// single block: loss value, reciprocal sums, hazard flag
+// loss value, reciprocal sums, hazard flag.  FIN_BLOCKS blocks each reduce a fixed slice in double
+// precision; the last block to finish adds the per-block partials in index order (deterministic).
+constexpr int FIN_BLOCKS = 32;
 __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum,
                                      const float* __restrict__ diag, int N, int n, int row_offset, int mode,
                                      const float* __restrict__ scale, const float* __restrict__ stats,
                                      float* __restrict__ loss_out, float* __restrict__ inv_rs, float* __restrict__ inv_cs,
-                                     int* __restrict__ flag) {
+                                     int* __restrict__ flag, double* __restrict__ partial, unsigned int* __restrict__ counter) {
   __shared__ double red[32];
   __shared__ int bad_s;
+  __shared__ bool is_last;
   const float s = *scale;
   const float c = s * LOG2E;
   const float U = fabsf(c) * sqrtf(stats[0] * stats[1]);
@@ -624,7 +636,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
   const int hi = (mode == ONEPROT_MODE_LOCAL) ? row_offset + n : N;
   double acc = 0.0;
   int bad = 0;
-  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
     const float rs = rowsum[k], cs = colsum[k];
     // validated window: sums must be finite and not have lost their leading terms to flush-to-zero
     if (!(rs >= 1e-24f && rs <= 3e38f) || !(cs >= 1e-24f && cs <= 3e38f)) bad = 1;
@@ -642,8 +654,18 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
-    loss_out[0] = static_cast<float>(t / (2.0 * (hi - lo)));
+    partial[blockIdx.x] = t;
     if (bad_s) atomicOr(flag, 1);
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += *(volatile double*)(partial + b);
+    loss_out[0] = static_cast<float>(t / (2.0 * (hi - lo)));
+    *counter = 0;   // ready for the next launch
   }
 }
 
@@ -651,7 +673,9 @@ __global__ void bwd_weights_kernel(const float* __restrict__ inv_rs, const float
                                    int row_offset, int mode, int use_gsum, int part, int world, int rank,
                                    const float* __restrict__ gvec, const float* __restrict__ scale,
                                    float* __restrict__ wr, float* __restrict__ wc, float* __restrict__ dg,
-                                   float* __restrict__ out_scale_a, float* __restrict__ out_scale_b) {
+                                   float* __restrict__ out_scale_a, float* __restrict__ out_scale_b, int what) {
+  // what: 0 = everything, 1 = panel weights only (wr, wc, dg), 2 = output scales only
+  const bool do_w = what != 2, do_s = what != 1;
   const float s = *scale;
   float gsum = 0.f;
   for (int r = 0; r < world; ++r) gsum += gvec[r];
@@ -665,25 +689,23 @@ __global__ void bwd_weights_kernel(const float* __restrict__ inv_rs, const float
     //   dA_r *= (use_gsum ? sum_r g_r : g_own),  dB_partial[j] *= (use_gsum ? sum_r g_r : g_owner(j))
     const float coef = s / (2.f * N);
     if (k < n) {
-      wr[k] = fr * coef * inv_rs[row_offset + k];
-      dg[k] = (fr + fc) * coef;
-      out_scale_a[k] = use_gsum ? gsum : g_own;
+      if (do_w) { wr[k] = fr * coef * inv_rs[row_offset + k]; dg[k] = (fr + fc) * coef; }
+      if (do_s) out_scale_a[k] = use_gsum ? gsum : g_own;
     }
     if (k < N) {
-      wc[k] = fc * coef * inv_cs[k];
-      out_scale_b[k] = use_gsum ? gsum : gvec[k / npr];
+      if (do_w) wc[k] = fc * coef * inv_cs[k];
+      if (do_s) out_scale_b[k] = use_gsum ? gsum : gvec[k / npr];
     }
   } else {
     // local loss: row i of rank r carries g_r (row softmax), column j carries g_owner(j)
     if (k < n) {
       const float coef = s * g_own / (2.f * n);
-      wr[k] = fr * coef * inv_rs[row_offset + k];
-      dg[k] = (fr + fc) * coef;
-      out_scale_a[k] = 1.f;
+      if (do_w) { wr[k] = fr * coef * inv_rs[row_offset + k]; dg[k] = (fr + fc) * coef; }
+      if (do_s) out_scale_a[k] = 1.f;
     }
     if (k < N) {
-      wc[k] = fc * s * gvec[k / npr] / (2.f * n) * inv_cs[k];
-      out_scale_b[k] = 1.f;
+      if (do_w) wc[k] = fc * s * gvec[k / npr] / (2.f * n) * inv_cs[k];
+      if (do_s) out_scale_b[k] = 1.f;
     }
   }
 }
@@ -1087,8 +1109,8 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
   op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
-  op::reduce_slots_kernel<<<cdiv(n, 256), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
-  op::reduce_slots_kernel<<<cdiv(N, 256), 256, 0, st>>>(p.colpart, 4 * p.nChunks, p.ldc, N, colsum);
+  op::reduce_slots_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
+  op::reduce_slots_kernel<<<cdiv(N, 32), 256, 0, st>>>(p.colpart, 4 * p.nChunks, p.ldc, N, colsum);
   g_launches += 2;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -1096,12 +1118,18 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
 
 int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N, int n,
                                int row_offset, int mode, const float* scale_dev, const float* stats, float* loss_out,
-                               float* inv_rowsum, float* inv_colsum, int* flag, void* stream) {
-  if (!rowsum_all || !colsum_all || !diag_all || !scale_dev || !stats || !loss_out || !inv_rowsum || !inv_colsum || !flag)
+                               float* inv_rowsum, float* inv_colsum, int* flag, void* scratch, void* stream) {
+  if (!rowsum_all || !colsum_all || !diag_all || !scale_dev || !stats || !loss_out || !inv_rowsum || !inv_colsum || !flag || !scratch)
     return fail(ONEPROT_ERR_ARG, "loss_finalize: null pointer");
   if (N <= 0 || n <= 0 || row_offset < 0 || row_offset + n > N) return fail(ONEPROT_ERR_ARG, "loss_finalize: bad sizes");
-  op::loss_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      rowsum_all, colsum_all, diag_all, N, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum, inv_colsum, flag);
+  if (reinterpret_cast<uintptr_t>(scratch) & 7) return fail(ONEPROT_ERR_ARG, "loss_finalize: scratch must be 8-byte aligned");
+  // scratch: FIN_BLOCKS doubles + one zero-initialised counter (the kernel resets it)
+  double* partial = static_cast<double*>(scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + op::FIN_BLOCKS);
+  const int blocks = std::min(op::FIN_BLOCKS, cdiv(N, 256));
+  op::loss_finalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rowsum_all, colsum_all, diag_all, N, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum, inv_colsum, flag,
+      partial, counter);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -1110,14 +1138,14 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
 int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, int N, int n, int row_offset, int mode,
                              int use_gsum, int part, int world, int rank, const float* gvec_dev,
                              const float* scale_dev, float* wr, float* wc, float* dg, float* out_scale_a,
-                             float* out_scale_b, void* stream) {
+                             float* out_scale_b, int what, void* stream) {
   if (!inv_rowsum || !inv_colsum || !gvec_dev || !scale_dev || !wr || !wc || !dg || !out_scale_a || !out_scale_b)
     return fail(ONEPROT_ERR_ARG, "bwd_weights: null pointer");
-  if (world <= 0 || rank < 0 || rank >= world || N % world || n <= 0 || row_offset + n > N)
+  if (world <= 0 || rank < 0 || rank >= world || N % world || n <= 0 || row_offset + n > N || what < 0 || what > 2)
     return fail(ONEPROT_ERR_ARG, "bwd_weights: bad sizes");
   op::bwd_weights_kernel<<<cdiv(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       inv_rowsum, inv_colsum, N, n, row_offset, mode, use_gsum, part, world, rank, gvec_dev, scale_dev, wr, wc, dg,
-      out_scale_a, out_scale_b);
+      out_scale_a, out_scale_b, what);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

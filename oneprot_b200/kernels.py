@@ -78,23 +78,31 @@ def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None):
     return scratch
 
 
+_FIN_SCRATCH = {}   # device index -> zero-initialised scratch of oneprot_clip_loss_finalize
+
+
 def loss_finalize(rowsum_all, colsum_all, diag_all, n: int, row_offset: int, mode: int, scale_dev, stats,
                   loss_out, inv_rowsum, inv_colsum, flag):
     _need_cuda(rowsum_all, colsum_all, diag_all, loss_out, inv_rowsum, inv_colsum, flag)
     N = rowsum_all.numel()
+    key = (rowsum_all.device.index, torch.cuda.current_stream().cuda_stream)
+    scratch = _FIN_SCRATCH.get(key)
+    if scratch is None:
+        scratch = _FIN_SCRATCH[key] = torch.zeros(64, dtype=torch.float64, device=rowsum_all.device)
     check(_lib.load().oneprot_clip_loss_finalize(ptr(rowsum_all), ptr(colsum_all), ptr(diag_all), N, n, row_offset,
                                                  mode, ptr(scale_dev), ptr(stats), ptr(loss_out), ptr(inv_rowsum),
-                                                 ptr(inv_colsum), ptr(flag), _stream()),
+                                                 ptr(inv_colsum), ptr(flag), ptr(scratch), _stream()),
           "oneprot_clip_loss_finalize")
 
 
 def bwd_weights(inv_rowsum, inv_colsum, n: int, row_offset: int, mode: int, use_gsum: bool, part: int, world: int,
-                rank: int, gvec, scale_dev, wr, wc, dg, out_scale_a, out_scale_b):
+                rank: int, gvec, scale_dev, wr, wc, dg, out_scale_a, out_scale_b, what: int = 0):
+    """what: 0 = everything, 1 = panel weights (wr, wc, dg) only, 2 = output scales only."""
     _need_cuda(inv_rowsum, inv_colsum, gvec, scale_dev, wr, wc, dg, out_scale_a, out_scale_b)
     N = inv_rowsum.numel()
     check(_lib.load().oneprot_clip_bwd_weights(ptr(inv_rowsum), ptr(inv_colsum), N, n, row_offset, mode,
                                                int(use_gsum), part, world, rank, ptr(gvec), ptr(scale_dev), ptr(wr),
-                                               ptr(wc), ptr(dg), ptr(out_scale_a), ptr(out_scale_b), _stream()),
+                                               ptr(wc), ptr(dg), ptr(out_scale_a), ptr(out_scale_b), what, _stream()),
           "oneprot_clip_bwd_weights")
 
 

@@ -76,8 +76,16 @@ def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_d
 
 
 def bwd_weights(inv_rowsum, inv_colsum, n, row_offset, mode, use_gsum, part, world, rank, gvec, scale_dev, wr, wc, dg,
-                out_scale_a, out_scale_b):
+                out_scale_a, out_scale_b, what=0):
     CALLS.append("bwd_weights")
+    if what != 0:   # emulate the selective writes by computing everything into temporaries
+        tw = [torch.empty_like(x) for x in (wr, wc, dg, out_scale_a, out_scale_b)]
+        bwd_weights(inv_rowsum, inv_colsum, n, row_offset, mode, use_gsum, part, world, rank, gvec, scale_dev, *tw)
+        if what == 1:
+            wr.copy_(tw[0]); wc.copy_(tw[1]); dg.copy_(tw[2])
+        else:
+            out_scale_a.copy_(tw[3]); out_scale_b.copy_(tw[4])
+        return
     N = inv_rowsum.numel()
     s = float(scale_dev[0])
     g = gvec.double()

@@ -173,10 +173,11 @@ class _GemmChain:
     """Sum of several GEMM terms into one output: fp32 accumulator chained through acc_in /
     acc_out, the last term applies the row scale and writes the final dtype."""
 
-    def __init__(self, M, Nc, out: torch.Tensor, row_scale, n_terms: int):
+    def __init__(self, M, Nc, out: torch.Tensor, row_scale, n_terms: int, push=None):
         self.M, self.Nc, self.out, self.row_scale, self.n_terms = M, Nc, out, row_scale, n_terms
         self.done = 0
         self.acc = None
+        self.push = push          # (owner addresses, rows per owner): last term pushes tiles to their owners
         if n_terms > 1 and out.dtype != torch.float32:
             self.acc = torch.empty(M, out.stride(0), dtype=torch.float32, device=out.device)[:, :Nc]
 
@@ -186,6 +187,12 @@ class _GemmChain:
         f32_out = self.out.dtype == torch.float32
         acc = self.out if f32_out else self.acc
         kw = dict(dot_mat=dot_mat, rowdot_part=rowdot_part)
+        if last and self.push is not None:
+            addrs, rows_per_owner = self.push
+            Kn.gemm_bf16_push(A, B, self.M, self.Nc, K, addrs, rows_per_owner, self.Nc,
+                              acc_in=None if first else acc, row_scale=self.row_scale)
+            self.done += 1
+            return
         if last:
             kw["row_scale"] = self.row_scale
             if f32_out:
@@ -309,8 +316,9 @@ class _ClipLossFunction(torch.autograd.Function):
                 K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
                               wr, wc, dg, sA, sB)
             dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
+            push = comm.db_push_targets(n, d, grad_dtype, rank, W) if (want_b and exchange_b) else None
             dBp = comm.db_buffer(N, d, grad_dtype, dev) if want_b else None
-            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp) if want_b else None
+            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp, push=(push, n) if push else None) if want_b else None
             rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
             last_pass = pi == len(passes) - 1
             ev_rs, dB_async = None, None
@@ -324,7 +332,7 @@ class _ClipLossFunction(torch.autograd.Function):
                 if want_b:                        # dB first: its exchange then hides under the dA GEMM
                     for Ap in ops.a_pieces(A_rows):
                         chain_b.add(Wp, True, Ap, True, rows)
-                    if exchange_b and side is not None and qi == len(panels) - 1:
+                    if exchange_b and side is not None and push is None and qi == len(panels) - 1:
                         evb = main.record_event()
                         with torch.cuda.stream(side):
                             side.wait_event(evb)
@@ -342,7 +350,9 @@ class _ClipLossFunction(torch.autograd.Function):
                             ds_terms.append(("unit", t))
                         else:
                             chain_a.add(Wp, False, Bp, True, N)
-            if want_b and exchange_b:
+            if want_b and exchange_b and push is not None:
+                dBp = comm.finish_pushed_db(n, d, rank, W, last_pass=last_pass)
+            elif want_b and exchange_b:
                 if dB_async is not None:
                     main.wait_event(ev_rs)
                     dB_async.record_stream(main)

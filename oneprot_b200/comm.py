@@ -91,6 +91,10 @@ class LocalComm:
         """Stream on which exchanges may overlap with compute (None: exchanges are synchronous)."""
         return None
 
+    def db_push_targets(self, n, d, dtype, rank, world):
+        """Per-owner destination addresses for the fused GEMM + reduce-scatter push, or None."""
+        return None
+
 
 class DistComm(LocalComm):
     """torch.distributed collectives; gathers first, so the row statistics see all of B at once."""
@@ -259,6 +263,23 @@ class NvlsComm(DistComm):
 
     def db_buffer(self, N, d, dtype, dev):
         return self._view(self._off_db(), (N, d), dtype)
+
+    def db_push_targets(self, n, d, dtype, rank, world):
+        if dtype != torch.bfloat16 or n % 128 or os.environ.get("ONEPROT_NO_PUSH"):
+            return None
+        # owner o keeps one (n x d) slot per source rank inside its dBp region: slot[src] at src*n*d
+        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        return [ptrs[o] + self._off_db() + rank * n * d * 2 for o in range(world)]
+
+    def finish_pushed_db(self, n, d, rank, world, last_pass=True):
+        """All ranks have pushed their tiles: add this rank's W slots (fixed order)."""
+        self._barrier()
+        slots = self._view(self._off_db(), (world * n, d), torch.bfloat16)
+        out = torch.empty(n, d, dtype=torch.bfloat16, device=self.dev)
+        self.K.sum_slots_bf16(slots, world, n * d, out)
+        if not last_pass:
+            self._barrier()
+        return out
 
     def reduce_scatter_db(self, dbp, rank, world, last_pass=True):
         K = self.K

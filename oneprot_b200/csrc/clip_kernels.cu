@@ -410,6 +410,7 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]);
 
 constexpr int GEMM_NS = 4;
 constexpr int GEMM_SMEM = smem_bytes(GEMM_NS, 0);
+constexpr int GEMM_PUSH_SMEM = smem_bytes(GEMM_NS, 2 * 16384);
 
 struct GParams {
   int M, Nc, nK;
@@ -422,13 +423,22 @@ struct GParams {
   const __nv_bfloat16* dot_mat;  // optional: rowdot_part[(nb*2+h)*ldd + m] = <unscaled value row, dot_mat row>
   float* rowdot_part;
   int ld_dot, ldd;
+  int rows_per_owner;            // PUSH: rows of C owned by each GPU (multiple of 128)
 };
 
-template <int A_MN, int B_MN>
+// PUSH: the epilogue does not write a local C but pushes each finished 128-row tile, as bf16,
+// into the memory of the GPU that owns those rows (TMA store over NVLink into a symmetric-memory
+// slot) - the reduce-scatter of the partial dB fused into the GEMM, tile by tile.
+struct OwnerMaps {
+  CUtensorMap m[8];
+};
+
+template <int A_MN, int B_MN, bool PUSH>
 __global__ void __maxnreg__(128)   // 384 x 128 registers: leaves 16 K registers per SM for a co-resident exchange kernel
-gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+            const __grid_constant__ OwnerMaps om, const GParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const Smem s = carve_smem<GEMM_NS, 0>(smem_raw);
+  const Smem s = carve_smem<GEMM_NS, PUSH ? STORE_STAGING_BYTES : 0>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
   const int warp = threadIdx.x >> 5;
   const int tiles = p.nMb * p.nNb;
@@ -479,6 +489,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int lane = lane_id();
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t stage_s = PUSH ? smem_u32(s.staging) + h * 16384 : 0u;
+    const bool store_issuer = (q == 0) && (lane == 0);
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int mb = t / p.nNb, nb = t % p.nNb;
       const int m = mb * BM + q * 32 + lane;
@@ -497,6 +509,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
+        }
+        if (PUSH) {
+          if ((cc & 1) == 0) {
+            if (store_issuer) bulk_wait_read<0>();     // previous TMA store finished reading the staging box
+            named_bar_sync(2 + h, 128);
+          }
+          const int r = q * 32 + lane;
+          const uint32_t line = stage_s + r * 128;
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = v[v8 * 8 + u];
+            const int n = n0 + cc * 32 + v8 * 8;
+            if (p.acc_in && m < p.M && n < p.Nc) {
+              const size_t base = static_cast<size_t>(m) * p.ldc + n;
+              const float4 a0 = *reinterpret_cast<const float4*>(p.acc_in + base);
+              const float4 a1 = *reinterpret_cast<const float4*>(p.acc_in + base + 4);
+              x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
+              x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
+            }
+            const uint32_t slot = static_cast<uint32_t>(((cc & 1) * 4 + v8) ^ (r & 7));
+            st_shared_v4(line + slot * 16, pack_bf16x2(x[0] * rs, x[1] * rs), pack_bf16x2(x[2] * rs, x[3] * rs),
+                         pack_bf16x2(x[4] * rs, x[5] * rs), pack_bf16x2(x[6] * rs, x[7] * rs));
+          }
+          if (cc & 1) {
+            fence_proxy_async();
+            named_bar_sync(2 + h, 128);
+            if (store_issuer) {
+              const int owner = (mb * BM) / p.rows_per_owner;
+              tma_store_2d(&om.m[owner], s.staging + h * 16384, n0 + (cc >> 1) * 64, mb * BM - owner * p.rows_per_owner);
+              bulk_commit();
+            }
+          }
+          continue;
         }
         if (m < p.M) {
           const size_t base = static_cast<size_t>(m) * p.ldc + n0 + cc * 32;
@@ -537,6 +584,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (p.rowdot_part && m < p.M) p.rowdot_part[static_cast<size_t>(nb * 2 + h) * p.ldd + m] = rdot;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (PUSH && store_issuer) bulk_wait<0>();   // all pushed tiles have left before the CTA retires
   }
   kernel_epilogue_dealloc(tmem_base);
 }
@@ -915,6 +963,22 @@ __global__ void mc_reduce_bf16_kernel(const uint4* src_mc, uint4* __restrict__ d
   }
 }
 
+// out[i] = bf16( sum_w slots[w][i] ) with fp32 accumulation in slot order (deterministic); 8 per thread
+__global__ void sum_slots_bf16_kernel(const uint4* __restrict__ slots, int W, size_t n16, uint4* __restrict__ out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < W; ++w) {
+      float f[8];
+      bf16x8_to_float(slots[static_cast<size_t>(w) * n16 + i], f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += f[u];
+    }
+    out[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                        pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 // fp32 -> bf16 limbs: x = h + m + l (each bf16).  side 0 (left operand):  [h h m | h m l]
 //                                                   side 1 (right operand): [h m h | l m h]
 // terms = 3 keeps the first three limb products (h.h + h.m + m.h), terms = 6 all six of order <= 2.
@@ -945,6 +1009,7 @@ __global__ void split_fp32_kernel(const float* __restrict__ x, __nv_bfloat16* __
 namespace {
 
 thread_local std::string g_err;
+op::OwnerMaps g_no_owner_maps{};   // placeholder kernel argument of the non-push GEMM instantiations
 std::atomic<long long> g_launches{0};   // process-wide: backward runs on autograd's thread
 
 int fail(int code, const std::string& msg) {
@@ -1213,14 +1278,54 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_GEMM(AM, BMJ)                                                                       \
   do {                                                                                             \
-    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ>, op::GEMM_SMEM))) return rc;                    \
-    op::gemm_kernel<AM, BMJ><<<grid, op::NUM_THREADS, op::GEMM_SMEM, st>>>(mapA, mapB, p);         \
+    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ, false>, op::GEMM_SMEM))) return rc;             \
+    op::gemm_kernel<AM, BMJ, false><<<grid, op::NUM_THREADS, op::GEMM_SMEM, st>>>(mapA, mapB, g_no_owner_maps, p); \
   } while (0)
   if (!a_mn && !b_mn) LAUNCH_GEMM(0, 0);
   else if (!a_mn && b_mn) LAUNCH_GEMM(0, 1);
   else if (a_mn && !b_mn) LAUNCH_GEMM(1, 0);
   else LAUNCH_GEMM(1, 1);
 #undef LAUNCH_GEMM
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
+                           const float* acc_in, int ld_acc, const float* row_scale, void* const* owner_dst, int owners,
+                           int rows_per_owner, int ld_dst, void* stream) {
+  if (!A || !B || !owner_dst) return fail(ONEPROT_ERR_ARG, "gemm_push: null pointer");
+  if (!a_mn || !b_mn) return fail(ONEPROT_ERR_ARG, "gemm_push: only the dB layout (a_mn = b_mn = 1) is instantiated");
+  if (owners <= 0 || owners > 8 || rows_per_owner <= 0 || rows_per_owner % op::BM || M != owners * rows_per_owner)
+    return fail(ONEPROT_ERR_ARG, "gemm_push: need <= 8 owners and rows_per_owner a multiple of 128 with M = owners * rows_per_owner");
+  if (Nc <= 0 || K <= 0 || Nc % 8 || ld_dst < Nc || ld_dst % 8 || (acc_in && (ld_acc < Nc || ld_acc % 8)))
+    return fail(ONEPROT_ERR_ARG, "gemm_push: bad sizes");
+  if (lda < M || ldb < Nc) return fail(ONEPROT_ERR_ARG, "gemm_push: leading dimension too small");
+  op::GParams p{};
+  p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
+  p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
+  p.acc_in = acc_in; p.ldc = ld_acc; p.row_scale = row_scale; p.rows_per_owner = rows_per_owner;
+  CUtensorMap mapA, mapB;
+  op::OwnerMaps om{};
+  int rc;
+  if ((rc = make_map(&mapA, A, M, K, lda, 64))) return rc;
+  if ((rc = make_map(&mapB, B, Nc, K, ldb, 64))) return rc;
+  for (int o = 0; o < owners; ++o)
+    if ((rc = make_map(&om.m[o], owner_dst[o], Nc, rows_per_owner, ld_dst, op::BM))) return rc;
+  const int grid = std::min(num_sms(), p.nMb * p.nNb);
+  if ((rc = prep_kernel(op::gemm_kernel<1, 1, true>, op::GEMM_PUSH_SMEM))) return rc;
+  op::gemm_kernel<1, 1, true><<<grid, op::NUM_THREADS, op::GEMM_PUSH_SMEM, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, om, p);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_sum_slots_bf16(const void* slots, int W, size_t count, void* out, void* stream) {
+  if (!slots || !out || W <= 0 || count == 0 || count % 8 || (reinterpret_cast<uintptr_t>(slots) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(ONEPROT_ERR_ARG, "sum_slots_bf16: count must be a multiple of 8, pointers 16-byte aligned");
+  const size_t n16 = count / 8;
+  const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+  op::sum_slots_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(slots), W, n16, static_cast<uint4*>(out));
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

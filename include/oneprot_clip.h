@@ -71,6 +71,32 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
                           const float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
                           void* stream);
 
+/* Same kernel with the all-gather of the second operand FUSED in (single NVSwitch node): the
+ * spare warp of every CTA pushes a slice of this rank's rows (src, rows_per_rank x d bf16) through
+ * the NVLink multicast alias dst_mc of their place inside B_all, in `chunks` row chunks, each
+ * followed by a multicast flag; the TMA producer of every GPU waits for the flag of a column
+ * block (flags == epoch) before loading it, so tiles of chunks that have landed are computed while
+ * later chunks are still in flight.  The norm maxima (`stats`, local rows only) travel the same
+ * way; their global maximum is written to stats_out[0..1] for the later kernels.
+ * flags/flags_mc: u32[world][chunks + 1]; stats_all/stats_mc: float[world][4]; counters:
+ * u32[chunks], zero-initialised once.  All *_mc pointers alias symmetric memory.
+ * Replaces gather_features (loss.py:19-46) for the forward, overlapped with get_logits. */
+typedef struct {
+  const void* src;
+  void* dst_mc;
+  unsigned int* counters;
+  unsigned int* flags_mc;
+  const unsigned int* flags;
+  float* stats_mc;
+  const float* stats_all;
+  float* stats_out;
+  unsigned int epoch;
+  int rank, world, chunks, rows_per_rank;
+} oneprot_ag_t;
+int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
+                             const float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
+                             size_t scratch_bytes, void* stream);
+
 /* Loss value + softmax normalisers from complete sums (all length N, global index order):
  *   loss_out[0] = this rank's return value (MODE_GLOBAL: mean over all N; MODE_LOCAL: mean over
  *   rows/cols [row_offset, row_offset+n)), fp32;  inv_rowsum/inv_colsum[k] = 1/sum;
@@ -139,11 +165,12 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
  * 128 x 256 tile (value = row_scale[m] * (acc + acc_in[m*ld_acc + n]), bf16) is TMA-stored into
  * owner_dst[m / rows_per_owner] (row-major rows_per_owner x Nc, leading dimension ld_dst; peer
  * memory of a symmetric allocation).  The owner then adds its slots (oneprot_sum_slots_bf16)
- * after a barrier.  Replaces the reduce-scatter SUM in the backward of
+ * after a barrier.  Rank r starts with the rows of owner r+1 so that no owner is the target of
+ * two ranks at once.  Replaces the reduce-scatter SUM in the backward of
  * torch.distributed.nn.all_gather (loss.py:32-33) overlapped with the dB contraction. */
 int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
                            const float* acc_in, int ld_acc, const float* row_scale, void* const* owner_dst, int owners,
-                           int rows_per_owner, int ld_dst, void* stream);
+                           int my_rank, int rows_per_owner, int ld_dst, void* stream);
 /* out[i] = bf16(sum_w slots[w*count + i]), fp32 accumulation in slot order (deterministic). */
 int oneprot_sum_slots_bf16(const void* slots, int W, size_t count, void* out, void* stream);
 

@@ -13,6 +13,14 @@ LIB_PATH = os.path.join(HERE, "liboneprot_clip.so")
 _vp, _fp, _ip = C.c_void_p, C.c_void_p, C.c_void_p   # all raw device pointers travel as void*
 _i, _f, _sz = C.c_int, C.c_float, C.c_size_t
 
+class AgDesc(C.Structure):
+    """oneprot_ag_t of include/oneprot_clip.h"""
+    _fields_ = [("src", C.c_void_p), ("dst_mc", C.c_void_p), ("counters", C.c_void_p), ("flags_mc", C.c_void_p),
+                ("flags", C.c_void_p), ("stats_mc", C.c_void_p), ("stats_all", C.c_void_p), ("stats_out", C.c_void_p),
+                ("epoch", C.c_uint), ("rank", C.c_int), ("world", C.c_int), ("chunks", C.c_int),
+                ("rows_per_rank", C.c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol include/oneprot_clip.h declares
 SIGNATURES = {
     "oneprot_abi_version": (_i, []),
@@ -24,13 +32,14 @@ SIGNATURES = {
     "oneprot_clip_rowstats": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "oneprot_clip_fwd_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_clip_fwd_sums": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "oneprot_clip_fwd_sums_ag": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, C.POINTER(AgDesc), _fp, _fp, _vp, _sz, _vp]),
     "oneprot_clip_loss_finalize": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _ip, _vp, _vp]),
     "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _vp]),
     "oneprot_clip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_rowdot_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_gemm_bf16_ex": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _fp, _vp, _i, _fp, _vp]),
-    "oneprot_gemm_bf16_push": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _i, _fp, C.POINTER(C.c_void_p), _i, _i, _i, _vp]),
+    "oneprot_gemm_bf16_push": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _i, _fp, C.POINTER(C.c_void_p), _i, _i, _i, _i, _vp]),
     "oneprot_sum_slots_bf16": (_i, [_vp, _i, _sz, _vp, _vp]),
     "oneprot_rowdot_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _fp, _vp]),
     "oneprot_sum_f32": (_i, [_fp, _i, _fp, _vp]),

@@ -188,8 +188,8 @@ class _GemmChain:
         acc = self.out if f32_out else self.acc
         kw = dict(dot_mat=dot_mat, rowdot_part=rowdot_part)
         if last and self.push is not None:
-            addrs, rows_per_owner = self.push
-            Kn.gemm_bf16_push(A, B, self.M, self.Nc, K, addrs, rows_per_owner, self.Nc,
+            addrs, my_rank, rows_per_owner = self.push
+            Kn.gemm_bf16_push(A, B, self.M, self.Nc, K, addrs, my_rank, rows_per_owner, self.Nc,
                               acc_in=None if first else acc, row_scale=self.row_scale)
             self.done += 1
             return
@@ -224,7 +224,11 @@ class _ClipLossFunction(torch.autograd.Function):
         B_all, sums = st["B_all"], st["sums"]
         K.rowstats(ops.A, st["stats_rows"], st["stats_off"], sums[2 * N + off:2 * N + off + n], st["stats"])
         stats = comm.global_stats(st)                  # one reference G on every rank
-        K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N])
+        if st.get("ag") is not None:     # all-gather fused into the forward kernel (NVLS provider)
+            K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N], ag=st["ag"])
+            stats = st["stats_glob"]     # global maxima, written by the kernel
+        else:
+            K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N])
         sums = comm.complete_sums(st)
         colsum, rowsum_all, diag_all = sums[0:N], sums[N:2 * N], sums[2 * N:3 * N]
 
@@ -318,7 +322,7 @@ class _ClipLossFunction(torch.autograd.Function):
             dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
             push = comm.db_push_targets(n, d, grad_dtype, rank, W) if (want_b and exchange_b) else None
             dBp = comm.db_buffer(N, d, grad_dtype, dev) if want_b else None
-            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp, push=(push, n) if push else None) if want_b else None
+            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp, push=(push, rank, n) if push else None) if want_b else None
             rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
             last_pass = pi == len(passes) - 1
             ev_rs, dB_async = None, None

@@ -171,7 +171,8 @@ class NvlsComm(DistComm):
         self.small_floats = (self.SUMS_AT + 3 * N + 63) // 64 * 64
         self.small_bytes = self.small_floats * 4
         self.db_bytes = self._al(N * cap[2] * 4)
-        total = 2 * self.bg_bytes + 2 * self.small_bytes + self.db_bytes
+        self.ctl_bytes = 4096           # flags u32[W][9] @0, stats_all f32[W][4] @1024, counters u32[8] @2048
+        total = 2 * self.bg_bytes + 2 * self.small_bytes + self.db_bytes + self.ctl_bytes
         buf = self.symm.empty(total, dtype=torch.uint8, device=self.dev)
         self.hdl = self.symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
         if not self.hdl.multicast_ptr:
@@ -210,6 +211,9 @@ class NvlsComm(DistComm):
     def _off_db(self):
         return 2 * self.bg_bytes + 2 * self.small_bytes
 
+    def _off_ctl(self):
+        return 2 * self.bg_bytes + 2 * self.small_bytes + self.db_bytes
+
     # ---- forward -------------------------------------------------------------------------
     def begin_forward(self, ops, rank, world):
         K = self.K
@@ -219,16 +223,30 @@ class NvlsComm(DistComm):
         p = self.calls & 1
         self.calls += 1
         self.gen[p] = self.calls
-        # second operand: one multimem.st pass puts this rank's rows into every GPU's Bg[p]
         Bg = self._view(self._off_bg(p), (N, dk), torch.bfloat16)
-        K.mc_store(ops.B, self.mc + self._off_bg(p) + rank * n * dk * 2, n * dk * 2)
         small = self._view(self._off_small(p), (self.SUMS_AT + 3 * N,), torch.float32)
         small.zero_()
-        return dict(B_all=Bg, sums=small[self.SUMS_AT:self.SUMS_AT + 3 * N], stats=small[self.STATS_AT:self.STATS_AT + 4],
-                    stats_rows=ops.B, stats_off=0, token=(p, self.calls), p=p, N=N)
+        st = dict(B_all=Bg, sums=small[self.SUMS_AT:self.SUMS_AT + 3 * N], stats=small[self.STATS_AT:self.STATS_AT + 4],
+                  stats_rows=ops.B, stats_off=0, token=(p, self.calls), p=p, N=N, ag=None)
+        chunks = next((c for c in (8, 4, 2, 1) if n % (c * 256) == 0), 0)
+        if chunks and not os.environ.get("ONEPROT_NO_FUSED_AG"):
+            # the gather is fused into the forward kernel: nothing to launch here
+            base = int(self.hdl.buffer_ptrs[rank]) + self._off_ctl()
+            mcb = self.mc + self._off_ctl()
+            st["stats_glob"] = torch.empty(4, dtype=torch.float32, device=self.dev)
+            st["ag"] = dict(src=ops.B.data_ptr(), dst_mc=self.mc + self._off_bg(p) + rank * n * dk * 2,
+                            counters=base + 2048, flags_mc=mcb, flags=base, stats_mc=mcb + 1024, stats_all=base + 1024,
+                            stats_out=st["stats_glob"].data_ptr(), epoch=self.calls & 0x7fffffff, rank=rank, world=world,
+                            chunks=chunks, rows_per_rank=n)
+        else:
+            # second operand: one multimem.st pass puts this rank's rows into every GPU's Bg[p]
+            K.mc_store(ops.B, self.mc + self._off_bg(p) + rank * n * dk * 2, n * dk * 2)
+        return st
 
     def global_stats(self, st):
         # (the caller ran rowstats on the LOCAL rows: stats holds this rank's maxima)
+        if st.get("ag") is not None:
+            return st["stats"]                    # published and maximised inside the forward kernel
         self._barrier()                           # B rows + local maxima of every rank are in place
         out = torch.empty(4, dtype=torch.float32, device=self.dev)
         self.K.mc_allreduce_f32(self.mc + self._off_small(st["p"]) + self.STATS_AT * 4, out, 4, 1)
@@ -265,7 +283,10 @@ class NvlsComm(DistComm):
         return self._view(self._off_db(), (N, d), dtype)
 
     def db_push_targets(self, n, d, dtype, rank, world):
-        if dtype != torch.bfloat16 or n % 128 or os.environ.get("ONEPROT_NO_PUSH"):
+        # Measured on 8 x B200 (N = 32768): the pull-reduce on a side stream under the dA GEMM gives a
+        # shorter step (0.98 ms) than pushing tiles from the dB GEMM epilogue (1.08 ms), so the push
+        # variant is opt-in.
+        if dtype != torch.bfloat16 or n % 128 or not os.environ.get("ONEPROT_PUSH"):
             return None
         # owner o keeps one (n x d) slot per source rank inside its dBp region: slot[src] at src*n*d
         ptrs = [int(x) for x in self.hdl.buffer_ptrs]

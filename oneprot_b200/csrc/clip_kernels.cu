@@ -186,13 +186,63 @@ struct SParams {
   const float* dg;
   __nv_bfloat16* Wz;
   int ldw;
+  // fused all-gather of the second operand (forward only; ag_src == nullptr: off).  The spare warp
+  // of every CTA pushes a slice of this rank's rows through the NVLink multicast alias and raises
+  // per-chunk flags; the TMA producer waits for the flag of a column block before loading it.
+  const uint4* ag_src;            // this rank's rows (local)
+  uint4* ag_dst_mc;               // multicast alias of this rank's rows inside the gathered operand
+  unsigned int* ag_counters;      // local, [ag_chunks], zero between launches
+  unsigned int* ag_flags_mc;      // multicast alias of flags[W][ag_chunks + 1]
+  const unsigned int* ag_flags;   // local copy of the flags
+  float* ag_stats_mc;             // multicast alias of stats_all[W][4]
+  const float* ag_stats;          // local copy
+  float* stats_out;               // global maxima written for the later kernels (2 floats)
+  unsigned int ag_epoch;
+  int ag_rank, ag_world, ag_chunks, ag_chunk16, ag_rows, ag_bpc;   // chunk16: 16-byte vectors per chunk; bpc: column blocks per chunk
 };
+
+__device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int epoch) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  if (v == epoch) return;
+  const long long t0 = clock64();
+  do {
+    __nanosleep(64);
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (clock64() - t0 > ONEPROT_WAIT_TRAP_CYCLES) __trap();
+  } while (v != epoch);
+}
+
+// logical column-block index -> actual column block: chunk-major (arrival order), own rank first
+__device__ __forceinline__ int map_jb(const SParams& p, int jl) {
+  if (!p.ag_src) return jl;
+  const int per = p.ag_world * p.ag_bpc;
+  const int c = jl / per, rem = jl % per;
+  const int r = (rem / p.ag_bpc + p.ag_rank) % p.ag_world;
+  return (r * p.ag_rows) / BN + c * p.ag_bpc + rem % p.ag_bpc;
+}
 
 __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& negG) {
   const float s = __ldg(p.scale);
   c = s * LOG2E;
-  const float U = fabsf(c) * sqrtf(__ldg(p.stats) * __ldg(p.stats + 1));
+  float ma, mb;
+  if (p.ag_src) {
+    ma = 0.f; mb = 0.f;
+    for (int r = 0; r < p.ag_world; ++r) {
+      wait_flag(p.ag_flags + r * (p.ag_chunks + 1) + p.ag_chunks, p.ag_epoch);
+      ma = fmaxf(ma, *(volatile const float*)(p.ag_stats + r * 4));
+      mb = fmaxf(mb, *(volatile const float*)(p.ag_stats + r * 4 + 1));
+    }
+  } else {
+    ma = __ldg(p.stats);
+    mb = __ldg(p.stats + 1);
+  }
+  const float U = fabsf(c) * sqrtf(ma * mb);
   negG = -fmaxf(0.f, U - G_MARGIN);
+  if (p.ag_src && p.stats_out && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32) {
+    p.stats_out[0] = ma;
+    p.stats_out[1] = mb;
+  }
 }
 
 enum { EPI_FWD = 0, EPI_DZ = 1 };
@@ -221,8 +271,15 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (lane_id() == 0) {
       PipeState<NS> ps;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int jb = item / p.nChunks, ch = item % p.nChunks;
+        const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
+        if (EPI == EPI_FWD && p.ag_src) {
+          // columns [256 jb, 256 jb + 256) belong to one chunk of one rank: wait until it has landed
+          const int col0 = jb * BN;
+          const int r = col0 / p.ag_rows;
+          const int c = ((col0 - r * p.ag_rows) / BN) / p.ag_bpc;
+          wait_flag(p.ag_flags + r * (p.ag_chunks + 1) + c, p.ag_epoch);
+        }
         for (int ib = ch * p.CI; ib < ib1; ++ib) {
           for (int kb = 0; kb < p.nK; ++kb) {
             mbar_wait(&s.tail->empty[ps.stage], ps.phase ^ 1);
@@ -262,6 +319,38 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
   } else if (warp < EPI_WARP0) {
     reg_dealloc<56>();
+    if (EPI == EPI_FWD && warp == 3 && p.ag_src) {
+      // ---------------------------------------------- all-gather push (spare warp)
+      const int lane = lane_id();
+      const int fl = p.ag_rank * (p.ag_chunks + 1);
+      if (blockIdx.x == 0 && lane == 0) {   // this rank's norm maxima, then their flag
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.ag_stats_mc + p.ag_rank * 4), "f"(p.stats[0]) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.ag_stats_mc + p.ag_rank * 4 + 1), "f"(p.stats[1]) : "memory");
+        __threadfence_system();
+        asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.ag_flags_mc + fl + p.ag_chunks), "r"(p.ag_epoch) : "memory");
+      }
+      const int per = (p.ag_chunk16 + gridDim.x - 1) / gridDim.x;
+      const int lo = min(p.ag_chunk16, static_cast<int>(blockIdx.x) * per), hi = min(p.ag_chunk16, lo + per);
+      for (int c = 0; c < p.ag_chunks; ++c) {
+        const size_t base = static_cast<size_t>(c) * p.ag_chunk16;
+        for (int i = lo + lane; i < hi; i += 32) {
+          const uint4 v = p.ag_src[base + i];
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.ag_dst_mc + base + i), "r"(v.x),
+                       "r"(v.y), "r"(v.z), "r"(v.w)
+                       : "memory");
+        }
+        __threadfence_system();             // this lane's stores are performed system-wide
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned int prev = atomicAdd(p.ag_counters + c, 1u);
+          if (prev == gridDim.x - 1) {      // every CTA has pushed (and fenced) its slice of chunk c
+            p.ag_counters[c] = 0;
+            __threadfence_system();
+            asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.ag_flags_mc + fl + c), "r"(p.ag_epoch) : "memory");
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------ epilogue (8 warps)
     reg_alloc<224>();
@@ -281,7 +370,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t stage_s = smem_u32(s.staging) + h * 16384;
     const bool store_issuer = (q == 0) && (lane == 0);
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int jb = item / p.nChunks, ch = item % p.nChunks;
+      const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
       const int j0 = jb * BN + h * 128;   // first column this thread sees
       if (EPI == EPI_FWD) {
@@ -424,6 +513,7 @@ struct GParams {
   float* rowdot_part;
   int ld_dot, ldd;
   int rows_per_owner;            // PUSH: rows of C owned by each GPU (multiple of 128)
+  int mb_rot;                    // PUSH: row-block rotation so that ranks push to different owners at any time
 };
 
 // PUSH: the epilogue does not write a local C but pushes each finished 128-row tile, as bf16,
@@ -448,7 +538,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     if (lane_id() == 0) {
       PipeState<GEMM_NS> ps;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int mb = t / p.nNb, nb = t % p.nNb;
+        const int mb = (t / p.nNb + p.mb_rot) % p.nMb, nb = t % p.nNb;
         for (int kb = 0; kb < p.nK; ++kb) {
           mbar_wait(&s.tail->empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = s.stages + ps.stage * STAGE_BYTES;
@@ -492,7 +582,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint32_t stage_s = PUSH ? smem_u32(s.staging) + h * 16384 : 0u;
     const bool store_issuer = (q == 0) && (lane == 0);
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int mb = t / p.nNb, nb = t % p.nNb;
+      const int mb = (t / p.nNb + p.mb_rot) % p.nMb, nb = t % p.nNb;
       const int m = mb * BM + q * 32 + lane;
       const int n0 = nb * BN + h * 128;
       const float rs = (p.row_scale && m < p.M) ? __ldg(p.row_scale + m) : 1.f;
@@ -1153,6 +1243,12 @@ size_t oneprot_clip_fwd_scratch_bytes(int n, int N) {
 int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
                           const float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
                           void* stream) {
+  return oneprot_clip_fwd_sums_ag(A, B_all, n, N, d, scale_dev, stats, nullptr, rowsum, colsum, scratch, scratch_bytes, stream);
+}
+
+int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
+                             const float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
+                             size_t scratch_bytes, void* stream) {
   if (!A || !B_all || !scale_dev || !stats || !rowsum || !colsum || !scratch) return fail(ONEPROT_ERR_ARG, "fwd_sums: null pointer");
   if (n <= 0 || N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "fwd_sums: need n, N > 0 and d a positive multiple of 8");
   if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "fwd_sums: scratch too small");
@@ -1164,12 +1260,32 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
   p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
   p.rowpart = static_cast<float*>(scratch);
   p.colpart = p.rowpart + 2 * static_cast<size_t>(p.nJ) * p.ldr;
+  if (ag) {
+    const int rows = ag->rows_per_rank, W = ag->world, CH = ag->chunks;
+    if (!ag->src || !ag->dst_mc || !ag->counters || !ag->flags_mc || !ag->flags || !ag->stats_mc || !ag->stats_all || !ag->stats_out)
+      return fail(ONEPROT_ERR_ARG, "fwd_sums_ag: null pointer in oneprot_ag_t");
+    if (W <= 0 || W > 8 || ag->rank < 0 || ag->rank >= W || rows * W != N || CH <= 0 || rows % (CH * op::BN))
+      return fail(ONEPROT_ERR_ARG, "fwd_sums_ag: need N = world * rows_per_rank and rows_per_rank a multiple of chunks * 256");
+    p.ag_src = static_cast<const uint4*>(ag->src);
+    p.ag_dst_mc = static_cast<uint4*>(ag->dst_mc);
+    p.ag_counters = ag->counters;
+    p.ag_flags_mc = ag->flags_mc;
+    p.ag_flags = ag->flags;
+    p.ag_stats_mc = ag->stats_mc;
+    p.ag_stats = ag->stats_all;
+    p.stats_out = ag->stats_out;
+    p.ag_epoch = ag->epoch;
+    p.ag_rank = ag->rank; p.ag_world = W; p.ag_chunks = CH; p.ag_rows = rows;
+    p.ag_bpc = rows / CH / op::BN;
+    p.ag_chunk16 = static_cast<int>(static_cast<size_t>(rows / CH) * d * 2 / 16);
+  }
   CUtensorMap mapA, mapB;
   int rc;
   if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
   if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
   constexpr int smem = op::SCfg<op::EPI_FWD>::SMEM;
   if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD>, smem))) return rc;
+  // fused gather: every CTA of the grid pushes a slice, so the grid must be fully co-resident (it is: <= #SMs)
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
   op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   ++g_launches;
@@ -1293,8 +1409,9 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
 
 int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
                            const float* acc_in, int ld_acc, const float* row_scale, void* const* owner_dst, int owners,
-                           int rows_per_owner, int ld_dst, void* stream) {
+                           int my_rank, int rows_per_owner, int ld_dst, void* stream) {
   if (!A || !B || !owner_dst) return fail(ONEPROT_ERR_ARG, "gemm_push: null pointer");
+  if (my_rank < 0 || my_rank >= owners) return fail(ONEPROT_ERR_ARG, "gemm_push: my_rank out of range");
   if (!a_mn || !b_mn) return fail(ONEPROT_ERR_ARG, "gemm_push: only the dB layout (a_mn = b_mn = 1) is instantiated");
   if (owners <= 0 || owners > 8 || rows_per_owner <= 0 || rows_per_owner % op::BM || M != owners * rows_per_owner)
     return fail(ONEPROT_ERR_ARG, "gemm_push: need <= 8 owners and rows_per_owner a multiple of 128 with M = owners * rows_per_owner");
@@ -1305,6 +1422,7 @@ int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int 
   p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
   p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
   p.acc_in = acc_in; p.ldc = ld_acc; p.row_scale = row_scale; p.rows_per_owner = rows_per_owner;
+  p.mb_rot = ((my_rank + 1) % owners) * (rows_per_owner / op::BM);   // start with the next rank's rows
   CUtensorMap mapA, mapB;
   op::OwnerMaps om{};
   int rc;

@@ -63,8 +63,9 @@ def fwd_scratch_bytes(n: int, N: int) -> int:
     return int(_lib.load().oneprot_clip_fwd_scratch_bytes(n, N))
 
 
-def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None):
-    """rowsum[i] = sum_j e_ij, colsum[j] = sum_i e_ij for the n x N logit panel (never stored)."""
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
+    """rowsum[i] = sum_j e_ij, colsum[j] = sum_i e_ij for the n x N logit panel (never stored).
+    ag: optional dict describing the fused all-gather (see oneprot_ag_t)."""
     _need_cuda(A, B_all, scale_dev, stats, rowsum, colsum)
     _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
     n, d = A.shape
@@ -72,9 +73,15 @@ def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None):
     need = fwd_scratch_bytes(n, N)
     if scratch is None or scratch.numel() * scratch.element_size() < need:
         scratch = torch.empty(need, dtype=torch.uint8, device=A.device)
-    check(_lib.load().oneprot_clip_fwd_sums(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(stats), ptr(rowsum),
-                                            ptr(colsum), ptr(scratch), scratch.numel() * scratch.element_size(),
-                                            _stream()), "oneprot_clip_fwd_sums")
+    desc = None
+    if ag is not None:
+        desc = _lib.AgDesc(ag["src"], ag["dst_mc"], ag["counters"], ag["flags_mc"], ag["flags"], ag["stats_mc"],
+                           ag["stats_all"], ag["stats_out"], ag["epoch"], ag["rank"], ag["world"], ag["chunks"],
+                           ag["rows_per_rank"])
+    check(_lib.load().oneprot_clip_fwd_sums_ag(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(stats),
+                                               C.byref(desc) if desc is not None else None, ptr(rowsum), ptr(colsum),
+                                               ptr(scratch), scratch.numel() * scratch.element_size(), _stream()),
+          "oneprot_clip_fwd_sums_ag")
     return scratch
 
 
@@ -212,14 +219,14 @@ def mc_reduce_bf16(src_mc_addr: int, dst, nbytes: int):
           "oneprot_mc_reduce_bf16")
 
 
-def gemm_bf16_push(A, B, M: int, Nc: int, K: int, owner_dst_addrs, rows_per_owner: int, ld_dst: int, *, acc_in=None,
-                   row_scale=None):
+def gemm_bf16_push(A, B, M: int, Nc: int, K: int, owner_dst_addrs, my_rank: int, rows_per_owner: int, ld_dst: int, *,
+                   acc_in=None, row_scale=None):
     """dB-layout GEMM (a_mn = b_mn = 1) whose tiles are pushed to their owners; see oneprot_gemm_bf16_push."""
     _need_cuda(A, B, acc_in, row_scale)
     arr = (C.c_void_p * len(owner_dst_addrs))(*[C.c_void_p(a) for a in owner_dst_addrs])
     check(_lib.load().oneprot_gemm_bf16_push(ptr(A), A.stride(0), 1, ptr(B), B.stride(0), 1, M, Nc, K, ptr(acc_in),
                                              acc_in.stride(0) if acc_in is not None else 0, ptr(row_scale), arr,
-                                             len(owner_dst_addrs), rows_per_owner, ld_dst, _stream()),
+                                             len(owner_dst_addrs), my_rank, rows_per_owner, ld_dst, _stream()),
           "oneprot_gemm_bf16_push")
 
 

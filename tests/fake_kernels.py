@@ -47,7 +47,7 @@ def fwd_scratch_bytes(n, N):
     return 16
 
 
-def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None):
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
     CALLS.append("fwd_sums")
     c, G = _G(scale_dev, stats)
     E = torch.exp2(c * (A.double() @ B_all.double().T) - G)

@@ -7,10 +7,12 @@
 
 namespace op {
 
-// Spin bound for mbarrier waits.  A protocol bug then traps (reported as a launch failure)
-// instead of hanging the GPU.  ~2^31 cycles ~ 1-2 s, far above any legitimate wait here.
+// Spin bound for mbarrier / flag waits.  A protocol bug then traps (reported as a launch failure)
+// instead of hanging the GPU for ever.  With the all-gather fused into the forward kernel a wait
+// can legitimately last as long as the slowest rank is late (host jitter, first-call set-up), and
+// every intra-kernel wait inherits that delay, so the bound is ~2^37 cycles (about a minute).
 #ifndef ONEPROT_WAIT_TRAP_CYCLES
-#define ONEPROT_WAIT_TRAP_CYCLES (1ll << 31)
+#define ONEPROT_WAIT_TRAP_CYCLES (1ll << 37)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -28,7 +28,7 @@ tot = sum(v[1] for v in agg.values())
 unit = rows[0]["Metric Unit"]
 with open(os.path.join(out, f"{tag}_launches_summary.txt"), "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, {len(rows)} launches of "
-            f"`python bench.py --steps 3 --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare SHARES)\n")
+            f"`python bench.py --steps N --warmup 3 --no-cpu-baseline` (cold-cache, serialised: compare SHARES)\n")
     f.write(f"# total {tot/1e6:.3f} ms ({unit})\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{v[1]/1e6:10.3f} ms {v[0]:5d}x {100*v[1]/tot:6.2f}%  avg {v[1]/v[0]/1e3:9.1f} us  {k}\n")
@@ -57,14 +57,17 @@ if os.path.exists(rep):
     # per-launch DRAM traffic keyed the way bench.py names the kernels
     names = {"clip_s_kernel<0>": "clip_s_kernel<FWD> (logits + exp-sums)",
              "clip_s_kernel<1>": "clip_s_kernel<DZ> (logits recompute + dL/dZ panel)",
-             "gemm_kernel<0, 1>": "gemm_kernel<K,MN> (dA = Wz . B)",
-             "gemm_kernel<1, 1>": "gemm_kernel<MN,MN> (dB = Wz^T . A)"}
+             "gemm_kernel<0, 1": "gemm_kernel<K,MN> (dA = Wz . B)",
+             "gemm_kernel<1, 1": "gemm_kernel<MN,MN> (dB = Wz^T . A)"}
     ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    traffic = {}
+    tpath = os.path.join(out, "ncu_traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    fresh = set()
     for row in r[2:]:
         for short, long in names.items():
-            if short in row[ki] and long not in traffic:
+            if short in row[ki] and long not in fresh:
+                fresh.add(long)
                 traffic[long] = float(row[ri]) * scale[units[ri]] + float(row[wi]) * scale[units[wi]]
     with open(os.path.join(out, "ncu_traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)

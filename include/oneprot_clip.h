@@ -51,7 +51,8 @@ void oneprot_launch_count_reset(void);
 /* ---- forward ------------------------------------------------------------------------------ */
 
 /* Row statistics: diag[i] = <a_i, b_{row_offset+i}> (fp32), stats[0] = max_i |a_i|^2,
- * stats[1] = max_j |b_j|^2 over B_all (atomic max; caller zero-initialises stats[0..1]).
+ * stats[1] = max_j |b_j|^2 over B_all (atomic max; stats has FOUR floats, all zero-initialised by
+ * the caller; [2..3] belong to the max pass of oneprot_clip_fwd_sums).
  * Replaces nothing 1:1 - it supplies the label logits that F.cross_entropy gathers
  * (loss.py:109-112 with labels from get_ground_truth, loss.py:72-83). */
 int oneprot_clip_rowstats(const void* A, const void* B_all, int n, int N, int d, int row_offset,
@@ -65,10 +66,14 @@ size_t oneprot_clip_fwd_scratch_bytes(int n, int N);
  *   rowsum[i] = sum_j e_ij (complete for this rank's rows)  and
  *   colsum[j] = sum_{i in panel} e_ij (partial over ranks; sum them across ranks).
  * Replaces get_logits (loss.py:85-101) + the log_softmax half of F.cross_entropy (loss.py:109-112).
- * scale_dev: device pointer to the fp32 logit_scale; stats: as written by rowstats (after a
- * cross-rank max when world_size > 1). */
+ * scale_dev: device pointer to the fp32 logit_scale; stats: FOUR floats, [0..1] as written by
+ * rowstats (after a cross-rank max when world_size > 1), [2..3] zero on entry.
+ * Robust tier: when n == N (whole matrix on this GPU) and |c| max|a| max|b| > 100 a max pass
+ * (same tensor-core mainloop, max epilogue) first writes the exact maximum logit to stats[2] and
+ * sets stats[3] = 1; every later kernel then uses G = max(0, stats[2] - 100).  The pass is always
+ * enqueued and returns immediately when the bound is rigorous (no host synchronisation). */
 int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
-                          const float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
+                          float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
                           void* stream);
 
 /* Same kernel with the all-gather of the second operand FUSED in (single NVSwitch node): the
@@ -94,7 +99,7 @@ typedef struct {
   int rank, world, chunks, rows_per_rank;
 } oneprot_ag_t;
 int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
-                             const float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
+                             float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
                              size_t scratch_bytes, void* stream);
 
 /* Loss value + softmax normalisers from complete sums (all length N, global index order):

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liboneprot_clip.so")
+# ONEPROT_LIB overrides the library path (A/B timing of kernel variants during development)
+LIB_PATH = os.environ.get("ONEPROT_LIB") or os.path.join(HERE, "liboneprot_clip.so")
 
 _vp, _fp, _ip = C.c_void_p, C.c_void_p, C.c_void_p   # all raw device pointers travel as void*
 _i, _f, _sz = C.c_int, C.c_float, C.c_size_t

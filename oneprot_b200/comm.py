@@ -233,7 +233,7 @@ class NvlsComm(DistComm):
             # the gather is fused into the forward kernel: nothing to launch here
             base = int(self.hdl.buffer_ptrs[rank]) + self._off_ctl()
             mcb = self.mc + self._off_ctl()
-            st["stats_glob"] = torch.empty(4, dtype=torch.float32, device=self.dev)
+            st["stats_glob"] = torch.zeros(4, dtype=torch.float32, device=self.dev)
             st["ag"] = dict(src=ops.B.data_ptr(), dst_mc=self.mc + self._off_bg(p) + rank * n * dk * 2,
                             counters=base + 2048, flags_mc=mcb, flags=base, stats_mc=mcb + 1024, stats_all=base + 1024,
                             stats_out=st["stats_glob"].data_ptr(), epoch=self.calls & 0x7fffffff, rank=rank, world=world,

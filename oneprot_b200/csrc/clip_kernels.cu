@@ -239,13 +239,16 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
   }
   const float U = fabsf(c) * sqrtf(ma * mb);
   negG = -fmaxf(0.f, U - G_MARGIN);
+  // exact maximum logit from the max pass (single-GPU robust tier): a tighter reference than the
+  // Cauchy-Schwarz bound when the bound alone would push every term below 2^-126
+  if (!p.ag_src && p.stats[3] != 0.f) negG = -fmaxf(0.f, p.stats[2] - G_MARGIN);
   if (p.ag_src && p.stats_out && blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32) {
     p.stats_out[0] = ma;
     p.stats_out[1] = mb;
   }
 }
 
-enum { EPI_FWD = 0, EPI_DZ = 1 };
+enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2 };
 
 template <int EPI>
 struct SCfg {
@@ -259,6 +262,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const __grid_constant__ CUtensorMap mapW, const SParams p) {
   constexpr int NS = SCfg<EPI>::NS;
+  if (EPI == EPI_MAX) {
+    // the max pass is always enqueued but does work only when the norm bound is not rigorous
+    const float U = fabsf(__ldg(p.scale) * LOG2E) * sqrtf(__ldg(p.stats) * __ldg(p.stats + 1));
+    if (U <= G_MARGIN) return;     // uniform over the grid, before any barrier / TMEM allocation
+  }
   extern __shared__ uint8_t smem_raw[];
   const Smem s = carve_smem<NS, SCfg<EPI>::STAGING>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
@@ -360,9 +368,11 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int lane = lane_id();
     const int r = q * 32 + lane; // row inside the tile
     float c, negG;
-    load_c_and_G(p, c, negG);
+    if (EPI == EPI_MAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
+    else load_c_and_G(p, c, negG);
     int acc = 0;
     uint32_t acc_phase = 0;
+    float xmax = 0.f;               // EPI_MAX: running max(0, x) of this thread
 
     float colacc[EPI == EPI_FWD ? 128 : 1];
     // DZ: bf16 staging of 64 columns of this warp group's half tile = one SWIZZLE_128B box {64 cols, 128 rows}
@@ -376,7 +386,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (EPI == EPI_FWD) {
 #pragma unroll
         for (int k = 0; k < 128; ++k) colacc[k] = 0.f;
-      } else {
+      } else if (EPI == EPI_DZ) {
         // stage the per-column weights of this item's 256 columns
         named_bar_sync(1, EPI_THREADS);
         const int t = threadIdx.x - EPI_WARP0 * 32;
@@ -399,16 +409,38 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
         float rsum = 0.f;
+        // DZ keeps no per-column accumulators, so the whole 128-column row slice fits in registers:
+        // read it at once and hand the TMEM buffer back before the (store-paced) rest of the epilogue.
+        float vall[EPI == EPI_DZ ? 4 : 1][32];
+        if (EPI == EPI_DZ) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(taddr + cc * 32, vall[cc]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
+        }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          float v[32];
-          tmem_ld_32x32(taddr + cc * 32, v);
-          tmem_ld_wait();
-          if (cc == 3) {
-            // accumulator fully read: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
+          float vbuf[32];
+          if (EPI != EPI_DZ) {
+            tmem_ld_32x32(taddr + cc * 32, vbuf);
+            tmem_ld_wait();
+            if (cc == 3) {
+              // accumulator fully read: hand the TMEM buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
+            }
+          }
+          float (&v)[32] = (EPI == EPI_DZ) ? vall[cc] : vbuf;
+          if (EPI == EPI_MAX) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const bool ok = rowok && (j0 + cc * 32 + k < p.N);
+              xmax = fmaxf(xmax, ok ? v[k] * c : 0.f);
+            }
+            continue;
           }
           if (EPI == EPI_FWD) {
             if (!edge) {
@@ -488,6 +520,12 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       }
     }
     if (EPI == EPI_DZ && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
+    if (EPI == EPI_MAX) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.stats_out + 2), __float_as_uint(xmax));
+      if (blockIdx.x == 0 && threadIdx.x == EPI_WARP0 * 32) p.stats_out[3] = 1.f;
+    }
   }
   kernel_epilogue_dealloc(tmem_base);
 }
@@ -767,7 +805,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
   const float s = *scale;
   const float c = s * LOG2E;
   const float U = fabsf(c) * sqrtf(stats[0] * stats[1]);
-  const float G = fmaxf(0.f, U - G_MARGIN);
+  const float G = (stats[3] != 0.f) ? fmaxf(0.f, stats[2] - G_MARGIN) : fmaxf(0.f, U - G_MARGIN);
   if (threadIdx.x == 0) bad_s = 0;
   __syncthreads();
   const int lo = (mode == ONEPROT_MODE_LOCAL) ? row_offset : 0;
@@ -777,7 +815,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
     const float rs = rowsum[k], cs = colsum[k];
     // validated window: sums must be finite and not have lost their leading terms to flush-to-zero
-    if (!(rs >= 1e-24f && rs <= 3e38f) || !(cs >= 1e-24f && cs <= 3e38f)) bad = 1;
+    if (!(rs >= 1e-27f && rs <= 3e38f) || !(cs >= 1e-27f && cs <= 3e38f)) bad = 1;   // 2^-90: flushed mass <= N 2^-126 stays below 2^-20 relative
     inv_rs[k] = 1.f / rs;
     inv_cs[k] = 1.f / cs;
     if (k >= lo && k < hi) {
@@ -1241,13 +1279,13 @@ size_t oneprot_clip_fwd_scratch_bytes(int n, int N) {
 }
 
 int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
-                          const float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
+                          float* stats, float* rowsum, float* colsum, void* scratch, size_t scratch_bytes,
                           void* stream) {
   return oneprot_clip_fwd_sums_ag(A, B_all, n, N, d, scale_dev, stats, nullptr, rowsum, colsum, scratch, scratch_bytes, stream);
 }
 
 int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
-                             const float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
+                             float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
                              size_t scratch_bytes, void* stream) {
   if (!A || !B_all || !scale_dev || !stats || !rowsum || !colsum || !scratch) return fail(ONEPROT_ERR_ARG, "fwd_sums: null pointer");
   if (n <= 0 || N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "fwd_sums: need n, N > 0 and d a positive multiple of 8");
@@ -1287,6 +1325,16 @@ int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int
   if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD>, smem))) return rc;
   // fused gather: every CTA of the grid pushes a slice, so the grid must be fully co-resident (it is: <= #SMs)
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  if (!ag && n == N) {
+    // Robust tier (whole matrix on this GPU): when the Cauchy-Schwarz bound exceeds the fp32 window
+    // the max pass finds the exact maximum logit (stats[2], stats[3] = 1) and the sums below use it
+    // as reference.  It returns immediately otherwise (device-side decision, no host sync).
+    p.stats_out = stats;
+    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_MAX>, smem))) return rc;
+    op::clip_s_kernel<op::EPI_MAX><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+    ++g_launches;
+    OP_CUDA(cudaGetLastError());
+  }
   op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   ++g_launches;
   OP_CUDA(cudaGetLastError());

@@ -70,7 +70,7 @@ def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_d
     inv_rowsum.copy_((1.0 / rowsum_all.double()).float())
     inv_colsum.copy_((1.0 / colsum_all.double()).float())
     bad = (~torch.isfinite(rowsum_all)).any() or (~torch.isfinite(colsum_all)).any() \
-        or (rowsum_all < 1e-24).any() or (colsum_all < 1e-24).any()
+        or (rowsum_all < 1e-27).any() or (colsum_all < 1e-27).any()
     if bool(bad):
         flag[0] = int(flag[0]) | 1
 

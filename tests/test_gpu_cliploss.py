@@ -158,14 +158,52 @@ def test_full_size_vs_fp32_port_on_gpu():
     assert cosine(B.grad.float().cpu().numpy(), dB.cpu().numpy()) >= GRAD_COS
 
 
-def test_hazard_flag_on_unnormalised_huge_logits():
+@pytest.mark.parametrize("n,d,amp", [(256, 512, 1.0), (300, 64, 1.5), (1024, 1024, 1.0)])
+def test_unnormalised_inputs_use_exact_max_reference(n, d, amp):
+    """|c| max|a| max|b| >> 100: the Cauchy-Schwarz reference alone would underflow every term; the
+    max pass supplies the exact maximum logit and the result still matches the float64 oracle."""
     g = torch.Generator().manual_seed(0)
-    A = (40 * torch.randn(256, 64, generator=g)).to(torch.bfloat16).cuda()
-    B = (40 * torch.randn(256, 64, generator=g)).to(torch.bfloat16).cuda()
+    a = (amp * torch.randn(n, d, generator=g)).to(torch.bfloat16)
+    b = (amp * torch.randn(n, d, generator=g)).to(torch.bfloat16)
+    ref = oc.clip_loss_closed_form(a.double().numpy(), b.double().numpy(), 1.0)
+    A = a.cuda().requires_grad_(True)
+    B = b.cuda().requires_grad_(True)
     m = _loss_mod(loss_dtype=torch.float32)
-    m(A, B, 1.0)
+    loss = m(A, B, 1.0)
+    loss.backward()
+    m.check_last_call()
+    assert rel_err(loss.item(), ref.loss) < BF16_LOSS_RTOL
+    assert cosine(A.grad.float().cpu().numpy(), ref.dA) >= GRAD_COS
+    assert cosine(B.grad.float().cpu().numpy(), ref.dB) >= GRAD_COS
+
+
+def test_hazard_flag_when_row_maxima_are_hundreds_of_bits_apart():
+    """Beyond the validated window (one row's best logit is > 2^200 below the global maximum) the
+    device flag is raised instead of returning a silently wrong value."""
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(256, 64, generator=g)
+    b = torch.randn(256, 64, generator=g)
+    a[:128] *= 60.0          # logits of the first rows are ~60x larger than those of the last rows
+    b[:128] *= 60.0
+    m = _loss_mod(loss_dtype=torch.float32)
+    m(a.to(torch.bfloat16).cuda(), b.to(torch.bfloat16).cuda(), 1.0)
     with pytest.raises(FloatingPointError):
         m.check_last_call()
+
+
+def test_odd_feature_dim_and_fp16_inputs():
+    g = torch.Generator().manual_seed(4)
+    a = torch.nn.functional.normalize(torch.randn(70, 13, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(70, 13, generator=g), dim=-1) * 8
+    for dt, tol in ((torch.bfloat16, BF16_LOSS_RTOL), (torch.float16, 1e-4)):
+        A = a.to(dt).cuda().requires_grad_(True)
+        B = b.to(dt).cuda().requires_grad_(True)
+        ref = oc.clip_loss_closed_form(A.detach().double().cpu().numpy(), B.detach().double().cpu().numpy(), 1.0)
+        loss = _loss_mod(loss_dtype=torch.float32)(A, B)
+        loss.backward()
+        assert rel_err(loss.item(), ref.loss) < tol
+        assert A.grad.shape == (70, 13) and A.grad.dtype == dt
+        assert cosine(A.grad.float().cpu().numpy(), ref.dA) >= GRAD_COS
 
 
 def test_epilogue_modules_match_golden():

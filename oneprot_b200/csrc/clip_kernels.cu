@@ -628,16 +628,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       mbar_wait(&s.tail->tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
+      // read this thread's whole 128-column slice, then hand the TMEM buffer back at once: the
+      // global loads / stores of the epilogue no longer hold up the next tile's MMAs
+      float vall[4][32];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(taddr + cc * 32, vall[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        float v[32];
-        tmem_ld_32x32(taddr + cc * 32, v);
-        tmem_ld_wait();
-        if (cc == 3) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
-        }
+        float (&v)[32] = vall[cc];
         if (PUSH) {
           if ((cc & 1) == 0) {
             if (store_issuer) bulk_wait_read<0>();     // previous TMA store finished reading the staging box

@@ -43,7 +43,8 @@ except ImportError:  # pragma: no cover
 # that lives under tests/; the product never does.
 _KERNELS = _cuda_kernels
 
-DEFAULT_PANEL_BYTES = 1 << 30   # bound of the bf16 dL/dZ panel workspace
+# bound of the bf16 dL/dZ panel workspace: 1.25 GiB lets N = 32768 run as two wave-aligned panels
+DEFAULT_PANEL_BYTES = int(__import__("os").environ.get("ONEPROT_PANEL_BYTES", 5 << 28))
 
 _SCALE_CACHE = {}               # (device, python float) -> 1-element fp32 device tensor
 
@@ -294,10 +295,16 @@ class _ClipLossFunction(torch.autograd.Function):
         ldw = (N + 63) // 64 * 64
         rows_cap = max(128, (cfg["panel_bytes"] // (2 * ldw)) // 128 * 128)
         if rows_cap < n:
-            # several panels: make the dA GEMM of every full panel an integer number of waves
+            # several panels: balance them and make the dA GEMM of every full panel an integer number
+            # of waves (its 128 x 256 tiles are dealt to one persistent CTA per SM)
             unit = K.panel_row_unit(d)
-            if rows_cap >= unit:
-                rows_cap = rows_cap // unit * unit
+            n_panels = -(-n // rows_cap)
+            target = -(-n // n_panels)
+            if unit <= rows_cap:
+                up = -(-target // unit) * unit
+                rows_cap = up if up <= rows_cap else rows_cap // unit * unit
+            else:
+                rows_cap = min(rows_cap, -(-target // 128) * 128)
         panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
         Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
 

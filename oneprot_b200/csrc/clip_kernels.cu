@@ -24,7 +24,7 @@ namespace op {
 constexpr int BM = 128;            // accumulator rows  (TMEM lanes)
 constexpr int BN = 256;            // accumulator cols  (TMEM columns per buffer)
 constexpr int BK = 64;             // bf16 elements per smem row = 128 B = one swizzle atom
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -720,6 +720,184 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair GEMM (cta_group::2): two CTAs of a cluster own one 256 x 256 tile.  Each loads its own
+// 128 rows of A and HALF of the B tile (the tensor cores of both SMs share the halves), so the
+// operand traffic from L2 and out of shared memory drops by a third per flop; six 32-KiB stages.
+// ------------------------------------------------------------------------------------------
+constexpr int P_STAGE_BYTES = 32768;   // per CTA: A 128 x 64 + B-half 128 x 64, bf16
+constexpr int P_NS = 6;
+constexpr int GEMM2_SMEM = P_NS * P_STAGE_BYTES + 1024 + static_cast<int>(sizeof(SmemTail));
+
+template <int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
+gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023);
+  uint8_t* stages = reinterpret_cast<uint8_t*>(base);
+  SmemTail* tail = reinterpret_cast<SmemTail*>(base + P_NS * P_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane_id() == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int i = 0; i < P_NS; ++i) {
+      mbar_init(&tail->full[i], 1);      // leader: its producer's arrive.expect_tx; bytes come from both CTAs
+      mbar_init(&tail->empty[i], 1);     // the leader's multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tail->tfull[i], 1);
+      mbar_init(&tail->tempty[i], 2 * EPI_THREADS / 32);   // epilogue warps of BOTH CTAs (leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  cluster_sync();                          // both CTAs' barriers exist before any remote signal
+  if (warp == 2) {
+    tmem_alloc_pair(&tail->tmem_base, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nMb2 = (p.M + 255) / 256;
+  const int tiles = nMb2 * p.nNb;
+
+  if (warp == 0) {
+    reg_dealloc<40>();
+    if (lane_id() == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < tiles; t += npairs) {
+        const int m0 = (t / p.nNb) * 256 + static_cast<int>(rank) * 128;
+        const int nh0 = (t % p.nNb) * BN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < p.nK; ++kb) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          uint64_t* fb = &tail->full[stage];
+          if (leader) mbar_arrive_expect_tx(fb, 2 * P_STAGE_BYTES);
+          uint8_t* sa = stages + stage * P_STAGE_BYTES;
+          uint8_t* sb = sa + 16384;
+          const int k0 = kb * BK;
+          if (A_MN == 0) {
+            tma_load_2d_pair(sa, &mapA, fb, k0, m0);
+          } else {
+            tma_load_2d_pair(sa, &mapA, fb, m0, k0);
+            tma_load_2d_pair(sa + 8192, &mapA, fb, m0 + 64, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d_pair(sb, &mapB, fb, k0, nh0);
+          } else {
+            tma_load_2d_pair(sb, &mapB, fb, nh0, k0);
+            tma_load_2d_pair(sb + 8192, &mapB, fb, nh0 + 64, k0);
+          }
+          if (++stage == P_NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    reg_dealloc<40>();
+    if (leader && lane_id() == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < tiles; t += npairs) {
+        mbar_wait(&tail->tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.nK; ++kb) {
+          mbar_wait(&tail->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stages + stage * P_STAGE_BYTES);
+          const uint32_t sb = sa + 16384;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16_pair(tmem_d, da, db, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit_pair(&tail->empty[stage], 3);     // frees the stage in both CTAs
+          if (++stage == P_NS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tail->tfull[acc], 3);          // accumulator ready in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    reg_dealloc<40>();
+  } else {
+    reg_alloc<168>();
+    const int ew = warp - EPI_WARP0;
+    const int q = ew & 3, h = ew >> 2;
+    const int lane = lane_id();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < tiles; t += npairs) {
+      const int nb = t % p.nNb;
+      const int m = (t / p.nNb) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      const int n0 = nb * BN + h * 128;
+      const float rs = (p.row_scale && m < p.M) ? __ldg(p.row_scale + m) : 1.f;
+      mbar_wait(&tail->tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
+      float vall[4][32];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(taddr + cc * 32, vall[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tempty[acc]), 0));   // the leader's barrier
+      if (m < p.M) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const size_t rowbase = static_cast<size_t>(m) * p.ldc + n0 + cc * 32;
+#pragma unroll
+          for (int v8 = 0; v8 < 4; ++v8) {
+            const int n = n0 + cc * 32 + v8 * 8;
+            if (n < p.Nc) {
+              float x[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) x[u] = vall[cc][v8 * 8 + u];
+              if (p.acc_in) {
+                const float4 a0 = *reinterpret_cast<const float4*>(p.acc_in + rowbase + v8 * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(p.acc_in + rowbase + v8 * 8 + 4);
+                x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
+                x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) x[u] *= rs;
+              if (p.acc_out) {
+                *reinterpret_cast<float4*>(p.acc_out + rowbase + v8 * 8) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(p.acc_out + rowbase + v8 * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              }
+              if (p.out) {
+                *reinterpret_cast<uint4*>(p.out + rowbase + v8 * 8) =
+                    make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                               pack_bf16x2(x[6], x[7]));
+              }
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                          // no CTA frees TMEM while its partner may still use the pair
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Small HBM-bound kernels
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -1200,7 +1378,7 @@ int num_sms() {
 
 template <typename K>
 int prep_kernel(K kernel, int smem_bytes) {
-  static thread_local const void* done[8] = {nullptr};
+  static thread_local const void* done[24] = {nullptr};
   for (auto& p : done) {
     if (p == reinterpret_cast<const void*>(kernel)) return ONEPROT_OK;
   }
@@ -1440,8 +1618,31 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
   if (rc) return rc;
   if (b_mn) rc = make_map(&mapB, B, Nc, K, ldb, 64); else rc = make_map(&mapB, B, K, Nc, ldb, op::BN);
   if (rc) return rc;
-  const int grid = std::min(num_sms(), p.nMb * p.nNb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool use_pairs = getenv("ONEPROT_CG2") != nullptr;
+  if (use_pairs && !dot_mat && (num_sms() % 2 == 0)) {
+    // CTA-pair variant: per-CTA boxes are 128 rows for both operands
+    if (a_mn) rc = make_map(&mapA, A, M, K, lda, 64); else rc = make_map(&mapA, A, K, M, lda, 128);
+    if (rc) return rc;
+    if (b_mn) rc = make_map(&mapB, B, Nc, K, ldb, 64); else rc = make_map(&mapB, B, K, Nc, ldb, 128);
+    if (rc) return rc;
+    const int tiles2 = cdiv(M, 256) * p.nNb;
+    const int grid2 = 2 * std::min(num_sms() / 2, tiles2);
+#define LAUNCH_GEMM2(AM, BMJ)                                                                      \
+  do {                                                                                             \
+    if ((rc = prep_kernel(op::gemm2_kernel<AM, BMJ>, op::GEMM2_SMEM))) return rc;                  \
+    op::gemm2_kernel<AM, BMJ><<<grid2, op::NUM_THREADS, op::GEMM2_SMEM, st>>>(mapA, mapB, p);      \
+  } while (0)
+    if (!a_mn && !b_mn) LAUNCH_GEMM2(0, 0);
+    else if (!a_mn && b_mn) LAUNCH_GEMM2(0, 1);
+    else if (a_mn && !b_mn) LAUNCH_GEMM2(1, 0);
+    else LAUNCH_GEMM2(1, 1);
+#undef LAUNCH_GEMM2
+    ++g_launches;
+    OP_CUDA(cudaGetLastError());
+    return ONEPROT_OK;
+  }
+  const int grid = std::min(num_sms(), p.nMb * p.nNb);
 #define LAUNCH_GEMM(AM, BMJ)                                                                       \
   do {                                                                                             \
     if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ, false>, op::GEMM_SMEM))) return rc;             \

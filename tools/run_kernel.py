@@ -35,6 +35,8 @@ fns = {
     "db": lambda: K.gemm_bf16(Wz, True, A[:rows], True, N, d, rows, out=dB),
 }
 fn = fns[which]
+if which in ('da', 'db'):
+    fns['dz'](); torch.cuda.synchronize()   # realistic panel contents (zeros would lower the MMA power)
 if which == "fwd":
     scratch = torch.empty(K.fwd_scratch_bytes(rows, N), dtype=torch.uint8, device=dev)
 fn(); torch.cuda.synchronize()

@@ -53,7 +53,7 @@ class ClockSampler:
     """Polls NVML (SM clock, power, clock-event reasons) every few ms while the timed region runs."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.004):
+    def __init__(self, gpu_index: int, period_s: float = 0.010):
         self.gpu, self.period, self.samples, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
 
     def start(self):

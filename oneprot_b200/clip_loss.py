@@ -212,6 +212,16 @@ class _ClipLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, A, B, scale_t, cfg):
+        with _KERNELS.stream_scope():
+            return _ClipLossFunction._forward_impl(ctx, A, B, scale_t, cfg)
+
+    @staticmethod
+    def backward(ctx, g_loss, _g32, _gflag):
+        with _KERNELS.stream_scope():
+            return _ClipLossFunction._backward_impl(ctx, g_loss)
+
+    @staticmethod
+    def _forward_impl(ctx, A, B, scale_t, cfg):
         K = _KERNELS
         W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
         dev = A.device
@@ -251,7 +261,7 @@ class _ClipLossFunction(torch.autograd.Function):
         return loss_out, loss_f32, flag
 
     @staticmethod
-    def backward(ctx, g_loss, _g32, _gflag):
+    def _backward_impl(ctx, g_loss):
         K = _KERNELS
         cfg, ops, mode = ctx.cfg, ctx.ops, ctx.mode
         W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
@@ -276,7 +286,7 @@ class _ClipLossFunction(torch.autograd.Function):
             gvec = torch.zeros((W + 3) // 4 * 4, dtype=torch.float32, device=dev)   # placeholder for `what=1`
             g_holder = {}
             ev0 = main.record_event()
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), K.stream_scope():
                 side.wait_event(ev0)
                 g_holder["gvec"] = comm.gather_grad_outputs(g32, rank, W, ctx.token)
         else:
@@ -319,7 +329,7 @@ class _ClipLossFunction(torch.autograd.Function):
             if g_holder is not None:
                 K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
                               wr, wc, dg, sA, sB, 1)                     # panel weights: no g needed
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(side), K.stream_scope():
                     K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, g_holder["gvec"],
                                   ctx.scale_dev, wr, wc, dg, sA, sB, 2)  # output scales from the gathered g
                     ev_g = side.record_event()
@@ -345,7 +355,7 @@ class _ClipLossFunction(torch.autograd.Function):
                         chain_b.add(Wp, True, Ap, True, rows)
                     if exchange_b and side is not None and push is None and qi == len(panels) - 1:
                         evb = main.record_event()
-                        with torch.cuda.stream(side):
+                        with torch.cuda.stream(side), K.stream_scope():
                             side.wait_event(evb)
                             dB_async = comm.reduce_scatter_db(dBp, rank, W, last_pass=last_pass)
                             ev_rs = side.record_event()

@@ -16,8 +16,33 @@ MODE_GLOBAL = 0
 MODE_LOCAL = 1
 
 
+import threading
+
+_TLS = threading.local()
+
+
+class stream_scope:
+    """Caches the raw handle of torch's current CUDA stream for the launches issued inside the
+    `with` block (one lookup per forward / backward instead of one per kernel).  Nested scopes
+    (e.g. a side stream) restore the outer handle on exit."""
+
+    def __enter__(self):
+        self.prev = getattr(_TLS, "stream", None)
+        _TLS.stream = "unset"          # looked up lazily by the first launch inside the scope
+        return self
+
+    def __exit__(self, *exc):
+        _TLS.stream = self.prev
+        return False
+
+
 def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    s = getattr(_TLS, "stream", None)
+    if s is None:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if s == "unset":
+        s = _TLS.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return s
 
 
 def _need_cuda(*ts):

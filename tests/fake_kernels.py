@@ -16,6 +16,14 @@ LOG2E = 1.4426950408889634
 CALLS = []
 
 
+class stream_scope:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def panel_row_unit(d):
     return 128
 

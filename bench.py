@@ -109,26 +109,24 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 def cpu_panel_step(A, B, m):
     """fwd+bwd of the reference's W=1 ClipLoss restricted to the first m rows of BOTH logit
-    matrices (loss.py:98-99,109-112).  Cost is m/N of the full step, so full-step throughput =
-    m / t (the N x N work is row-separable; the port's ops and threading are unchanged)."""
-    import torch
-    import torch.nn.functional as F
+    matrices (oracle.clip_oracle.clip_loss_port_panel, reference loss.py:98-99,109-112).  Cost is
+    m/N of the full step, so full-step throughput = m / t (the N x N work is row-separable; the
+    port's ops and threading are unchanged)."""
+    from oracle.clip_oracle import clip_loss_port_panel
     A = A.detach().requires_grad_(True)
     B = B.detach().requires_grad_(True)
-    z_ab = (1.0 * A[:m]) @ B.T
-    z_ba = (1.0 * B[:m]) @ A.T
-    t = torch.arange(m)
-    loss = (F.cross_entropy(z_ab, t) + F.cross_entropy(z_ba, t)) / 2
+    loss = clip_loss_port_panel(A, B, m, 1.0)
     loss.backward()
     return float(loss.detach())
 
 
 def cpu_reference(steps, warmup, budget_s_per_step):
+    """The only place of bench.py that executes oracle/ code (cpu_baseline / --impl reference leg)."""
     import torch
-    from oracle import clip_oracle as oc
+    from tools.synthetic import synthetic_pair
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    a, b = oc.synthetic_pair(GLOBAL_N, DIM, seed=1234, dtype="fp32")
+    a, b = synthetic_pair(GLOBAL_N, DIM, seed=1234, dtype="fp32")
     # probe to size the panel
     t0 = time.perf_counter(); cpu_panel_step(a, b, 128); cpu_panel_step(a, b, 128)
     t_probe = (time.perf_counter() - t0) / 2
@@ -181,7 +179,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from oneprot_b200 import ClipLoss, kernels
-    from oracle import clip_oracle as oc   # synthetic generator + cpu_baseline leg only
+    from tools.synthetic import synthetic_pair   # input generator (not the oracle)
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -197,8 +195,8 @@ def run_ours(args):
     n = GLOBAL_N // world
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
-    a, b = oc.synthetic_pair(n, DIM, seed=1234, pair_id=0, rank=rank, correlated=True, temperature_into_b=True,
-                             dtype="bf16")
+    a, b = synthetic_pair(n, DIM, seed=1234, pair_id=0, rank=rank, correlated=True, temperature_into_b=True,
+                          dtype="bf16")
     a_pin, b_pin = a.pin_memory(), b.pin_memory()
     A = a.to(dev).requires_grad_(True)
     B = b.to(dev).requires_grad_(True)

@@ -168,6 +168,19 @@ def clip_loss_port(A, B, logit_scale=1.0):
     return (F.cross_entropy(z_ab, target) + F.cross_entropy(z_ba, target)) / 2
 
 
+def clip_loss_port_panel(A, B, m, logit_scale=1.0):
+    """The port restricted to the first m rows of both logit matrices (a bounded, row-separable
+    sample of the N x N work for the CPU baseline of bench.py): same ops as ``clip_loss_port``
+    (loss.py:98-99,109-112) on z_ab[:m] and z_ba[:m]."""
+    import torch
+    import torch.nn.functional as F
+
+    z_ab = (logit_scale * A[:m]) @ B.T
+    z_ba = (logit_scale * B[:m]) @ A.T
+    target = torch.arange(m, device=A.device, dtype=torch.long)
+    return (F.cross_entropy(z_ab, target) + F.cross_entropy(z_ba, target)) / 2
+
+
 def clip_loss_port_fwd_bwd(A, B, logit_scale=1.0):
     """One fwd+bwd step of the port; returns (loss, dA, dB) as detached tensors."""
     A = A.detach().requires_grad_(True)
@@ -213,23 +226,7 @@ def clip_loss_port_distributed(a_loc, b_loc, logit_scale, *, rank, world_size, l
 
 
 # ----------------------------------------------------------------------------------------------
-# deterministic synthetic inputs - shared by tests and bench
+# deterministic synthetic inputs: defined in tools/synthetic.py (bench.py's product arm must not
+# import the oracle), re-exported here for the tests
 # ----------------------------------------------------------------------------------------------
-def synthetic_pair(n: int, d: int, *, seed: int = 1234, pair_id: int = 0, rank: int = 0,
-                   correlated: bool = True, temperature_into_b: bool = True,
-                   dtype: str = "bf16"):
-    """Per-rank synthetic embeddings: A = normalize(randn), B = normalize(A + 0.5 randn)
-    (uncorrelated: B = normalize(randn)); training-faithful scaling multiplies B by 1/0.07
-    (LearnableLogitScaling is applied to the modality tower, base_encoder.py:30)
-    and rounds to ``dtype``.  Returns torch CPU tensors (A, B) in ``dtype``."""
-    import torch
-    import torch.nn.functional as F
-
-    g = torch.Generator(device="cpu").manual_seed(seed + 1000 * pair_id + rank)
-    a = F.normalize(torch.randn(n, d, generator=g, dtype=torch.float32), dim=-1)
-    noise = torch.randn(n, d, generator=g, dtype=torch.float32)
-    b = F.normalize(a + 0.5 * noise, dim=-1) if correlated else F.normalize(noise, dim=-1)
-    if temperature_into_b:
-        b = b * (1.0 / 0.07)
-    td = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[dtype]
-    return a.to(td), b.to(td)
+from tools.synthetic import synthetic_pair  # noqa: E402,F401

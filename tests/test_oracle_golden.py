@@ -89,3 +89,13 @@ def test_synthetic_generator_is_deterministic():
     # unit-norm anchor, temperature folded into B
     assert abs(a1.float().norm(dim=-1).mean().item() - 1.0) < 1e-2
     assert abs(b1.float().norm(dim=-1).mean().item() - 1 / 0.07) < 0.2
+
+
+def test_panel_port_is_the_row_restriction_of_the_port():
+    a, b = oc.synthetic_pair(64, 32, seed=9, dtype="fp32")
+    full_ab = torch.nn.functional.cross_entropy(a @ b.T, torch.arange(64), reduction="none")
+    full_ba = torch.nn.functional.cross_entropy(b @ a.T, torch.arange(64), reduction="none")
+    want = (full_ab[:16].mean() + full_ba[:16].mean()) / 2
+    got = oc.clip_loss_port_panel(a, b, 16, 1.0)
+    assert abs(got.item() - want.item()) < 1e-6
+    assert abs(oc.clip_loss_port_panel(a, b, 64, 1.0).item() - oc.clip_loss_port(a, b, 1.0).item()) < 1e-6

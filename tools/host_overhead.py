@@ -4,7 +4,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oneprot_b200 import ClipLoss
-from oracle import clip_oracle as oc
+from tools import synthetic as oc
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 a, b = oc.synthetic_pair(n, 1024, seed=1)
 A = a.cuda().requires_grad_(True); B = b.cuda().requires_grad_(True)

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 from oneprot_b200 import ClipLoss, clip_loss, kernels
-from oracle import clip_oracle as oc
+from tools import synthetic as oc
 
 world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)

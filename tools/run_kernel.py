@@ -8,7 +8,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oneprot_b200 import kernels as K
-from oracle import clip_oracle as oc
+from tools import synthetic as oc
 
 which = sys.argv[1] if len(sys.argv) > 1 else "dz"
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 16384

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from torch.profiler import profile, ProfilerActivity
 from oneprot_b200 import ClipLoss
-from oracle import clip_oracle as oc
+from tools import synthetic as oc
 world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 if world > 1: dist.init_process_group("nccl", device_id=dev)

@@ -19,6 +19,7 @@ bf16, synthetic unit-norm anchors with the temperature folded into the second op
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -29,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# load every kernel of the CUDA modules when they are first touched (in warm-up), not lazily inside
+# the timed steps
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 GLOBAL_N = int(os.environ.get("ONEPROT_BENCH_N", 32768))
 DIM = int(os.environ.get("ONEPROT_BENCH_D", 1024))
@@ -223,7 +227,17 @@ def run_ours(args):
         return Ad.grad
 
     def timed(fn, k):
-        """k steps, each bracketed by its own event pair; the L2 flush sits between the pairs."""
+        """k steps, each bracketed by its own event pair; the L2 flush sits between the pairs.
+        The Python garbage collector is parked for the duration: a generation-2 collection on one
+        rank (tens of ms with torch loaded) would stall all ranks at the next exchange."""
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(fn, k)
+        finally:
+            gc.enable()
+
+    def _timed(fn, k):
         evs = []
         for _ in range(k):
             flush.zero_()
@@ -244,6 +258,7 @@ def run_ours(args):
     ms = timed(step_device, steps)
     barrier()
     launches = kernels.launch_count()
+    ms_steps_rank0 = [round(x, 4) for x in ms]
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -291,7 +306,7 @@ def run_ours(args):
                                    f"gather_with_grad=True, {GLOBAL_N // world} rows per GPU",
                        "global_batch": GLOBAL_N, "dim": DIM, "rows_per_gpu": n,
                        "l2": "256 MiB buffer written between timed steps (L2 flush); inputs 128 MiB",
-                       "loss": loss_val},
+                       "loss": loss_val, "ms_steps_rank0": ms_steps_rank0},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": dk["tflops"], "peak": peaks["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": dk["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
                          "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",

@@ -198,6 +198,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n = GLOBAL_N // world
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    # Strong scaling: one step is 1/world of the single-GPU device work (0.9 ms at 8 GPUs), so W
+    # steps would be ~3 ms of warm-up - shorter than the GPUs' clock ramp (measured: per-step time
+    # still falling 1.06 -> 0.89 ms over the first 13 steps at 8 GPUs).  Scale the step COUNT by
+    # world so that the warm-up covers the same device time (~20 ms) at every GPU count; the count
+    # actually run is what the JSON line reports as "warmup".
+    warmup = warmup * world
 
     a, b = synthetic_pair(n, DIM, seed=1234, pair_id=0, rank=rank, correlated=True, temperature_into_b=True,
                           dtype="bf16")
@@ -269,7 +275,7 @@ def run_ours(args):
 
     # ---- e2e: pinned host inputs -> H2D -> fwd+bwd -> D2H loss
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
-    for _ in range(2):
+    for _ in range(max(3, world)):
         step_e2e(host_loss)
     barrier()
     ms_e2e = timed(lambda: step_e2e(host_loss), max(3, steps // 2))

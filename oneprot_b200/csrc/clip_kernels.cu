@@ -1,12 +1,20 @@
 // B200 (sm_100a) kernels + C ABI for the OneProt ClipLoss hot path.  See include/oneprot_clip.h for
 // the contract of every entry point and DESIGN.md for the data layout and rooflines.
 //
-// One warp-specialised mainloop serves every tensor-core kernel here:
+// One warp-specialised mainloop serves every tensor-core kernel here (one persistent CTA per SM):
 //   warp 0      TMA producer   (cp.async.bulk.tensor -> 4-stage smem ring, SWIZZLE_128B)
 //   warp 1      UMMA issuer    (tcgen05.mma cta_group::1, M=128 x N=256 x K=16, fp32 accum in TMEM)
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warp 3      spare; in the fused forward it pushes this rank's rows through the NVLink multicast
 //   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers; thread = one accumulator row)
-// The epilogues differ: exp-sum (forward), dL/dZ panel (backward), plain store (dA / dB GEMMs).
+// The epilogues differ:
+//   clip_s_kernel<FWD>  exp-sums of the logits (row sums thread-local, column sums in registers)
+//   clip_s_kernel<MAX>  exact maximum logit (robust tier, early-exits when the norm bound suffices)
+//   clip_s_kernel<DZ>   dL/dZ panel, bf16, staged through swizzled smem and written by TMA stores
+//   gemm_kernel         dA = Wz.B / dB = Wz^T.A with row-scale, row-dot, fp32 accumulate, and a PUSH
+//                       variant that TMA-stores finished tiles into the owner GPU's memory
+//   gemm2_kernel        the same GEMM on CTA pairs (tcgen05.mma cta_group::2), opt-in
+// plus the HBM-bound vector kernels and the multimem (NVLS) exchange kernels at the end.
 #include "ptx.cuh"
 #include "../../include/oneprot_clip.h"
 

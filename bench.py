@@ -53,28 +53,93 @@ def _peaks():
 # ----------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi while the timed region runs)
 # ----------------------------------------------------------------------------------------------
+_SAMPLER_CHILD = r"""
+import signal, sys, time
+import pynvml as nv
+idx, period = int(sys.argv[1]), float(sys.argv[2])
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(idx)
+print("ready", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+stop = []
+signal.signal(signal.SIGTERM, lambda *a: stop.append(1))
+while not stop:
+    print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+          nv.nvmlDeviceGetCurrentClocksEventReasons(h), flush=True)
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """Polls NVML (SM clock, power, clock-event reasons) every few ms while the timed region runs."""
+    """SM clock, power and clock-event reasons while the timed region runs.
+
+    The NVML polling lives in a CHILD PROCESS: NVML queries take driver locks, and polling from a
+    thread of rank 0 can hold up that rank's kernel launches for a millisecond - at 8 GPUs a whole
+    step, which every other rank then waits for inside its forward kernel.  The parent only reads
+    the child's lines.  Falls back to an in-process thread (slow period) if the child cannot start."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int, period_s: float = 0.010):
-        self.gpu, self.period, self.samples, self.stop_flag, self.thread, self.err = gpu_index, period_s, [], False, None, None
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.lines, self.max_sm, self.err = [], [], None, None
+        self.proc = self.reader = self.thread = None
+        self.stop_flag = False
+
+    def _nvml_index(self):
+        # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            return int(vis.split(",")[self.gpu])
+        return self.gpu
 
     def start(self):
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(self._nvml_index()), str(self.period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.reader = threading.Thread(target=self._read_child, daemon=True)
+            self.reader.start()
+            t0 = time.time()
+            while self.max_sm is None and self.proc.poll() is None and time.time() - t0 < 8.0:
+                time.sleep(0.01)
+            if self.max_sm is not None:
+                return
+            self.err = "sampler child did not start"
+            self._kill_child()
+        except Exception as e:   # pragma: no cover
+            self.err = repr(e)
+        self._start_thread_fallback()
+
+    def _read_child(self):
+        for line in self.proc.stdout:
+            f = line.split()
+            if not f:
+                continue
+            if f[0] == "ready":
+                self.max_sm = float(f[1])
+            elif len(f) == 3:
+                try:
+                    self.samples.append((float(f[0]), float(f[1]), int(f[2])))
+                except ValueError:
+                    pass
+
+    def _kill_child(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:   # pragma: no cover
+                self.proc.kill()
+
+    def _start_thread_fallback(self):
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            idx = self.gpu
-            if vis and all(t.strip().isdigit() for t in vis.split(",")):
-                idx = int(vis.split(",")[self.gpu])
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception as e:   # pragma: no cover
             self.err = repr(e)
             return
+        self.period = max(self.period, 0.05)
         self.thread = threading.Thread(target=self._poll, daemon=True)
         self.thread.start()
 
@@ -82,10 +147,9 @@ class ClockSampler:
         nv = self.nv
         while not self.stop_flag:
             try:
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.samples.append((sm, pw, rs))
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
             except Exception as e:   # pragma: no cover
                 self.err = repr(e)
                 return
@@ -93,8 +157,10 @@ class ClockSampler:
 
     def stop(self):
         self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=2)
+        self._kill_child()
+        for t in (self.reader, self.thread):
+            if t is not None:
+                t.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
         reasons = set()
@@ -104,7 +170,7 @@ class ClockSampler:
                     reasons.add(name)
         pmax = max(p for _, p, _ in self.samples)
         load = [s for s, p, _ in self.samples if p >= 0.6 * pmax] or [s for s, _, _ in self.samples]
-        return {"sm_mhz": statistics.median(load), "sm_max_mhz": float(self.max_sm), "power_w_max": pmax,
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.max_sm, "power_w_max": pmax,
                 "samples": len(self.samples), "samples_under_load": len(load), "reasons": sorted(reasons)}
 
 

@@ -299,17 +299,7 @@ def run_ours(args):
         return Ad.grad
 
     def timed(fn, k):
-        """k steps, each bracketed by its own event pair; the L2 flush sits between the pairs.
-        The Python garbage collector is parked for the duration: a generation-2 collection on one
-        rank (tens of ms with torch loaded) would stall all ranks at the next exchange."""
-        gc.collect()
-        gc.disable()
-        try:
-            return _timed(fn, k)
-        finally:
-            gc.enable()
-
-    def _timed(fn, k):
+        """k steps, each bracketed by its own event pair; the L2 flush sits between the pairs."""
         evs = []
         for _ in range(k):
             flush.zero_()
@@ -319,12 +309,20 @@ def run_ours(args):
         torch.cuda.synchronize()
         return [e0.elapsed_time(e1) for e0, e1 in evs]
 
-    for _ in range(warmup):
-        step_device()
-    barrier()
+    # everything slow (sampler child start-up, ~0.3 s) happens BEFORE the warm-up so that the timed
+    # steps follow the warm-up back to back: an idle gap in between lets the clocks fall back and the
+    # first timed steps would pay the ramp again (seen as 1.68 / 1.06 / 0.98 ms ... at 8 GPUs)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # The Python garbage collector is parked from here to the end of the measurements: a
+    # generation-2 collection on one rank (tens of ms with torch loaded) would stall all ranks at
+    # the next exchange, and a collection between warm-up and timing would re-open the idle gap.
+    gc.collect()
+    gc.disable()
+    barrier()
+    for _ in range(warmup):
+        step_device()
     kernels.launch_count_reset()
     barrier()
     ms = timed(step_device, steps)

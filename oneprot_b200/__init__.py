@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("Normalize", "LearnableLogitScaling", "NormalizeAndScale"):
         from . import epilogue
         return getattr(epilogue, name)
+    if name == "PinnedPairPrefetcher":
+        from . import prefetch
+        return prefetch.PinnedPairPrefetcher
     raise AttributeError(name)

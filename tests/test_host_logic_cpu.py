@@ -157,3 +157,9 @@ def test_two_rank_gloo_conventions_vs_reference_golden():
                         assert abs(np.linalg.norm(got[k]) / np.linalg.norm(want) - 1) < 1e-2, (r, ref, k)
                     if sg:
                         assert rel_err(got["ds"], g[f"r{r}_dscale_{ref}"]) < 2e-2, (r, ref)
+
+
+def test_prefetcher_rejects_cpu_device():
+    from oneprot_b200.prefetch import PinnedPairPrefetcher
+    with pytest.raises(ValueError):
+        PinnedPairPrefetcher("cpu")

@@ -221,6 +221,103 @@ int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* st
  * concatenated K reproduces the fp32 dot product. */
 int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int terms, void* stream);
 
+/* ---- host-side step sequencer (oneprot_b200/csrc/clip_sequence.cu) -------------------------------
+ * One call enqueues a whole PHASE of ClipLoss.forward / its autograd backward (loss.py:103-114 and
+ * the implicit backward): the memsets, the kernels above and the event records /
+ * waits between the compute stream and the exchange stream, out of one caller-provided workspace.
+ * Same launches, order and streams as the Python host (oneprot_b200/clip_loss.py); a phase ends
+ * where the caller has to run a symmetric-memory barrier.  Scope: bf16 operands (d % 8 == 0), one
+ * pass over both softmax directions (world 1; local_loss = False; local_loss = True with
+ * gather_with_grad = True), logit_scale without gradient, exchanges through the NVLS provider with
+ * the all-gather fused into the forward kernel.  Everything else stays on the Python path. */
+
+/* `saved` (float*, 16-byte aligned, ONEPROT_SAVED_HEADER_FLOATS + 2 N floats) is what the backward
+ * needs from the forward: [loss | maxima (stats, 4 floats) | hazard flag (int32) | 1/rowsum N | 1/colsum N] */
+#define ONEPROT_SAVED_LOSS_AT 0
+#define ONEPROT_SAVED_STATS_AT 4
+#define ONEPROT_SAVED_FLAG_AT 8
+#define ONEPROT_SAVED_HEADER_FLOATS 16
+
+typedef struct {
+  const void* A;            /* n x d bf16: this rank's first operand */
+  const void* B_all;        /* N x d bf16: second operand of all ranks (world 1: the caller's B) */
+  const void* stats_rows;   /* rows oneprot_clip_rowstats reads as its B_all: B_all (world 1) or this rank's B */
+  const float* scale;       /* device fp32 logit_scale */
+  float* stats;             /* 4 floats written by rowstats: saved + ONEPROT_SAVED_STATS_AT (world 1) or
+                               this rank's maxima inside the symmetric buffer (fused gather) */
+  float* saved;
+  void* zero_ptr;           /* fused gather: symmetric [g | maxima | sums] buffer to clear first; else NULL */
+  size_t zero_bytes;
+  float* sums;              /* fused gather: this rank's partial [colsum | rowsum | diag] (3 N floats) in
+                               symmetric memory; NULL: the sums are complete locally (workspace) */
+  const float* sums_mc;     /* multicast alias of `sums`, or NULL */
+  const oneprot_ag_t* ag;   /* fused all-gather descriptor (stats_out = saved + ONEPROT_SAVED_STATS_AT), or NULL */
+  void* ws;                 /* 16-byte aligned, oneprot_seq_fwd_ws_bytes(n, N) bytes */
+  size_t ws_bytes;
+  void* stream;
+  int n, N, d, row_offset, mode;
+  int stats_rows_n;         /* rows of stats_rows */
+  int stats_off;            /* row of stats_rows that holds the label of A's row 0 */
+} oneprot_fwd_seq_t;
+
+size_t oneprot_seq_fwd_ws_bytes(int n, int N);
+/* memsets + rowstats + fused forward (what comes before NvlsComm.complete_sums' barrier) */
+int oneprot_seq_fwd_begin(const oneprot_fwd_seq_t* f);
+/* [switch-side sum of the partial sums] + loss_finalize */
+int oneprot_seq_fwd_end(const oneprot_fwd_seq_t* f);
+/* both phases back to back (world 1) */
+int oneprot_seq_fwd(const oneprot_fwd_seq_t* f);
+
+typedef struct {
+  const void* A;
+  const void* B_all;
+  const float* scale;
+  const float* stats;        /* saved + ONEPROT_SAVED_STATS_AT */
+  const float* inv_rowsum;   /* saved + ONEPROT_SAVED_HEADER_FLOATS */
+  const float* inv_colsum;   /* ... + N */
+  const float* g;            /* device fp32: this rank's upstream gradient */
+  void* dA;                  /* n x d bf16 (want_a) */
+  void* dB;                  /* N x d bf16: dB (world 1) or the partial-dB region in symmetric memory */
+  void* ws;                  /* 16-byte aligned, oneprot_seq_bwd_ws_bytes(...) bytes */
+  size_t ws_bytes;
+  size_t panel_bytes;        /* bound of the bf16 dL/dZ panel */
+  void* stream;              /* compute stream */
+  /* exchange through the NVLS provider (world > 1); NULL / 0 otherwise */
+  void* side_stream;
+  float* g_slot;             /* this GPU's copy of the gradient slot ((world+3)/4*4 floats) in symmetric memory */
+  const float* g_slot_mc;    /* its multicast alias */
+  const void* dB_mc_mine;    /* multicast alias of this rank's n x d rows of dB */
+  void* dB_out;              /* n x d bf16: this rank's rows of the summed dB */
+  void* seq;                 /* oneprot_seq_create handle (events) */
+  int n, N, d, row_offset, mode, use_gsum, world, rank;
+  int want_a, want_b;
+  int g_on_side;             /* gather the upstream gradients on the side stream under the dL/dZ kernel (MODE_GLOBAL) */
+} oneprot_bwd_seq_t;
+
+int oneprot_seq_create(void** out);
+void oneprot_seq_destroy(void* seq);
+size_t oneprot_seq_bwd_ws_bytes(int n, int N, int d, int world, int want_b, size_t panel_bytes);
+/* number of dL/dZ panels for a panel_bytes bound (+ rows per full panel, allocated panel rows) */
+int oneprot_seq_bwd_panels(int n, int N, int d, size_t panel_bytes, int* rows_per_panel, int* wz_rows);
+/* world > 1: this rank's one-hot upstream gradient into the symmetric slot (before the caller's barrier) */
+int oneprot_seq_bwd_begin(const oneprot_bwd_seq_t* q);
+/* [gather of the upstream gradients] + bwd_weights + per panel: dz_panel, dB GEMM, dA GEMM
+ * (world > 1: ends with the side stream waiting for the last dB GEMM, before the caller's barrier;
+ * the last panel's dA GEMM is left to oneprot_seq_bwd_end) */
+int oneprot_seq_bwd_main(const oneprot_bwd_seq_t* q);
+/* world > 1: switch-side reduce of this rank's dB rows on the side stream, the last panel's dA GEMM
+ * on the compute stream over it, then the compute stream waits for the reduce */
+int oneprot_seq_bwd_end(const oneprot_bwd_seq_t* q);
+
+/* ---- launch trace (test support) -------------------------------------------------------------
+ * Between oneprot_trace_begin and oneprot_trace_end every entry point of this library appends one
+ * text line with its arguments; with dry_run != 0 it then returns without any CUDA call, so the
+ * launch sequence of a phase can be inspected on a machine without a GPU.  oneprot_trace_end
+ * copies the text (NUL-terminated, truncated to cap) and returns its full length. */
+void oneprot_trace_begin(int dry_run);
+size_t oneprot_trace_end(char* out, size_t cap);
+void oneprot_trace_note(const char* text);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,28 @@ class AgDesc(C.Structure):
                 ("rows_per_rank", C.c_int)]
 
 
+class FwdSeq(C.Structure):
+    """oneprot_fwd_seq_t of include/oneprot_clip.h"""
+    _fields_ = [("A", C.c_void_p), ("B_all", C.c_void_p), ("stats_rows", C.c_void_p), ("scale", C.c_void_p),
+                ("stats", C.c_void_p), ("saved", C.c_void_p), ("zero_ptr", C.c_void_p), ("zero_bytes", C.c_size_t),
+                ("sums", C.c_void_p), ("sums_mc", C.c_void_p), ("ag", C.POINTER(AgDesc)), ("ws", C.c_void_p),
+                ("ws_bytes", C.c_size_t), ("stream", C.c_void_p),
+                ("n", C.c_int), ("N", C.c_int), ("d", C.c_int), ("row_offset", C.c_int), ("mode", C.c_int),
+                ("stats_rows_n", C.c_int), ("stats_off", C.c_int)]
+
+
+class BwdSeq(C.Structure):
+    """oneprot_bwd_seq_t of include/oneprot_clip.h"""
+    _fields_ = [("A", C.c_void_p), ("B_all", C.c_void_p), ("scale", C.c_void_p), ("stats", C.c_void_p),
+                ("inv_rowsum", C.c_void_p), ("inv_colsum", C.c_void_p), ("g", C.c_void_p), ("dA", C.c_void_p),
+                ("dB", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t), ("panel_bytes", C.c_size_t),
+                ("stream", C.c_void_p), ("side_stream", C.c_void_p), ("g_slot", C.c_void_p), ("g_slot_mc", C.c_void_p),
+                ("dB_mc_mine", C.c_void_p), ("dB_out", C.c_void_p), ("seq", C.c_void_p),
+                ("n", C.c_int), ("N", C.c_int), ("d", C.c_int), ("row_offset", C.c_int), ("mode", C.c_int),
+                ("use_gsum", C.c_int), ("world", C.c_int), ("rank", C.c_int), ("want_a", C.c_int), ("want_b", C.c_int),
+                ("g_on_side", C.c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol include/oneprot_clip.h declares
 SIGNATURES = {
     "oneprot_abi_version": (_i, []),
@@ -52,6 +74,21 @@ SIGNATURES = {
     "oneprot_mc_allreduce_f32": (_i, [_fp, _fp, _i, _i, _vp]),
     "oneprot_mc_reduce_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "oneprot_split_fp32": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
+    # host-side step sequencer + launch trace (csrc/clip_sequence.cu)
+    "oneprot_seq_fwd_ws_bytes": (_sz, [_i, _i]),
+    "oneprot_seq_fwd_begin": (_i, [C.POINTER(FwdSeq)]),
+    "oneprot_seq_fwd_end": (_i, [C.POINTER(FwdSeq)]),
+    "oneprot_seq_fwd": (_i, [C.POINTER(FwdSeq)]),
+    "oneprot_seq_create": (_i, [C.POINTER(C.c_void_p)]),
+    "oneprot_seq_destroy": (None, [_vp]),
+    "oneprot_seq_bwd_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _sz]),
+    "oneprot_seq_bwd_panels": (_i, [_i, _i, _i, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "oneprot_seq_bwd_begin": (_i, [C.POINTER(BwdSeq)]),
+    "oneprot_seq_bwd_main": (_i, [C.POINTER(BwdSeq)]),
+    "oneprot_seq_bwd_end": (_i, [C.POINTER(BwdSeq)]),
+    "oneprot_trace_begin": (None, [_i]),
+    "oneprot_trace_end": (_sz, [C.c_char_p, _sz]),
+    "oneprot_trace_note": (None, [C.c_char_p]),
 }
 
 _lib = None

@@ -10,8 +10,10 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "clip_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "ptx.cuh"), os.path.join(HERE, "..", "include", "oneprot_clip.h")]
+SRCS = [os.path.join(HERE, "csrc", "clip_kernels.cu"),     # kernels + one entry point per kernel
+        os.path.join(HERE, "csrc", "clip_sequence.cu")]    # host-side step sequencer + launch trace
+DEPS = SRCS + [os.path.join(HERE, "csrc", "ptx.cuh"), os.path.join(HERE, "csrc", "host_trace.h"),
+               os.path.join(HERE, "..", "include", "oneprot_clip.h")]
 LIB = os.path.join(HERE, "liboneprot_clip.so")
 
 NVCC_FLAGS = [
@@ -38,7 +40,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, SRC]
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, *SRCS]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

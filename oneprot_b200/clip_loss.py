@@ -31,6 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import kernels as _cuda_kernels
+from . import sequencer as _seq
 
 try:  # same guard as the reference (loss.py:5-11)
     import torch.distributed as dist
@@ -230,6 +231,17 @@ class _ClipLossFunction(torch.autograd.Function):
         N = W * n
         comm = _get_comm(W, rank, group, dev)
         scale_dev = scale_t.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        loss_dtype = cfg["loss_dtype"] or ops.in_dtype
+
+        if K is _cuda_kernels and _seq.enabled(cfg) and _seq.eligible(cfg, ops, comm, scale_t.requires_grad):
+            # host-side step sequencer: the launches below, issued from one C call per phase
+            loss32, flag = _seq.forward(ctx, ops, scale_dev, cfg, comm, K)
+            ctx.cfg, ctx.ops, ctx.comm = cfg, ops, comm
+            ctx.set_materialize_grads(False)
+            loss_out = loss32.reshape(()).to(loss_dtype)
+            loss_f32 = loss32.reshape(()).clone()
+            ctx.mark_non_differentiable(loss_f32, flag)
+            return loss_out, loss_f32, flag
 
         st = comm.begin_forward(ops, rank, W)          # second operand of all ranks + zeroed [colsum | rowsum | diag]
         B_all, sums = st["B_all"], st["sums"]
@@ -254,7 +266,6 @@ class _ClipLossFunction(torch.autograd.Function):
         ctx.scale_needs_grad = scale_t.requires_grad
         ctx.scale_meta = (scale_t.dtype, scale_t.device, scale_t.shape)
         ctx.set_materialize_grads(False)
-        loss_dtype = cfg["loss_dtype"] or ops.in_dtype
         loss_out = loss32.reshape(()).to(loss_dtype)
         loss_f32 = loss32.reshape(()).clone()
         ctx.mark_non_differentiable(loss_f32, flag)
@@ -263,6 +274,10 @@ class _ClipLossFunction(torch.autograd.Function):
     @staticmethod
     def _backward_impl(ctx, g_loss):
         K = _KERNELS
+        if getattr(ctx, "seq", None) is not None:
+            dA, dB = _seq.backward(ctx, g_loss, ctx.cfg, ctx.ops, ctx.comm, K)
+            return (_finish_grad(dA, ctx.ops, ctx.needs_input_grad[0]), _finish_grad(dB, ctx.ops, ctx.needs_input_grad[1]),
+                    None, None)
         cfg, ops, mode = ctx.cfg, ctx.ops, ctx.mode
         W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
         n, d, dk = ops.n, ops.d, ops.dk
@@ -448,11 +463,13 @@ class ClipLoss(nn.Module):
                    (bf16 in -> bf16 out).  The fp32 value is always kept in ``last_loss_fp32``.
       panel_bytes  bound of the bf16 dL/dZ panel workspace used by the backward.
       group        process group for the collectives (default: the world group).
+      host_sequencer  enqueue each phase of the step from one C call (sequencer.py; opt-in, also
+                   ONEPROT_SEQ=1) instead of kernel by kernel from Python.
     """
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
-                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None):
+                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -463,6 +480,7 @@ class ClipLoss(nn.Module):
         self.loss_dtype = loss_dtype
         self.panel_bytes = int(panel_bytes)
         self.group = group
+        self.host_sequencer = bool(host_sequencer)
         # cache state (same attributes as the reference, loss.py:68-70)
         self.prev_num_logits = 0
         self.labels = {}
@@ -533,7 +551,7 @@ class ClipLoss(nn.Module):
             scale_t = _float_scale_on(A.device, logit_scale)   # cached: no host-to-device copy per call
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
-                   panel_bytes=self.panel_bytes)
+                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer)
         total_loss, loss32, flag = _ClipLossFunction.apply(A, B, scale_t, cfg)
         self.last_loss_fp32, self.last_hazard_flag = loss32, flag
         return {"contrastive_loss": total_loss} if output_dict else total_loss

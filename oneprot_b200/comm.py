@@ -260,6 +260,49 @@ class NvlsComm(DistComm):
         self.K.mc_allreduce_f32(self.mc + self._off_small(st["p"]) + self.SUMS_AT * 4, out, cnt, 0)
         return out[0:3 * N]
 
+    # ---- raw addresses for the host-side step sequencer (sequencer.py) -----------------------
+    def seq_ready(self, n, dev):
+        """The sequencer covers the fused-gather forward and the side-stream backward only."""
+        chunks = next((c for c in (8, 4, 2, 1) if n % (c * 256) == 0), 0)
+        return bool(chunks) and not os.environ.get("ONEPROT_NO_FUSED_AG") and self.side_stream(dev) is not None
+
+    def _base(self):
+        return int(self.hdl.buffer_ptrs[self.rank])
+
+    def seq_forward_desc(self, ops, rank, world, stats_out_addr):
+        """begin_forward without its memsets and views: addresses only (the C side clears the
+        [g | maxima | sums] buffer itself)."""
+        n, dk = ops.n, ops.dk
+        N = world * n
+        self._ensure(n, dk, ops.d)
+        p = self.calls & 1
+        self.calls += 1
+        self.gen[p] = self.calls
+        base, small = self._base(), self._off_small(p)
+        ctl, mcb = base + self._off_ctl(), self.mc + self._off_ctl()
+        chunks = next(c for c in (8, 4, 2, 1) if n % (c * 256) == 0)
+        # field order of oneprot_ag_t
+        ag = (ops.B.data_ptr(), self.mc + self._off_bg(p) + rank * n * dk * 2, ctl + 2048, mcb, ctl, mcb + 1024, ctl + 1024,
+              stats_out_addr, self.calls & 0x7fffffff, rank, world, chunks, n)
+        return dict(B_all=base + self._off_bg(p), stats=base + small + self.STATS_AT * 4, zero_ptr=base + small,
+                    zero_bytes=(self.SUMS_AT + 3 * N) * 4, sums=base + small + self.SUMS_AT * 4,
+                    sums_mc=self.mc + small + self.SUMS_AT * 4, ag=ag, token=(p, self.calls))
+
+    def seq_backward_desc(self, n, d, rank, token):
+        base, g_off = self._base(), self._off_small(token[0]) + self.G_AT * 4
+        return dict(dB=base + self._off_db(), dB_mc_mine=self.mc + self._off_db() + rank * n * d * 2,
+                    g_slot=base + g_off, g_slot_mc=self.mc + g_off)
+
+    def seq_handle(self):
+        """Event holder of the C sequencer (one per provider)."""
+        if getattr(self, "_seq", None) is None:
+            import ctypes
+            from . import _lib
+            h = ctypes.c_void_p()
+            _lib.check(_lib.load().oneprot_seq_create(ctypes.byref(h)), "oneprot_seq_create")
+            self._seq = h
+        return self._seq
+
     # ---- backward ------------------------------------------------------------------------
     def gather_grad_outputs(self, g32, rank, world, token=None):
         p = token[0] if token is not None else ((self.calls - 1) & 1)

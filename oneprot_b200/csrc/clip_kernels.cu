@@ -16,6 +16,7 @@
 //   gemm2_kernel        the same GEMM on CTA pairs (tcgen05.mma cta_group::2), opt-in
 // plus the HBM-bound vector kernels and the multimem (NVLS) exchange kernels at the end.
 #include "ptx.cuh"
+#include "host_trace.h"
 #include "../../include/oneprot_clip.h"
 
 #include <cuda_bf16.h>
@@ -1428,6 +1429,11 @@ void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
 
 }  // namespace
 
+namespace opint {
+// error reporting for the other translation units of the library (clip_sequence.cu)
+int fail(int code, const std::string& msg) { return ::fail(code, msg); }
+}  // namespace opint
+
 extern "C" {
 
 int oneprot_abi_version(void) { return ONEPROT_ABI_VERSION; }
@@ -1450,6 +1456,8 @@ int oneprot_clip_rowstats(const void* A, const void* B_all, int n, int N, int d,
   if (!A || !B_all || !diag || !stats || n <= 0 || N <= 0 || d <= 0) return fail(ONEPROT_ERR_ARG, "rowstats: bad argument");
   if (d % 8) return fail(ONEPROT_ERR_ARG, "rowstats: d must be a multiple of 8");
   if (row_offset < 0 || row_offset + n > N) return fail(ONEPROT_ERR_ARG, "rowstats: row_offset out of range");
+  if (optrace::recording()) optrace::add("rowstats A=%p B=%p n=%d N=%d d=%d off=%d diag=%p stats=%p st=%p", A, B_all, n, N, d, row_offset, (void*)diag, (void*)stats, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const int total = n > N ? n : N;
   const int blocks = std::min(cdiv(total, 8), num_sms() * 8);
   op::rowstats_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1505,6 +1513,15 @@ int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int
     p.ag_bpc = rows / CH / op::BN;
     p.ag_chunk16 = static_cast<int>(static_cast<size_t>(rows / CH) * d * 2 / 16);
   }
+  if (optrace::recording()) {
+    optrace::add("fwd_sums A=%p B=%p n=%d N=%d d=%d scale=%p stats=%p rowsum=%p colsum=%p scratch=%p maxpass=%d st=%p", A, B_all, n, N,
+                 d, (const void*)scale_dev, (void*)stats, (void*)rowsum, (void*)colsum, scratch, (!ag && n == N) ? 1 : 0, stream);
+    if (ag)
+      optrace::add("  ag src=%p dst_mc=%p counters=%p flags_mc=%p flags=%p stats_mc=%p stats_all=%p stats_out=%p epoch=%u rank=%d world=%d chunks=%d rows=%d",
+                   ag->src, ag->dst_mc, (void*)ag->counters, (void*)ag->flags_mc, (const void*)ag->flags, (void*)ag->stats_mc,
+                   (const void*)ag->stats_all, (void*)ag->stats_out, ag->epoch, ag->rank, ag->world, ag->chunks, ag->rows_per_rank);
+  }
+  if (optrace::dry()) { g_launches += (!ag && n == N) ? 4 : 3; return ONEPROT_OK; }
   CUtensorMap mapA, mapB;
   int rc;
   if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
@@ -1540,6 +1557,11 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
     return fail(ONEPROT_ERR_ARG, "loss_finalize: null pointer");
   if (N <= 0 || n <= 0 || row_offset < 0 || row_offset + n > N) return fail(ONEPROT_ERR_ARG, "loss_finalize: bad sizes");
   if (reinterpret_cast<uintptr_t>(scratch) & 7) return fail(ONEPROT_ERR_ARG, "loss_finalize: scratch must be 8-byte aligned");
+  if (optrace::recording())
+    optrace::add("loss_finalize rowsum=%p colsum=%p diag=%p N=%d n=%d off=%d mode=%d scale=%p stats=%p loss=%p inv_rs=%p inv_cs=%p flag=%p scratch=%p st=%p",
+                 (const void*)rowsum_all, (const void*)colsum_all, (const void*)diag_all, N, n, row_offset, mode, (const void*)scale_dev,
+                 (const void*)stats, (void*)loss_out, (void*)inv_rowsum, (void*)inv_colsum, (void*)flag, scratch, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   // scratch: FIN_BLOCKS doubles + one zero-initialised counter (the kernel resets it)
   double* partial = static_cast<double*>(scratch);
   unsigned int* counter = reinterpret_cast<unsigned int*>(partial + op::FIN_BLOCKS);
@@ -1560,6 +1582,11 @@ int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, i
     return fail(ONEPROT_ERR_ARG, "bwd_weights: null pointer");
   if (world <= 0 || rank < 0 || rank >= world || N % world || n <= 0 || row_offset + n > N || what < 0 || what > 2)
     return fail(ONEPROT_ERR_ARG, "bwd_weights: bad sizes");
+  if (optrace::recording())
+    optrace::add("bwd_weights inv_rs=%p inv_cs=%p N=%d n=%d off=%d mode=%d use_gsum=%d part=%d world=%d rank=%d gvec=%p scale=%p wr=%p wc=%p dg=%p sA=%p sB=%p what=%d st=%p",
+                 (const void*)inv_rowsum, (const void*)inv_colsum, N, n, row_offset, mode, use_gsum, part, world, rank, (const void*)gvec_dev,
+                 (const void*)scale_dev, (void*)wr, (void*)wc, (void*)dg, (void*)out_scale_a, (void*)out_scale_b, what, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   op::bwd_weights_kernel<<<cdiv(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       inv_rowsum, inv_colsum, N, n, row_offset, mode, use_gsum, part, world, rank, gvec_dev, scale_dev, wr, wc, dg,
       out_scale_a, out_scale_b, what);
@@ -1574,6 +1601,10 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
   if (!A_rows || !B_all || !scale_dev || !stats || !wr || !wc || !dg || !Wz) return fail(ONEPROT_ERR_ARG, "dz_panel: null pointer");
   if (rows <= 0 || N <= 0 || d <= 0 || d % 8 || ldw < N || ldw % 8) return fail(ONEPROT_ERR_ARG, "dz_panel: bad sizes");
   if (reinterpret_cast<uintptr_t>(Wz) & 15) return fail(ONEPROT_ERR_ARG, "dz_panel: Wz must be 16-byte aligned");
+  if (optrace::recording())
+    optrace::add("dz_panel A=%p B=%p rows=%d N=%d d=%d grow0=%d scale=%p stats=%p wr=%p wc=%p dg=%p Wz=%p ldw=%d st=%p", A_rows, B_all, rows,
+                 N, d, grow0, (const void*)scale_dev, (const void*)stats, (const void*)wr, (const void*)wc, (const void*)dg, Wz, ldw, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   op::SParams p{};
   s_schedule(rows, N, 1, p);
   p.rows = rows; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = grow0;
@@ -1613,6 +1644,11 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
     return fail(ONEPROT_ERR_ARG, "gemm: dot_mat and rowdot_part go together, ld_dot >= Nc and a multiple of 8");
   if (M <= 0 || Nc <= 0 || K <= 0 || Nc % 8 || ldc % 8 || ldc < Nc) return fail(ONEPROT_ERR_ARG, "gemm: need Nc, ldc multiples of 8, ldc >= Nc");
   if (lda < (a_mn ? M : K) || ldb < (b_mn ? Nc : K)) return fail(ONEPROT_ERR_ARG, "gemm: leading dimension too small");
+  if (optrace::recording())
+    optrace::add("gemm A=%p lda=%d a_mn=%d B=%p ldb=%d b_mn=%d M=%d Nc=%d K=%d acc_in=%p acc_out=%p out=%p ldc=%d row_scale=%p dot_mat=%p ld_dot=%d rowdot=%p st=%p",
+                 A, lda, a_mn, B, ldb, b_mn, M, Nc, K, (const void*)acc_in, (void*)acc_out, out_bf16, ldc, (const void*)row_scale, dot_mat,
+                 ld_dot, (void*)rowdot_part, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   op::GParams p{};
   p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
   p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
@@ -1677,6 +1713,10 @@ int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int 
   if (Nc <= 0 || K <= 0 || Nc % 8 || ld_dst < Nc || ld_dst % 8 || (acc_in && (ld_acc < Nc || ld_acc % 8)))
     return fail(ONEPROT_ERR_ARG, "gemm_push: bad sizes");
   if (lda < M || ldb < Nc) return fail(ONEPROT_ERR_ARG, "gemm_push: leading dimension too small");
+  if (optrace::recording())
+    optrace::add("gemm_push A=%p lda=%d B=%p ldb=%d M=%d Nc=%d K=%d acc_in=%p ld_acc=%d row_scale=%p owners=%d my_rank=%d rows_per_owner=%d ld_dst=%d st=%p",
+                 A, lda, B, ldb, M, Nc, K, (const void*)acc_in, ld_acc, (const void*)row_scale, owners, my_rank, rows_per_owner, ld_dst, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   op::GParams p{};
   p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
   p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
@@ -1700,6 +1740,8 @@ int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int 
 int oneprot_sum_slots_bf16(const void* slots, int W, size_t count, void* out, void* stream) {
   if (!slots || !out || W <= 0 || count == 0 || count % 8 || (reinterpret_cast<uintptr_t>(slots) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return fail(ONEPROT_ERR_ARG, "sum_slots_bf16: count must be a multiple of 8, pointers 16-byte aligned");
+  if (optrace::recording()) optrace::add("sum_slots_bf16 slots=%p W=%d count=%zu out=%p st=%p", slots, W, count, out, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const size_t n16 = count / 8;
   const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   op::sum_slots_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(slots), W, n16, static_cast<uint4*>(out));
@@ -1710,6 +1752,8 @@ int oneprot_sum_slots_bf16(const void* slots, int W, size_t count, void* out, vo
 
 int oneprot_rowdot_bf16(const void* x, int ldx, const void* y, int ldy, int rows, int d, float* out, void* stream) {
   if (!x || !y || !out || rows <= 0 || d <= 0 || d % 8 || ldx % 8 || ldy % 8) return fail(ONEPROT_ERR_ARG, "rowdot: bad argument");
+  if (optrace::recording()) optrace::add("rowdot_bf16 x=%p ldx=%d y=%p ldy=%d rows=%d d=%d out=%p st=%p", x, ldx, y, ldy, rows, d, (void*)out, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
   op::rowdot_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(y), ldy, rows, d, out);
@@ -1720,6 +1764,8 @@ int oneprot_rowdot_bf16(const void* x, int ldx, const void* y, int ldy, int rows
 
 int oneprot_sum_f32(const float* v, int count, float* out, void* stream) {
   if (!v || !out || count <= 0) return fail(ONEPROT_ERR_ARG, "sum: bad argument");
+  if (optrace::recording()) optrace::add("sum_f32 v=%p count=%d out=%p st=%p", (const void*)v, count, (void*)out, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   op::sum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(v, count, out);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
@@ -1776,6 +1822,8 @@ int oneprot_rowdot(const void* x, const void* y, int rows, int d, int is_fp32, f
 int oneprot_mc_store(const void* src, void* dst_mc, size_t bytes, void* stream) {
   if (!src || !dst_mc || bytes == 0 || bytes % 16 || (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst_mc) & 15))
     return fail(ONEPROT_ERR_ARG, "mc_store: need 16-byte aligned pointers and size");
+  if (optrace::recording()) optrace::add("mc_store src=%p dst_mc=%p bytes=%zu st=%p", src, dst_mc, bytes, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const size_t n16 = bytes / 16;
   const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   op::mc_store_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst_mc), n16);
@@ -1788,6 +1836,8 @@ int oneprot_mc_allreduce_f32(const float* src_mc, float* dst, int count, int op,
   if (!src_mc || !dst || count <= 0 || count % 4 || (op != 0 && op != 1) || (reinterpret_cast<uintptr_t>(src_mc) & 15) ||
       (reinterpret_cast<uintptr_t>(dst) & 15))
     return fail(ONEPROT_ERR_ARG, "mc_allreduce: count must be a multiple of 4, pointers 16-byte aligned");
+  if (optrace::recording()) optrace::add("mc_allreduce_f32 src_mc=%p dst=%p count=%d op=%d st=%p", (const void*)src_mc, (void*)dst, count, op, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   op::mc_allreduce_kernel<<<cdiv(count / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src_mc, dst, count, op);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
@@ -1797,6 +1847,8 @@ int oneprot_mc_allreduce_f32(const float* src_mc, float* dst, int count, int op,
 int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* stream) {
   if (!src_mc || !dst || bytes == 0 || bytes % 16 || (reinterpret_cast<uintptr_t>(src_mc) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
     return fail(ONEPROT_ERR_ARG, "mc_reduce_bf16: need 16-byte aligned pointers and size");
+  if (optrace::recording()) optrace::add("mc_reduce_bf16 src_mc=%p dst=%p bytes=%zu st=%p", src_mc, dst, bytes, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const size_t n16 = bytes / 16;
   const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
   op::mc_reduce_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src_mc), static_cast<uint4*>(dst), n16);
@@ -1808,6 +1860,8 @@ int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* st
 int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int terms, void* stream) {
   if (!x || !out || rows <= 0 || d <= 0 || (terms != 3 && terms != 6) || (side != 0 && side != 1))
     return fail(ONEPROT_ERR_ARG, "split_fp32: bad argument");
+  if (optrace::recording()) optrace::add("split_fp32 x=%p out=%p rows=%d d=%d side=%d terms=%d st=%p", (const void*)x, out, rows, d, side, terms, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const size_t total = static_cast<size_t>(rows) * d;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(num_sms()) * 16));
   op::split_fp32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(out), rows, d, side, terms);

@@ -36,16 +36,60 @@ class stream_scope:
         return False
 
 
+def current_stream_handle() -> int:
+    """Raw cudaStream_t of torch's current stream (dry-run traces: the test's stand-in)."""
+    if _DRY is not None:
+        return int(_DRY())
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
 def _stream() -> C.c_void_p:
     s = getattr(_TLS, "stream", None)
     if s is None:
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(current_stream_handle())
     if s == "unset":
-        s = _TLS.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        s = _TLS.stream = C.c_void_p(current_stream_handle())
     return s
 
 
+# Launch-trace dry run (tests/test_sequencer_cpu.py): a callable returning the stand-in handle of the
+# "current stream".  While it is set the library skips every CUDA call (oneprot_trace_begin(1)), so
+# the wrappers accept CPU tensors - their addresses only label the trace lines.
+_DRY = None
+
+
+class launch_trace:
+    """Records one text line per entry-point call of liboneprot_clip.so; ``dry_stream`` (a callable
+    returning the current stand-in stream handle) makes it a dry run without any CUDA work."""
+
+    def __init__(self, dry_stream=None):
+        self.dry_stream = dry_stream
+        self.lines = []
+
+    def __enter__(self):
+        global _DRY
+        _lib.load().oneprot_trace_begin(1 if self.dry_stream is not None else 0)
+        _DRY = self.dry_stream
+        return self
+
+    def __exit__(self, *exc):
+        global _DRY
+        _DRY = None
+        lib = _lib.load()
+        n = int(lib.oneprot_trace_end(None, 0))
+        buf = C.create_string_buffer(n + 1)
+        lib.oneprot_trace_end(buf, n + 1)
+        self.lines = [ln for ln in buf.value.decode().split("\n") if ln]
+        return False
+
+
+def trace_note(text: str):
+    _lib.load().oneprot_trace_note(text.encode())
+
+
 def _need_cuda(*ts):
+    if _DRY is not None:
+        return
     for t in ts:
         if t is not None and not t.is_cuda:
             raise _lib.OneProtKernelError("oneprot_b200 kernels need CUDA tensors (no CPU fallback exists)")
@@ -117,7 +161,7 @@ def loss_finalize(rowsum_all, colsum_all, diag_all, n: int, row_offset: int, mod
                   loss_out, inv_rowsum, inv_colsum, flag):
     _need_cuda(rowsum_all, colsum_all, diag_all, loss_out, inv_rowsum, inv_colsum, flag)
     N = rowsum_all.numel()
-    key = (rowsum_all.device.index, torch.cuda.current_stream().cuda_stream)
+    key = (rowsum_all.device.index, current_stream_handle())
     scratch = _FIN_SCRATCH.get(key)
     if scratch is None:
         scratch = _FIN_SCRATCH[key] = torch.zeros(64, dtype=torch.float64, device=rowsum_all.device)

@@ -115,6 +115,24 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
                                float* loss_out, float* inv_rowsum, float* inv_colsum, int* flag, void* scratch,
                                void* stream);
 
+/* ---- two-reference (robust) path: inputs whose row / column maxima are too far apart for one
+ * common reference.  (1) oneprot_clip_rowcol_max: per-row maxima of the panel (complete) and
+ * per-column maxima over this rank's rows (max them across ranks), in log2 units, same
+ * tensor-core mainloop as the forward.  (2) oneprot_augment_bf16 appends 8 columns to an operand:
+ * [x | e | 0..0] with e = bf16(-ref/c) or 1, so that a GEMM over d + 8 columns yields
+ * x_ij - ref'_i with ref'_i = -c * float(e) (returned in ref_q).  The forward / dz / GEMM kernels
+ * then run unchanged on the augmented operands with G = 0 (stats = [*, *, 0, 1]), once per softmax
+ * direction.  (3) oneprot_clip_loss_finalize_ex adds the per-element references back:
+ * LSE_row_i = ln2 * (row_ref[i] + log2 rowsum_i). */
+int oneprot_clip_rowcol_max(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev, float* rowmax,
+                            float* colmax, void* scratch, size_t scratch_bytes, void* stream);
+int oneprot_augment_bf16(const void* in, int rows, int d, const float* ref, const float* scale_dev, void* out, float* ref_q,
+                         void* stream);
+int oneprot_clip_loss_finalize_ex(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N, int n,
+                                  int row_offset, int mode, const float* scale_dev, const float* stats, float* loss_out,
+                                  float* inv_rowsum, float* inv_colsum, int* flag, void* scratch, const float* row_ref,
+                                  const float* col_ref, void* stream);
+
 /* ---- backward ----------------------------------------------------------------------------- */
 
 /* Per-row / per-column / diagonal coefficients of dL/dZ for the panel of this rank:

@@ -69,11 +69,11 @@ from .comm import _all_gather_rows, _reduce_scatter_rows, make_comm   # noqa: E4
 _COMMS = {}     # (device, group id, world, rank, kernel provider) -> exchange provider (owns the NVLS workspace)
 
 
-def _get_comm(world, rank, group, device):
-    key = (str(device), id(group), world, rank, id(_KERNELS))
+def _get_comm(world, rank, group, device, prefer=None):
+    key = (str(device), id(group), world, rank, id(_KERNELS), prefer)
     c = _COMMS.get(key)
     if c is None:
-        c = make_comm(_KERNELS, world, rank, group, device)
+        c = make_comm(_KERNELS, world, rank, group, device, prefer=prefer)
         _COMMS[key] = c
     return c
 
@@ -206,6 +206,48 @@ class _GemmChain:
         self.done += 1
 
 
+def _robust_forward(K, comm, ops, B_all, scale_dev, diag_loc, n, N, off, W, mode):
+    """Forward of the two-reference path.  References: rho_i = max_j x_ij (this rank's rows),
+    gamma_j = max_i x_ij (all ranks).  Augmenting the operands with the reference as one more K
+    column makes the unchanged tensor-core kernels produce x_ij - rho'_i (row direction) resp.
+    x_ij - gamma'_j (column direction) with G = 0, so every sum is in [1, N]: no overflow, no
+    underflow, for any inputs.  Costs one max pass + two sum passes (3 GEMM units instead of 1)."""
+    dev = ops.A.device
+    dk = ops.A.shape[1]
+    rowmax = torch.empty(n, dtype=torch.float32, device=dev)
+    colmax = torch.empty(N, dtype=torch.float32, device=dev)
+    K.rowcol_max(ops.A, B_all, scale_dev, rowmax, colmax)
+    if W > 1:
+        dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=comm.group)
+    A_r = torch.empty(n, dk + 8, dtype=torch.bfloat16, device=dev)
+    A_1 = torch.empty(n, dk + 8, dtype=torch.bfloat16, device=dev)
+    B_1 = torch.empty(N, dk + 8, dtype=torch.bfloat16, device=dev)
+    B_c = torch.empty(N, dk + 8, dtype=torch.bfloat16, device=dev)
+    # vec: [colsum | rowsum | diag | row_ref] in global order, summed over ranks
+    vec = torch.zeros(4 * N, dtype=torch.float32, device=dev)
+    col_ref = torch.empty(N, dtype=torch.float32, device=dev)
+    K.augment(ops.A, rowmax, scale_dev, A_r, vec[3 * N + off:3 * N + off + n])
+    K.augment(B_all, None, scale_dev, B_1, None)
+    K.augment(ops.A, None, scale_dev, A_1, None)
+    K.augment(B_all, colmax, scale_dev, B_c, col_ref)
+    stats = torch.zeros(4, dtype=torch.float32, device=dev)
+    stats[3] = 1.0                                   # exact-reference override with stats[2] = 0  =>  G = 0
+    junk_r = torch.empty(n, dtype=torch.float32, device=dev)
+    junk_c = torch.empty(N, dtype=torch.float32, device=dev)
+    K.fwd_sums(A_r, B_1, scale_dev, stats, vec[N + off:N + off + n], junk_c)      # row sums (complete)
+    K.fwd_sums(A_1, B_c, scale_dev, stats, junk_r, vec[0:N])                      # column sums (partial)
+    vec[2 * N + off:2 * N + off + n].copy_(diag_loc)
+    if W > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=comm.group)
+    out = torch.empty(1 + 2 * N, dtype=torch.float32, device=dev)
+    loss32, inv_rs, inv_cs = out[0:1], out[1:1 + N], out[1 + N:]
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    K.loss_finalize(vec[N:2 * N], vec[0:N], vec[2 * N:3 * N], n, off, mode, scale_dev, stats, loss32, inv_rs, inv_cs, flag,
+                    row_ref=vec[3 * N:4 * N], col_ref=col_ref)
+    return dict(loss32=loss32, inv_rs=inv_rs, inv_cs=inv_cs, flag=flag, stats=stats,
+                dz_ops={1: (A_r, B_1), 2: (A_1, B_c)})
+
+
 # ---------------------------------------------------------------------------------------------
 # the autograd function
 # ---------------------------------------------------------------------------------------------
@@ -261,6 +303,20 @@ class _ClipLossFunction(torch.autograd.Function):
         mode = K.MODE_LOCAL if (W > 1 and cfg["local_loss"]) else K.MODE_GLOBAL
         K.loss_finalize(rowsum_all, colsum, diag_all, n, off, mode, scale_dev, stats, loss32, inv_rs, inv_cs, flag)
 
+        ctx.dz_ops = None
+        robust = cfg["robust"]
+        if robust == "always" or (robust == "auto" and int(flag.item()) != 0):     # "auto" pays one host sync
+            # Two-reference path: per-row and per-column references, one pass per softmax direction
+            # on operands augmented with the reference as an extra K column.
+            B_all = comm.b_all_for_backward(ops, B_all, st["token"], rank, W)
+            if W > 1 and comm.name == "nvls":
+                B_all = B_all.clone()            # the symmetric buffer is recycled by later forwards
+            comm = _get_comm(W, rank, group, dev, prefer="dist") if W > 1 else comm
+            rr = _robust_forward(K, comm, ops, B_all, scale_dev, diag_all[off:off + n], n, N, off, W, mode)
+            loss32, inv_rs, inv_cs, flag, stats = rr["loss32"], rr["inv_rs"], rr["inv_cs"], rr["flag"], rr["stats"]
+            ctx.dz_ops = rr["dz_ops"]
+            st = dict(st, token=None)
+
         ctx.cfg, ctx.ops, ctx.mode, ctx.comm, ctx.token = cfg, ops, mode, comm, st["token"]
         ctx.B_all, ctx.scale_dev, ctx.stats, ctx.inv_rs, ctx.inv_cs = B_all, scale_dev, stats, inv_rs, inv_cs
         ctx.scale_needs_grad = scale_t.requires_grad
@@ -311,8 +367,8 @@ class _ClipLossFunction(torch.autograd.Function):
         exchange_b = W > 1
         if local and not gwg:
             passes = [(1, need_a or need_s, False), (2, False, need_b or need_s)]
-        elif local and need_s:
-            passes = [(1, True, True), (2, True, True)]
+        elif (local and need_s) or ctx.dz_ops is not None:
+            passes = [(1, True, True), (2, True, True)]       # one pass per softmax direction
         else:
             passes = [(0, need_a or need_s, need_b or (W > 1))]
         # collectives must be entered by every rank: with W > 1 the partial dB is always exchanged
@@ -360,7 +416,12 @@ class _ClipLossFunction(torch.autograd.Function):
             ev_rs, dB_async = None, None
             for qi, (r0, rows) in enumerate(panels):
                 A_rows = ops.A[r0:r0 + rows]
-                K.dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc, dg[r0:r0 + rows], Wz)
+                if ctx.dz_ops is not None:       # two-reference path: augmented operands of this direction
+                    A_aug, B_aug = ctx.dz_ops[part]
+                    K.dz_panel(A_aug[r0:r0 + rows], B_aug, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc,
+                               dg[r0:r0 + rows], Wz)
+                else:
+                    K.dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc, dg[r0:r0 + rows], Wz)
                 Wp = Wz[:rows]
                 if ev_g is not None:
                     main.wait_event(ev_g)        # GEMM epilogues read the output scales
@@ -465,11 +526,16 @@ class ClipLoss(nn.Module):
       group        process group for the collectives (default: the world group).
       host_sequencer  enqueue each phase of the step from one C call (sequencer.py; opt-in, also
                    ONEPROT_SEQ=1) instead of kernel by kernel from Python.
+      robust       "off" (default): one common reference, validated window, device flag;
+                   "always": per-row / per-column references for arbitrary inputs (2.25x the work);
+                   "auto": run the normal path, read the device flag (one host sync per forward)
+                   and fall back to the two-reference path only when it is raised.
     """
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
-                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False):
+                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
+                 robust: str = "off"):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -481,6 +547,9 @@ class ClipLoss(nn.Module):
         self.panel_bytes = int(panel_bytes)
         self.group = group
         self.host_sequencer = bool(host_sequencer)
+        if robust not in ("off", "auto", "always"):
+            raise ValueError("robust must be 'off', 'auto' or 'always'")
+        self.robust = robust
         # cache state (same attributes as the reference, loss.py:68-70)
         self.prev_num_logits = 0
         self.labels = {}
@@ -551,7 +620,7 @@ class ClipLoss(nn.Module):
             scale_t = _float_scale_on(A.device, logit_scale)   # cached: no host-to-device copy per call
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
-                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer)
+                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer, robust=self.robust)
         total_loss, loss32, flag = _ClipLossFunction.apply(A, B, scale_t, cfg)
         self.last_loss_fp32, self.last_hazard_flag = loss32, flag
         return {"contrastive_loss": total_loss} if output_dict else total_loss

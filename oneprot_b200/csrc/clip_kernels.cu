@@ -170,6 +170,21 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32]) {
   }
 }
 
+// same butterfly with max: lane l ends with the maximum over the 32 lanes of column l in v[0]
+__device__ __forceinline__ void warp_transpose_max32(float (&v)[32]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < o; ++k) {
+      const float keep = up ? v[k + o] : v[k];
+      const float send = up ? v[k] : v[k + o];
+      v[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // S-kernels: logits tile = A_rows(128 x d) . B_all(256 x d)^T, both K-major.
 // Work item = (column block j, chunk of CI row blocks); rows sweep inside an item so that the
@@ -257,12 +272,12 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
   }
 }
 
-enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2 };
+enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3 };   // RCMAX: per-row and per-column maxima
 
 template <int EPI>
 struct SCfg {
   static constexpr int NS = 4;                                             // operand ring depth
-  static constexpr int STAGING = (EPI == EPI_DZ) ? STORE_STAGING_BYTES : 0;
+  static constexpr int STAGING = (EPI == EPI_DZ) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX need none
   static constexpr int SMEM = smem_bytes(NS, STAGING);
 };
 
@@ -377,13 +392,13 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int lane = lane_id();
     const int r = q * 32 + lane; // row inside the tile
     float c, negG;
-    if (EPI == EPI_MAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
+    if (EPI == EPI_MAX || EPI == EPI_RCMAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
     else load_c_and_G(p, c, negG);
     int acc = 0;
     uint32_t acc_phase = 0;
     float xmax = 0.f;               // EPI_MAX: running max(0, x) of this thread
 
-    float colacc[EPI == EPI_FWD ? 128 : 1];
+    float colacc[(EPI == EPI_FWD || EPI == EPI_RCMAX) ? 128 : 1];
     // DZ: bf16 staging of 64 columns of this warp group's half tile = one SWIZZLE_128B box {64 cols, 128 rows}
     const uint32_t colvec_s = smem_u32(&s.tail->colvec[0]);
     const uint32_t stage_s = smem_u32(s.staging) + h * 16384;
@@ -392,9 +407,9 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
       const int j0 = jb * BN + h * 128;   // first column this thread sees
-      if (EPI == EPI_FWD) {
+      if (EPI == EPI_FWD || EPI == EPI_RCMAX) {
 #pragma unroll
-        for (int k = 0; k < 128; ++k) colacc[k] = 0.f;
+        for (int k = 0; k < 128; ++k) colacc[k] = (EPI == EPI_FWD) ? 0.f : -INFINITY;
       } else if (EPI == EPI_DZ) {
         // stage the per-column weights of this item's 256 columns
         named_bar_sync(1, EPI_THREADS);
@@ -448,6 +463,18 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int k = 0; k < 32; ++k) {
               const bool ok = rowok && (j0 + cc * 32 + k < p.N);
               xmax = fmaxf(xmax, ok ? v[k] * c : 0.f);
+            }
+            continue;
+          }
+          if (EPI == EPI_RCMAX) {
+            // rsum doubles as the running row maximum of this 128-column slice (log2 units)
+            if (cc == 0) rsum = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const bool ok = rowok && (j0 + cc * 32 + k < p.N);
+              const float x = ok ? v[k] * c : -INFINITY;
+              rsum = fmaxf(rsum, x);
+              colacc[cc * 32 + k] = fmaxf(colacc[cc * 32 + k], x);
             }
             continue;
           }
@@ -511,19 +538,19 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
           }
         }
-        if (EPI == EPI_FWD) {
+        if (EPI == EPI_FWD || EPI == EPI_RCMAX) {
           p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (EPI == EPI_FWD) {
-        // flush column sums of this item: reduce over the 32 rows of the warp, one slot per (chunk, quadrant)
+      if (EPI == EPI_FWD || EPI == EPI_RCMAX) {
+        // flush column sums (maxima) of this item: reduce over the 32 rows of the warp, one slot per (chunk, quadrant)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           float v[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) v[k] = colacc[cc * 32 + k];
-          warp_transpose_sum32(v);
+          if (EPI == EPI_FWD) warp_transpose_sum32(v); else warp_transpose_max32(v);
           p.colpart[static_cast<size_t>(ch * 4 + q) * p.ldc + j0 + cc * 32 + lane] = v[0];  // ldc covers nJ*256
         }
       }
@@ -980,6 +1007,53 @@ __global__ void reduce_slots_kernel(const float* __restrict__ part, int slots, i
   }
 }
 
+// out[k] = max_s part[s*ld + k]
+__global__ void reduce_slots_max_kernel(const float* __restrict__ part, int slots, int ld, int count, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  float acc = -INFINITY;
+  if (k < count)
+    for (int s = grp; s < slots; s += 8) acc = fmaxf(acc, part[static_cast<size_t>(s) * ld + k]);
+  red[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && k < count) {
+    float t = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t = fmaxf(t, red[g][lane]);
+    out[k] = t;
+  }
+}
+
+// Operand augmentation for the two-reference (robust) path: out = [in | e | 0 x 7] (row pitch d + 8)
+// with e = bf16(-ref[i] / c) (ref != nullptr) or 1.  The GEMM over d + 8 columns against an operand
+// augmented with 1 (resp. e) then yields x_ij - ref'_i, where ref'_i = -c * float(e) is returned in
+// ref_q: the reference actually applied, exact in fp32 although e is rounded to bf16.
+__global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, int d, const float* __restrict__ ref,
+                               const float* __restrict__ scale, __nv_bfloat16* __restrict__ out, float* __restrict__ ref_q) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float c = *scale * LOG2E;
+  const int ld = d + 8;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * d);
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ld);
+    for (int k = lane; k < d / 8; k += 32) dst[k] = src[k];
+    if (lane == 0) {
+      __nv_bfloat16 e = __float2bfloat16_rn(1.f);
+      if (ref) {
+        e = __float2bfloat16_rn(-ref[row] / c);
+        if (ref_q) ref_q[row] = -c * __bfloat162float(e);
+      }
+      __nv_bfloat16 tail[8];
+      tail[0] = e;
+#pragma unroll
+      for (int u = 1; u < 8; ++u) tail[u] = __float2bfloat16_rn(0.f);
+      dst[d / 8] = *reinterpret_cast<uint4*>(tail);
+    }
+  }
+}
+
 // loss value, reciprocal sums, hazard flag.  FIN_BLOCKS blocks each reduce a fixed slice in double
 // precision; the last block to finish adds the per-block partials in index order (deterministic).
 constexpr int FIN_BLOCKS = 32;
@@ -987,7 +1061,8 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
                                      const float* __restrict__ diag, int N, int n, int row_offset, int mode,
                                      const float* __restrict__ scale, const float* __restrict__ stats,
                                      float* __restrict__ loss_out, float* __restrict__ inv_rs, float* __restrict__ inv_cs,
-                                     int* __restrict__ flag, double* __restrict__ partial, unsigned int* __restrict__ counter) {
+                                     int* __restrict__ flag, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                                     const float* __restrict__ row_ref, const float* __restrict__ col_ref) {
   __shared__ double red[32];
   __shared__ int bad_s;
   __shared__ bool is_last;
@@ -1009,7 +1084,8 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
     inv_cs[k] = 1.f / cs;
     if (k >= lo && k < hi) {
       const float zd = s * diag[k];
-      acc += static_cast<double>(LN2 * (G + log2f(rs)) - zd) + static_cast<double>(LN2 * (G + log2f(cs)) - zd);
+      const float gr = row_ref ? row_ref[k] : G, gc = col_ref ? col_ref[k] : G;   // two-reference path: per-element G
+      acc += static_cast<double>(LN2 * (gr + log2f(rs)) - zd) + static_cast<double>(LN2 * (gc + log2f(cs)) - zd);
     }
   }
   if (bad) bad_s = 1;
@@ -1553,14 +1629,23 @@ int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int
 int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N, int n,
                                int row_offset, int mode, const float* scale_dev, const float* stats, float* loss_out,
                                float* inv_rowsum, float* inv_colsum, int* flag, void* scratch, void* stream) {
+  return oneprot_clip_loss_finalize_ex(rowsum_all, colsum_all, diag_all, N, n, row_offset, mode, scale_dev, stats, loss_out,
+                                       inv_rowsum, inv_colsum, flag, scratch, nullptr, nullptr, stream);
+}
+
+int oneprot_clip_loss_finalize_ex(const float* rowsum_all, const float* colsum_all, const float* diag_all, int N, int n,
+                                  int row_offset, int mode, const float* scale_dev, const float* stats, float* loss_out,
+                                  float* inv_rowsum, float* inv_colsum, int* flag, void* scratch, const float* row_ref,
+                                  const float* col_ref, void* stream) {
   if (!rowsum_all || !colsum_all || !diag_all || !scale_dev || !stats || !loss_out || !inv_rowsum || !inv_colsum || !flag || !scratch)
     return fail(ONEPROT_ERR_ARG, "loss_finalize: null pointer");
   if (N <= 0 || n <= 0 || row_offset < 0 || row_offset + n > N) return fail(ONEPROT_ERR_ARG, "loss_finalize: bad sizes");
   if (reinterpret_cast<uintptr_t>(scratch) & 7) return fail(ONEPROT_ERR_ARG, "loss_finalize: scratch must be 8-byte aligned");
+  if ((row_ref != nullptr) != (col_ref != nullptr)) return fail(ONEPROT_ERR_ARG, "loss_finalize: row_ref and col_ref go together");
   if (optrace::recording())
-    optrace::add("loss_finalize rowsum=%p colsum=%p diag=%p N=%d n=%d off=%d mode=%d scale=%p stats=%p loss=%p inv_rs=%p inv_cs=%p flag=%p scratch=%p st=%p",
+    optrace::add("loss_finalize rowsum=%p colsum=%p diag=%p N=%d n=%d off=%d mode=%d scale=%p stats=%p loss=%p inv_rs=%p inv_cs=%p flag=%p scratch=%p row_ref=%p col_ref=%p st=%p",
                  (const void*)rowsum_all, (const void*)colsum_all, (const void*)diag_all, N, n, row_offset, mode, (const void*)scale_dev,
-                 (const void*)stats, (void*)loss_out, (void*)inv_rowsum, (void*)inv_colsum, (void*)flag, scratch, stream);
+                 (const void*)stats, (void*)loss_out, (void*)inv_rowsum, (void*)inv_colsum, (void*)flag, scratch, (const void*)row_ref, (const void*)col_ref, stream);
   if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   // scratch: FIN_BLOCKS doubles + one zero-initialised counter (the kernel resets it)
   double* partial = static_cast<double*>(scratch);
@@ -1568,7 +1653,47 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
   const int blocks = std::min(op::FIN_BLOCKS, cdiv(N, 256));
   op::loss_finalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       rowsum_all, colsum_all, diag_all, N, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum, inv_colsum, flag,
-      partial, counter);
+      partial, counter, row_ref, col_ref);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_clip_rowcol_max(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev, float* rowmax,
+                            float* colmax, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!A || !B_all || !scale_dev || !rowmax || !colmax || !scratch) return fail(ONEPROT_ERR_ARG, "rowcol_max: null pointer");
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "rowcol_max: need n, N > 0 and d a positive multiple of 8");
+  if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "rowcol_max: scratch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  op::SParams p{};
+  s_schedule(n, N, 2, p);
+  p.rows = n; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = 0;
+  p.scale = scale_dev; p.stats = nullptr;
+  p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
+  p.rowpart = static_cast<float*>(scratch);
+  p.colpart = p.rowpart + 2 * static_cast<size_t>(p.nJ) * p.ldr;
+  CUtensorMap mapA, mapB;
+  int rc;
+  if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_RCMAX>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_RCMAX>, smem))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_RCMAX><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+  op::reduce_slots_max_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowmax);
+  op::reduce_slots_max_kernel<<<cdiv(N, 32), 256, 0, st>>>(p.colpart, 4 * p.nChunks, p.ldc, N, colmax);
+  g_launches += 3;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_augment_bf16(const void* in, int rows, int d, const float* ref, const float* scale_dev, void* out, float* ref_q,
+                         void* stream) {
+  if (!in || !out || !scale_dev || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "augment: need d a positive multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(ONEPROT_ERR_ARG, "augment: pointers must be 16-byte aligned");
+  const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
+  op::augment_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), rows, d, ref, scale_dev, static_cast<__nv_bfloat16*>(out), ref_q);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

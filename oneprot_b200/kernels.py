@@ -158,17 +158,45 @@ _FIN_SCRATCH = {}   # device index -> zero-initialised scratch of oneprot_clip_l
 
 
 def loss_finalize(rowsum_all, colsum_all, diag_all, n: int, row_offset: int, mode: int, scale_dev, stats,
-                  loss_out, inv_rowsum, inv_colsum, flag):
-    _need_cuda(rowsum_all, colsum_all, diag_all, loss_out, inv_rowsum, inv_colsum, flag)
+                  loss_out, inv_rowsum, inv_colsum, flag, row_ref=None, col_ref=None):
+    """row_ref / col_ref: per-element references (log2 units) of the two-reference path."""
+    _need_cuda(rowsum_all, colsum_all, diag_all, loss_out, inv_rowsum, inv_colsum, flag, row_ref, col_ref)
     N = rowsum_all.numel()
     key = (rowsum_all.device.index, current_stream_handle())
     scratch = _FIN_SCRATCH.get(key)
     if scratch is None:
         scratch = _FIN_SCRATCH[key] = torch.zeros(64, dtype=torch.float64, device=rowsum_all.device)
-    check(_lib.load().oneprot_clip_loss_finalize(ptr(rowsum_all), ptr(colsum_all), ptr(diag_all), N, n, row_offset,
-                                                 mode, ptr(scale_dev), ptr(stats), ptr(loss_out), ptr(inv_rowsum),
-                                                 ptr(inv_colsum), ptr(flag), ptr(scratch), _stream()),
-          "oneprot_clip_loss_finalize")
+    check(_lib.load().oneprot_clip_loss_finalize_ex(ptr(rowsum_all), ptr(colsum_all), ptr(diag_all), N, n, row_offset,
+                                                    mode, ptr(scale_dev), ptr(stats), ptr(loss_out), ptr(inv_rowsum),
+                                                    ptr(inv_colsum), ptr(flag), ptr(scratch), ptr(row_ref), ptr(col_ref),
+                                                    _stream()),
+          "oneprot_clip_loss_finalize_ex")
+
+
+def rowcol_max(A, B_all, scale_dev, rowmax, colmax, scratch=None):
+    """Per-row maxima (complete) and per-column maxima over these rows of x = c <a_i, b_j> (log2 units)."""
+    _need_cuda(A, B_all, scale_dev, rowmax, colmax)
+    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
+    n, d = A.shape
+    N = B_all.shape[0]
+    need = fwd_scratch_bytes(n, N)
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=A.device)
+    check(_lib.load().oneprot_clip_rowcol_max(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(rowmax), ptr(colmax),
+                                              ptr(scratch), scratch.numel() * scratch.element_size(), _stream()),
+          "oneprot_clip_rowcol_max")
+    return scratch
+
+
+def augment(x, ref, scale_dev, out, ref_q=None):
+    """out = [x | bf16(-ref/c) or 1 | 0 x 7]; ref_q = reference actually applied (see oneprot_augment_bf16)."""
+    _need_cuda(x, ref, scale_dev, out, ref_q)
+    _need(x, torch.bfloat16, "x"); _need(out, torch.bfloat16, "out")
+    rows, d = x.shape
+    if out.shape != (rows, d + 8):
+        raise ValueError("augment: out must be rows x (d + 8)")
+    check(_lib.load().oneprot_augment_bf16(ptr(x), rows, d, ptr(ref), ptr(scale_dev), ptr(out), ptr(ref_q), _stream()),
+          "oneprot_augment_bf16")
 
 
 def bwd_weights(inv_rowsum, inv_colsum, n: int, row_offset: int, mode: int, use_gsum: bool, part: int, world: int,

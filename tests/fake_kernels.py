@@ -39,6 +39,8 @@ def launch_count_reset():
 def _G(scale_dev, stats):
     c = float(scale_dev[0]) * LOG2E
     U = abs(c) * math.sqrt(float(stats[0]) * float(stats[1]))
+    if stats.numel() > 3 and float(stats[3]) != 0.0:        # exact-max / two-reference override
+        return c, max(0.0, float(stats[2]) - 100.0)
     return c, max(0.0, U - 100.0)
 
 
@@ -65,14 +67,16 @@ def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
 
 
 def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum,
-                  inv_colsum, flag):
+                  inv_colsum, flag, row_ref=None, col_ref=None):
     CALLS.append("loss_finalize")
     c, G = _G(scale_dev, stats)
     s = float(scale_dev[0])
     N = rowsum_all.numel()
     lo, hi = (row_offset, row_offset + n) if mode == MODE_LOCAL else (0, N)
-    rl = (G + torch.log2(rowsum_all.double())) / LOG2E
-    cl = (G + torch.log2(colsum_all.double())) / LOG2E
+    gr = row_ref.double() if row_ref is not None else G
+    gc = col_ref.double() if col_ref is not None else G
+    rl = (gr + torch.log2(rowsum_all.double())) / LOG2E
+    cl = (gc + torch.log2(colsum_all.double())) / LOG2E
     zd = s * diag_all.double()
     loss_out[0] = float(((rl - zd)[lo:hi].sum() + (cl - zd)[lo:hi].sum()) / (2 * (hi - lo)))
     inv_rowsum.copy_((1.0 / rowsum_all.double()).float())
@@ -81,6 +85,30 @@ def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_d
         or (rowsum_all < 1e-27).any() or (colsum_all < 1e-27).any()
     if bool(bad):
         flag[0] = int(flag[0]) | 1
+
+
+def rowcol_max(A, B_all, scale_dev, rowmax, colmax, scratch=None):
+    CALLS.append("rowcol_max")
+    c = float(scale_dev[0]) * LOG2E
+    X = c * (A.double() @ B_all.double().T)
+    rowmax.copy_(X.max(1).values.float())
+    colmax.copy_(X.max(0).values.float())
+    return scratch
+
+
+def augment(x, ref, scale_dev, out, ref_q=None):
+    CALLS.append("augment")
+    c = float(scale_dev[0]) * LOG2E
+    d = x.shape[1]
+    out.zero_()
+    out[:, :d] = x
+    if ref is None:
+        out[:, d] = 1.0
+    else:
+        e = (-ref.double() / c).to(torch.bfloat16)
+        out[:, d] = e
+        if ref_q is not None:
+            ref_q.copy_((-c * e.double()).float())
 
 
 def bwd_weights(inv_rowsum, inv_colsum, n, row_offset, mode, use_gsum, part, world, rank, gvec, scale_dev, wr, wc, dg,

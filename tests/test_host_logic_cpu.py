@@ -99,6 +99,53 @@ def test_odd_feature_dim_is_padded(fake):
     assert A.grad.shape == (20, 13) and cosine(A.grad.float().numpy(), ref.dA) > 0.9999
 
 
+def _wild_inputs(n=96, d=32, seed=3):
+    """Row maxima thousands of bits apart: far outside the single-reference window."""
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(n, d, generator=g)
+    b = torch.randn(n, d, generator=g)
+    a[: n // 2] *= 40.0
+    b[: n // 3] *= 25.0
+    return a.to(torch.bfloat16), b.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("mode", ["always", "auto"])
+def test_two_reference_path_handles_arbitrary_inputs(fake, mode):
+    a, b = _wild_inputs()
+    ref = oc.clip_loss_closed_form(a.double().numpy(), b.double().numpy(), 1.0)
+    # the default path must refuse these inputs ...
+    m0 = fake.ClipLoss(loss_dtype=torch.float32)
+    m0(a, b)
+    with pytest.raises(FloatingPointError):
+        m0.check_last_call()
+    # ... the two-reference path computes them
+    A = a.clone().requires_grad_(True)
+    B = b.clone().requires_grad_(True)
+    ls = torch.tensor(1.0, requires_grad=True)
+    m = fake.ClipLoss(loss_dtype=torch.float32, robust=mode, panel_bytes=128 * 128 * 2)
+    loss = m(A, B, ls)
+    loss.backward()
+    m.check_last_call()
+    assert rel_err(loss.item(), ref.loss) < 1e-5
+    assert cosine(A.grad.float().numpy(), ref.dA) > 0.9999
+    assert cosine(B.grad.float().numpy(), ref.dB) > 0.9999
+    assert abs(ls.grad.item() - ref.dscale) < 2e-2 * abs(ref.dscale) + 1e-6
+
+
+def test_two_reference_path_equals_default_inside_the_window(fake):
+    g = load_golden("clip_single_n100_d72_scale.npz")
+    outs = []
+    for mode in ("off", "always", "auto"):
+        A = bf16_from_bits(g["A_bf16"]).requires_grad_(True)
+        B = bf16_from_bits(g["B_bf16"]).requires_grad_(True)
+        loss = fake.ClipLoss(loss_dtype=torch.float32, robust=mode)(A, B, float(g["scale"]))
+        loss.backward()
+        outs.append((loss.item(), A.grad.float().numpy(), B.grad.float().numpy()))
+        assert rel_err(loss.item(), g["loss_f64"]) < 1e-5
+    assert cosine(outs[0][1], outs[1][1]) > 0.99999 and cosine(outs[0][2], outs[1][2]) > 0.99999
+    assert outs[0][0] == outs[2][0]              # "auto" stays on the default path here
+
+
 # ----------------------------------------------------------------------------------------------
 # world_size = 2, gloo
 # ----------------------------------------------------------------------------------------------
@@ -120,13 +167,18 @@ def _worker(rank, world, port, results):
                 A = a.clone().requires_grad_(True)
                 B = b.clone().requires_grad_(True)
                 ls = torch.tensor(float(g["scale"]), requires_grad=scale_grad)
-                m = clip_loss.ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank,
-                                       world_size=world, loss_dtype=torch.float32, panel_bytes=128 * 64 * 2)
-                loss = m(A, B, ls)
-                (loss * gout).backward()
-                tag = f"ll{int(ll)}_gwg{int(gwg)}_sg{int(scale_grad)}"
-                rec[tag] = dict(loss=loss.item(), dA=A.grad.float().numpy(), dB=B.grad.float().numpy(),
-                                ds=(ls.grad.item() if scale_grad else None))
+                for robust in ("off", "always"):
+                    A = a.clone().requires_grad_(True)
+                    B = b.clone().requires_grad_(True)
+                    ls = torch.tensor(float(g["scale"]), requires_grad=scale_grad)
+                    m = clip_loss.ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank,
+                                           world_size=world, loss_dtype=torch.float32, panel_bytes=128 * 64 * 2,
+                                           robust=robust)
+                    loss = m(A, B, ls)
+                    (loss * gout).backward()
+                    tag = f"ll{int(ll)}_gwg{int(gwg)}_sg{int(scale_grad)}" + ("_rob" if robust == "always" else "")
+                    rec[tag] = dict(loss=loss.item(), dA=A.grad.float().numpy(), dB=B.grad.float().numpy(),
+                                    ds=(ls.grad.item() if scale_grad else None))
     # gather_features keeps the reference contract
     am, asq = clip_loss.gather_features(a.float().requires_grad_(True), b.float(), False, True, rank, world)
     rec["gather_shape"] = tuple(am.shape)
@@ -147,8 +199,8 @@ def test_two_rank_gloo_conventions_vs_reference_golden():
         for ll in (0, 1):
             for gwg in (0, 1):
                 ref = f"ll{ll}_gwg{gwg}"
-                for sg in (0, 1):
-                    got = rec[f"{ref}_sg{sg}"]
+                for sg, rob in ((0, ""), (1, ""), (0, "_rob"), (1, "_rob")):
+                    got = rec[f"{ref}_sg{sg}{rob}"]
                     assert rel_err(got["loss"], g[f"r{r}_loss_{ref}"]) < 1e-5, (r, ref)
                     # bf16 gradients: direction AND magnitude (the W-factor conventions of SURVEY.md 8a)
                     for k in ("dA", "dB"):

@@ -133,6 +133,14 @@ int oneprot_clip_loss_finalize_ex(const float* rowsum_all, const float* colsum_a
                                   float* inv_rowsum, float* inv_colsum, int* flag, void* scratch, const float* row_ref,
                                   const float* col_ref, void* stream);
 
+/* ---- retrieval metric (src/models/components/retrieval_metric.py:76-102) ----
+ * rank_s2m[i] = #{ j != i : <s_i, m_j> > <s_i, m_i> }  (position of the label in the descending
+ * argsort of logits_per_sequence row i when there are no ties), rank_m2s[j] likewise over the
+ * columns - from the logits tiles of the same tensor-core mainloop, never materialising S M^T.
+ * label_dot[i] = <s_i, m_i> as written by oneprot_clip_rowstats (diag).  S, M: N x d bf16. */
+int oneprot_retrieval_ranks(const void* S, const void* M, int N, int d, const float* label_dot, float* rank_s2m,
+                            float* rank_m2s, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- backward ----------------------------------------------------------------------------- */
 
 /* Per-row / per-column / diagonal coefficients of dL/dZ for the panel of this rank:

@@ -60,6 +60,7 @@ SIGNATURES = {
     "oneprot_clip_loss_finalize_ex": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _ip, _vp, _fp, _fp, _vp]),
     "oneprot_clip_rowcol_max": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
     "oneprot_augment_bf16": (_i, [_vp, _i, _i, _fp, _fp, _vp, _fp, _vp]),
+    "oneprot_retrieval_ranks": (_i, [_vp, _vp, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
     "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _vp]),
     "oneprot_clip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _vp]),

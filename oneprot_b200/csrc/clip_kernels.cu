@@ -272,7 +272,7 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
   }
 }
 
-enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3 };   // RCMAX: per-row and per-column maxima
+enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4 };   // RCMAX: row/col maxima; RANK: retrieval ranks
 
 template <int EPI>
 struct SCfg {
@@ -393,12 +393,13 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int r = q * 32 + lane; // row inside the tile
     float c, negG;
     if (EPI == EPI_MAX || EPI == EPI_RCMAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
+    else if (EPI == EPI_RANK) { c = 1.f; negG = 0.f; }
     else load_c_and_G(p, c, negG);
     int acc = 0;
     uint32_t acc_phase = 0;
     float xmax = 0.f;               // EPI_MAX: running max(0, x) of this thread
 
-    float colacc[(EPI == EPI_FWD || EPI == EPI_RCMAX) ? 128 : 1];
+    float colacc[(EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) ? 128 : 1];
     // DZ: bf16 staging of 64 columns of this warp group's half tile = one SWIZZLE_128B box {64 cols, 128 rows}
     const uint32_t colvec_s = smem_u32(&s.tail->colvec[0]);
     const uint32_t stage_s = smem_u32(s.staging) + h * 16384;
@@ -407,10 +408,11 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
       const int j0 = jb * BN + h * 128;   // first column this thread sees
-      if (EPI == EPI_FWD || EPI == EPI_RCMAX) {
+      if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) {
 #pragma unroll
-        for (int k = 0; k < 128; ++k) colacc[k] = (EPI == EPI_FWD) ? 0.f : -INFINITY;
-      } else if (EPI == EPI_DZ) {
+        for (int k = 0; k < 128; ++k) colacc[k] = (EPI == EPI_RCMAX) ? -INFINITY : 0.f;
+      }
+      if (EPI == EPI_DZ || EPI == EPI_RANK) {
         // stage the per-column weights of this item's 256 columns
         named_bar_sync(1, EPI_THREADS);
         const int t = threadIdx.x - EPI_WARP0 * 32;
@@ -463,6 +465,26 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int k = 0; k < 32; ++k) {
               const bool ok = rowok && (j0 + cc * 32 + k < p.N);
               xmax = fmaxf(xmax, ok ? v[k] * c : 0.f);
+            }
+            continue;
+          }
+          if (EPI == EPI_RANK) {
+            // retrieval ranks: how many logits of this row (column) beat the label logit d_i (d_j).
+            // wr = label dot of the row, colvec = label dots of the columns (raw dot products).
+            if (cc == 0) rsum = 0.f;
+            const float d_i = rowok ? __ldg(p.wr + i) : INFINITY;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 w4 = ld_shared_f4(colvec_s + (h * 128 + cc * 32 + k4 * 4) * 4);
+              const float dj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int k = k4 * 4 + u;
+                const int col = j0 + cc * 32 + k;
+                const bool ok = rowok && col < p.N && (p.grow0 + i != col);   // the label itself never counts
+                rsum += (ok && v[k] > d_i) ? 1.f : 0.f;
+                colacc[cc * 32 + k] += (ok && v[k] > dj[u]) ? 1.f : 0.f;
+              }
             }
             continue;
           }
@@ -538,19 +560,19 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
           }
         }
-        if (EPI == EPI_FWD || EPI == EPI_RCMAX) {
+        if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) {
           p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (EPI == EPI_FWD || EPI == EPI_RCMAX) {
-        // flush column sums (maxima) of this item: reduce over the 32 rows of the warp, one slot per (chunk, quadrant)
+      if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) {
+        // flush column sums (maxima, counts) of this item: reduce over the 32 rows of the warp, one slot per (chunk, quadrant)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           float v[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) v[k] = colacc[cc * 32 + k];
-          if (EPI == EPI_FWD) warp_transpose_sum32(v); else warp_transpose_max32(v);
+          if (EPI == EPI_RCMAX) warp_transpose_max32(v); else warp_transpose_sum32(v);
           p.colpart[static_cast<size_t>(ch * 4 + q) * p.ldc + j0 + cc * 32 + lane] = v[0];  // ldc covers nJ*256
         }
       }
@@ -1682,6 +1704,34 @@ int oneprot_clip_rowcol_max(const void* A, const void* B_all, int n, int N, int 
   op::clip_s_kernel<op::EPI_RCMAX><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   op::reduce_slots_max_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowmax);
   op::reduce_slots_max_kernel<<<cdiv(N, 32), 256, 0, st>>>(p.colpart, 4 * p.nChunks, p.ldc, N, colmax);
+  g_launches += 3;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_retrieval_ranks(const void* S, const void* M, int N, int d, const float* label_dot, float* rank_s2m,
+                            float* rank_m2s, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!S || !M || !label_dot || !rank_s2m || !rank_m2s || !scratch) return fail(ONEPROT_ERR_ARG, "retrieval_ranks: null pointer");
+  if (N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "retrieval_ranks: need N > 0 and d a positive multiple of 8");
+  if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(N, N)) return fail(ONEPROT_ERR_ARG, "retrieval_ranks: scratch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  op::SParams p{};
+  s_schedule(N, N, 2, p);
+  p.rows = N; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = 0;
+  p.wr = label_dot; p.wc = label_dot;
+  p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
+  p.rowpart = static_cast<float*>(scratch);
+  p.colpart = p.rowpart + 2 * static_cast<size_t>(p.nJ) * p.ldr;
+  CUtensorMap mapA, mapB;
+  int rc;
+  if ((rc = make_map(&mapA, S, d, N, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, M, d, N, d, op::BN))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_RANK>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_RANK>, smem))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_RANK><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+  op::reduce_slots_kernel<<<cdiv(N, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, N, rank_s2m);
+  op::reduce_slots_kernel<<<cdiv(N, 32), 256, 0, st>>>(p.colpart, 4 * p.nChunks, p.ldc, N, rank_m2s);
   g_launches += 3;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

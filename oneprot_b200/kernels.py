@@ -330,3 +330,16 @@ def gemm_bf16_push(A, B, M: int, Nc: int, K: int, owner_dst_addrs, my_rank: int,
 def sum_slots_bf16(slots, W: int, count: int, out):
     _need_cuda(slots, out)
     check(_lib.load().oneprot_sum_slots_bf16(ptr(slots), W, count, ptr(out), _stream()), "oneprot_sum_slots_bf16")
+
+
+def retrieval_ranks(S, M, label_dot, rank_s2m, rank_m2s, scratch=None):
+    """rank_s2m[i] = #{j != i: <s_i, m_j> > label_dot[i]}, rank_m2s[j] = #{i != j: <s_i, m_j> > label_dot[j]}."""
+    _need_cuda(S, M, label_dot, rank_s2m, rank_m2s)
+    _need(S, torch.bfloat16, "S"); _need(M, torch.bfloat16, "M")
+    N, d = S.shape
+    need = fwd_scratch_bytes(N, N)
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=S.device)
+    check(_lib.load().oneprot_retrieval_ranks(ptr(S), ptr(M), N, d, ptr(label_dot), ptr(rank_s2m), ptr(rank_m2s),
+                                              ptr(scratch), scratch.numel() * scratch.element_size(), _stream()),
+          "oneprot_retrieval_ranks")

@@ -151,6 +151,23 @@ def logit_scaling_closed_form(x: np.ndarray, log_logit_scale: float, max_logit_s
     return s * np.asarray(x, dtype=np.float64), s
 
 
+def retrieval_metric_closed_form(sequence_outputs: np.ndarray, modality_outputs: np.ndarray, ks=(1, 10, 100)) -> dict:
+    """``RetrievalMetric.compute`` (src/models/components/retrieval_metric.py:76-102) restated with
+    numpy: similarity S M^T, descending argsort, position of the label, floor(median)+1 and R@k."""
+    S = np.asarray(sequence_outputs, dtype=np.float64)
+    M = np.asarray(modality_outputs, dtype=np.float64)
+    out = {}
+    logits = {"seq_to_mod": S @ M.T, "mod_to_seq": (S @ M.T).T}
+    gt = np.arange(len(M)).reshape(-1, 1)
+    for name, z in logits.items():
+        ranking = np.argsort(-z, axis=1, kind="stable")
+        preds = np.where(ranking == gt)[1]
+        out[f"{name}_median_rank"] = np.floor(np.median(preds)) + 1
+        for k in ks:
+            out[f"{name}_R@{k}"] = np.mean(preds < k)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # torch CPU port (same library ops as the reference; the timed CPU baseline)
 # ----------------------------------------------------------------------------------------------

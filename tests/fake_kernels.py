@@ -204,3 +204,13 @@ def split_fp32(x, out, side, terms):
     d = x.shape[1]
     for t in range(terms):
         out[:, t * d:(t + 1) * d] = (R if side else L)[t]
+
+
+def retrieval_ranks(S, M, label_dot, rank_s2m, rank_m2s, scratch=None):
+    CALLS.append("retrieval_ranks")
+    Z = S.double() @ M.double().T
+    N = Z.shape[0]
+    off = ~torch.eye(N, dtype=torch.bool)
+    d = label_dot.double()
+    rank_s2m.copy_(((Z > d[:, None]) & off).sum(1).float())
+    rank_m2s.copy_(((Z > d[None, :]) & off).sum(0).float())

@@ -215,3 +215,22 @@ def test_prefetcher_rejects_cpu_device():
     from oneprot_b200.prefetch import PinnedPairPrefetcher
     with pytest.raises(ValueError):
         PinnedPairPrefetcher("cpu")
+
+
+def test_retrieval_metric_matches_reference_restatement(monkeypatch):
+    from oneprot_b200 import clip_loss, retrieval
+    monkeypatch.setattr(clip_loss, "_KERNELS", fake_kernels)
+    monkeypatch.setattr(retrieval, "_KERNELS", fake_kernels)
+    g = torch.Generator().manual_seed(12)
+    S = torch.nn.functional.normalize(torch.randn(300, 48, generator=g), dim=-1)
+    M = torch.nn.functional.normalize(S + 0.8 * torch.randn(300, 48, generator=g), dim=-1)
+    m = retrieval.RetrievalMetric(k=[1, 10, 100])
+    for lo in range(0, 300, 64):                      # several update() calls, like validation batches
+        m.update(S[lo:lo + 64], M[lo:lo + 64])
+    got = m.compute()
+    want = oc.retrieval_metric_closed_form(S.double().numpy(), M.double().numpy())
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(float(got[k]) - float(want[k])) < 1e-9, k
+    m.reset()
+    assert len(m.preds) == 0 and len(m.target) == 0

@@ -274,3 +274,22 @@ def test_retrieval_metric_rank_count_kernel():
             # near-ties resolve differently in bf16 products: allow one rank of slack in the median, 1 % in R@k
             tol = 1.0 if "median" in k else 0.01
             assert abs(float(got[k]) - float(want[k])) <= tol, (k, got[k], want[k])
+
+
+def test_graph_mode_replays_match_eager():
+    """ClipLoss(graph=True): captured forward / backward graphs give the eager results on new data."""
+    outs = {}
+    for graph in (False, True):
+        m = _loss_mod(loss_dtype=torch.float32, graph=graph)
+        res = []
+        for seed in (31, 32, 33):
+            a, b = oc.synthetic_pair(1000, 256, seed=seed)
+            A = a.cuda().requires_grad_(True)
+            B = b.cuda().requires_grad_(True)
+            loss = m(A, B)
+            loss.backward()
+            res.append((loss.item(), A.grad.float().cpu().numpy(), B.grad.float().cpu().numpy()))
+        outs[graph] = res
+    for (l0, a0, b0), (l1, a1, b1) in zip(outs[False], outs[True]):
+        assert l0 == l1
+        assert np.array_equal(a0, a1) and np.array_equal(b0, b1)

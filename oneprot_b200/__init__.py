@@ -14,13 +14,10 @@ def __getattr__(name):
     if name in ("Normalize", "LearnableLogitScaling", "NormalizeAndScale"):
         from . import epilogue
         return getattr(epilogue, name)
-<<<<<<< HEAD
     if name == "PinnedPairPrefetcher":
         from . import prefetch
         return prefetch.PinnedPairPrefetcher
-=======
     if name in ("RetrievalMetric", "retrieval_ranks"):
         from . import retrieval
         return getattr(retrieval, name)
->>>>>>> 8ea768c (WIP (unvalidated on hardware): RetrievalMetric as a rank-count epilogue of the logits mainloop + oracle restatement + tests)
     raise AttributeError(name)

@@ -304,7 +304,7 @@ class _ClipLossFunction(torch.autograd.Function):
         K.loss_finalize(rowsum_all, colsum, diag_all, n, off, mode, scale_dev, stats, loss32, inv_rs, inv_cs, flag)
 
         ctx.dz_ops = None
-        robust = cfg["robust"]
+        robust = cfg.get("robust", "off")
         if robust == "always" or (robust == "auto" and int(flag.item()) != 0):     # "auto" pays one host sync
             # Two-reference path: per-row and per-column references, one pass per softmax direction
             # on operands augmented with the reference as an extra K column.

@@ -33,7 +33,7 @@ def enabled(cfg) -> bool:
 
 
 def eligible(cfg, ops, comm, scale_requires_grad: bool) -> bool:
-    if ops.split or ops.pad or scale_requires_grad:
+    if ops.split or ops.pad or scale_requires_grad or cfg.get("robust", "off") != "off":
         return False
     W = cfg["world_size"]
     if W == 1:

@@ -191,41 +191,6 @@ def test_hazard_flag_when_row_maxima_are_hundreds_of_bits_apart():
         m.check_last_call()
 
 
-@pytest.mark.parametrize("mode", ["always", "auto"])
-def test_two_reference_path_on_wild_inputs(mode):
-    """Row maxima thousands of bits apart (outside the single-reference window): robust modes must
-    still match the float64 oracle."""
-    g = torch.Generator().manual_seed(3)
-    a = torch.randn(300, 128, generator=g)
-    b = torch.randn(300, 128, generator=g)
-    a[:150] *= 40.0
-    b[:100] *= 25.0
-    a, b = a.to(torch.bfloat16), b.to(torch.bfloat16)
-    ref = oc.clip_loss_closed_form(a.double().numpy(), b.double().numpy(), 1.0)
-    A = a.cuda().requires_grad_(True)
-    B = b.cuda().requires_grad_(True)
-    m = _loss_mod(loss_dtype=torch.float32, robust=mode)
-    loss = m(A, B, 1.0)
-    loss.backward()
-    m.check_last_call()
-    assert rel_err(loss.item(), ref.loss) < BF16_LOSS_RTOL
-    assert cosine(A.grad.float().cpu().numpy(), ref.dA) >= GRAD_COS
-    assert cosine(B.grad.float().cpu().numpy(), ref.dB) >= GRAD_COS
-
-
-def test_two_reference_path_matches_default_on_normalised_inputs():
-    a, b = oc.synthetic_pair(1000, 512, seed=21)
-    outs = []
-    for mode in ("off", "always"):
-        A = a.cuda().requires_grad_(True)
-        B = b.cuda().requires_grad_(True)
-        loss = _loss_mod(loss_dtype=torch.float32, robust=mode)(A, B)
-        loss.backward()
-        outs.append((loss.item(), A.grad.float().cpu().numpy(), B.grad.float().cpu().numpy()))
-    assert rel_err(outs[1][0], outs[0][0]) < 1e-5
-    assert cosine(outs[0][1], outs[1][1]) > 0.9999 and cosine(outs[0][2], outs[1][2]) > 0.9999
-
-
 def test_odd_feature_dim_and_fp16_inputs():
     g = torch.Generator().manual_seed(4)
     a = torch.nn.functional.normalize(torch.randn(70, 13, generator=g), dim=-1)
@@ -255,41 +220,3 @@ def test_epilogue_modules_match_golden():
     assert np.allclose(ys.detach().cpu().numpy(), g["ys_f32"], rtol=1e-5)
     big = LearnableLogitScaling(logit_scale_init=250.0, learnable=False).cuda()
     assert np.allclose(big(y.detach()).cpu().numpy(), g["yb_f32"], rtol=1e-5)
-
-
-def test_retrieval_metric_rank_count_kernel():
-    """RetrievalMetric through the rank-count epilogue vs the numpy restatement of the reference."""
-    from oneprot_b200 import RetrievalMetric
-    g = torch.Generator().manual_seed(12)
-    for n, d, dt in ((1000, 1024, torch.float32), (257, 64, torch.bfloat16)):
-        S = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
-        M = torch.nn.functional.normalize(S + 1.5 * torch.randn(n, d, generator=g), dim=-1)
-        S, M = S.to(dt), M.to(dt)
-        m = RetrievalMetric()
-        for lo in range(0, n, 128):
-            m.update(S[lo:lo + 128].cuda(), M[lo:lo + 128].cuda())
-        got = m.compute()
-        want = oc.retrieval_metric_closed_form(S.double().numpy(), M.double().numpy())
-        for k in want:
-            # near-ties resolve differently in bf16 products: allow one rank of slack in the median, 1 % in R@k
-            tol = 1.0 if "median" in k else 0.01
-            assert abs(float(got[k]) - float(want[k])) <= tol, (k, got[k], want[k])
-
-
-def test_graph_mode_replays_match_eager():
-    """ClipLoss(graph=True): captured forward / backward graphs give the eager results on new data."""
-    outs = {}
-    for graph in (False, True):
-        m = _loss_mod(loss_dtype=torch.float32, graph=graph)
-        res = []
-        for seed in (31, 32, 33):
-            a, b = oc.synthetic_pair(1000, 256, seed=seed)
-            A = a.cuda().requires_grad_(True)
-            B = b.cuda().requires_grad_(True)
-            loss = m(A, B)
-            loss.backward()
-            res.append((loss.item(), A.grad.float().cpu().numpy(), B.grad.float().cpu().numpy()))
-        outs[graph] = res
-    for (l0, a0, b0), (l1, a1, b1) in zip(outs[False], outs[True]):
-        assert l0 == l1
-        assert np.array_equal(a0, a1) and np.array_equal(b0, b1)

@@ -1,0 +1,39 @@
+"""GPU: RetrievalMetric as a rank-count epilogue of the logits mainloop (oneprot_b200/retrieval.py) against the
+numpy restatement of the reference metric (retrieval_metric.py:76-102).  Not yet run on hardware."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as oc
+from tests.helpers import cosine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+BF16_LOSS_RTOL = 1e-3
+GRAD_COS = 0.9999
+
+
+def _loss_mod(**kw):
+    from oneprot_b200 import ClipLoss
+    return ClipLoss(**kw)
+
+
+def test_retrieval_metric_rank_count_kernel():
+    """RetrievalMetric through the rank-count epilogue vs the numpy restatement of the reference."""
+    from oneprot_b200 import RetrievalMetric
+    g = torch.Generator().manual_seed(12)
+    for n, d, dt in ((1000, 1024, torch.float32), (257, 64, torch.bfloat16)):
+        S = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
+        M = torch.nn.functional.normalize(S + 1.5 * torch.randn(n, d, generator=g), dim=-1)
+        S, M = S.to(dt), M.to(dt)
+        m = RetrievalMetric()
+        for lo in range(0, n, 128):
+            m.update(S[lo:lo + 128].cuda(), M[lo:lo + 128].cuda())
+        got = m.compute()
+        want = oc.retrieval_metric_closed_form(S.double().numpy(), M.double().numpy())
+        for k in want:
+            # near-ties resolve differently in bf16 products: allow one rank of slack in the median, 1 % in R@k
+            tol = 1.0 if "median" in k else 0.01
+            assert abs(float(got[k]) - float(want[k])) <= tol, (k, got[k], want[k])

@@ -247,6 +247,32 @@ int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* st
  * concatenated K reproduces the fp32 dot product. */
 int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int terms, void* stream);
 
+/* ---- projection heads in front of the path (base_encoder.py:107-194) --------
+ * HBM-bound row kernels (oneprot_b200/csrc/head_kernels.cu); x / y / gradients are bf16, or fp32 when
+ * is_fp32, and gamma / beta have the dtype of x.  The Linear layers run on oneprot_gemm_bf16_ex. */
+
+/* torch.nn.LayerNorm over the last dim (base_encoder.py:148,154,157): y = (x - mean) * rstd * gamma + beta
+ * with the biased variance and eps inside the root; mean / rstd (fp32, one per row) are saved for
+ * the backward.  d: multiple of 8, at most 2048. */
+int oneprot_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int d,
+                          int is_fp32, float eps, void* stream);
+/* gx = rstd * (g - mean(g) - xhat * mean(g * xhat)) with g = gy * gamma (gx may be NULL);
+ * dgamma = sum_rows gy * xhat, dbeta = sum_rows gy (fp32, both or neither; summed over
+ * per-row-chunk partials in `scratch` in a fixed order). */
+size_t oneprot_layernorm_bwd_scratch_bytes(int rows, int d);
+int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, const float* mean, const float* rstd, void* gx,
+                          float* dgamma, float* dbeta, void* scratch, size_t scratch_bytes, int rows, int d, int is_fp32,
+                          void* stream);
+/* exact (erf) GELU of base_encoder.py:156: gy == NULL: out = gelu(x); else out = gy * gelu'(x).  count % 8 == 0. */
+int oneprot_gelu(const void* x, const void* gy, void* out, size_t count, int is_fp32, void* stream);
+/* MeanPooling.forward (base_encoder.py:107-118): y[b] = sum_l mask[b,l] x[b,l,:] / sum_l mask[b,l]
+ * for x of shape B x L x D; mask fp32 B x L or NULL (plain mean); inv_count[b] = 1 / sum_l mask[b,l]. */
+int oneprot_meanpool_fwd(const void* x, const float* mask, void* y, float* inv_count, int B, int L, int D, int is_fp32,
+                         void* stream);
+/* gx[b,l,:] = mask[b,l] * inv_count[b] * gy[b,:] */
+int oneprot_meanpool_bwd(const void* gy, const float* mask, const float* inv_count, void* gx, int B, int L, int D, int is_fp32,
+                         void* stream);
+
 /* ---- host-side step sequencer (oneprot_b200/csrc/clip_sequence.cu) -------------------------------
  * One call enqueues a whole PHASE of ClipLoss.forward / its autograd backward (loss.py:103-114 and
  * the implicit backward): the memsets, the kernels above and the event records /

@@ -20,4 +20,7 @@ def __getattr__(name):
     if name in ("RetrievalMetric", "retrieval_ranks"):
         from . import retrieval
         return getattr(retrieval, name)
+    if name in ("BaseEncoder", "LayerNorm", "Linear", "GELU", "MeanPooling", "CLSTokenPooling"):
+        from . import heads
+        return getattr(heads, name)
     raise AttributeError(name)

@@ -78,6 +78,13 @@ SIGNATURES = {
     "oneprot_mc_allreduce_f32": (_i, [_fp, _fp, _i, _i, _vp]),
     "oneprot_mc_reduce_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "oneprot_split_fp32": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
+    # projection-head row kernels (csrc/head_kernels.cu)
+    "oneprot_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _f, _vp]),
+    "oneprot_layernorm_bwd_scratch_bytes": (_sz, [_i, _i]),
+    "oneprot_layernorm_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _sz, _i, _i, _i, _vp]),
+    "oneprot_gelu": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "oneprot_meanpool_fwd": (_i, [_vp, _fp, _vp, _fp, _i, _i, _i, _i, _vp]),
+    "oneprot_meanpool_bwd": (_i, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _vp]),
     # host-side step sequencer + launch trace (csrc/clip_sequence.cu)
     "oneprot_seq_fwd_ws_bytes": (_sz, [_i, _i]),
     "oneprot_seq_fwd_begin": (_i, [C.POINTER(FwdSeq)]),

@@ -1,0 +1,428 @@
+// HBM-bound row kernels of the projection heads in front of the ClipLoss path (SURVEY.md section 8f,
+// reference src/models/components/base_encoder.py:107-194): masked mean pooling, LayerNorm and GELU,
+// forward and backward.  The Linear layers between them run on the tcgen05 GEMM of clip_kernels.cu
+// (oneprot_gemm_bf16_ex); the L2-normalise / logit-scale epilogue after them is there as well.
+//
+// All kernels: 16-byte vector loads (8 bf16 or 2 x 4 fp32 per lane), fp32 arithmetic, warp-shuffle
+// reductions, one warp per row where a row reduction is needed; column reductions (d gamma, d beta)
+// go through per-chunk partial slots that are summed in a fixed order (deterministic).
+#include "host_trace.h"
+#include "../../include/oneprot_clip.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+
+namespace opint {
+int fail(int code, const std::string& msg);
+void count_launch(int n);
+}  // namespace opint
+
+namespace oph {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <bool FP32>
+__device__ __forceinline__ void load8(const void* base, size_t idx, float (&f)[8]) {
+  if (FP32) {
+    const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + idx);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+
+template <bool FP32>
+__device__ __forceinline__ void store8(void* base, size_t idx, const float (&f)[8]) {
+  if (FP32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + idx) =
+        make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+}
+
+constexpr int LN_MAXC = 8;   // 8 chunks x 32 lanes x 8 elements = rows of up to 2048 elements held in registers
+
+// ---- LayerNorm forward: y = (x - mean) * rstd * gamma + beta, one warp per row, one read of x ----
+template <bool FP32>
+__global__ void layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma, const void* __restrict__ beta,
+                                     void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows, int d,
+                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    float v[LN_MAXC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+        load8<FP32>(x, base + k, v[c]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[c][u];
+      }
+    }
+    const float mu = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float t = v[c][u] - mu; q = fmaf(t, t, q); }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_d + eps);     // biased variance, eps inside the root (torch.nn.LayerNorm)
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+        float g[8], b[8], o[8];
+        load8<FP32>(gamma, k, g);
+        load8<FP32>(beta, k, b);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = fmaf((v[c][u] - mu) * rs, g[u], b[u]);
+        store8<FP32>(y, base + k, o);
+      }
+    }
+  }
+}
+
+// ---- LayerNorm backward, row part: gx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = gy * gamma ----
+template <bool FP32>
+__global__ void layernorm_bwd_rows_kernel(const void* __restrict__ x, const void* __restrict__ gy, const void* __restrict__ gamma,
+                                          const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ gx,
+                                          int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAXC][8], g[LN_MAXC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+        float gm[8];
+        load8<FP32>(x, base + k, xh[c]);
+        load8<FP32>(gy, base + k, g[c]);
+        load8<FP32>(gamma, k, gm);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          xh[c][u] = (xh[c][u] - mu) * rs;
+          g[c][u] *= gm[u];
+          s1 += g[c][u];
+          s2 = fmaf(g[c][u], xh[c][u], s2);
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = rs * (g[c][u] - c1 - xh[c][u] * c2);
+        store8<FP32>(gx, base + k, o);
+      }
+    }
+  }
+}
+
+// ---- LayerNorm backward, column part: partial d gamma = sum_rows gy * xhat, d beta = sum_rows gy.
+// grid (ceil(d / 256), row chunks); block = 8 warps x (32 lanes x 8 columns); slot = blockIdx.y.
+template <bool FP32>
+__global__ void layernorm_bwd_cols_kernel(const void* __restrict__ x, const void* __restrict__ gy, const float* __restrict__ mean,
+                                          const float* __restrict__ rstd, int rows, int d, int rows_per_chunk,
+                                          float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int ld) {
+  __shared__ float red[2][8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float ag[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ab[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (k < d) {
+    for (int row = r0 + warp; row < r1; row += 8) {
+      const size_t base = static_cast<size_t>(row) * d + k;
+      const float mu = mean[row], rs = rstd[row];
+      float fx[8], fg[8];
+      load8<FP32>(x, base, fx);
+      load8<FP32>(gy, base, fg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        ag[u] = fmaf(fg[u], (fx[u] - mu) * rs, ag[u]);
+        ab[u] += fg[u];
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { red[0][warp][lane * 8 + u] = ag[u]; red[1][warp][lane * 8 + u] = ab[u]; }
+  __syncthreads();
+  // 256 threads: thread t sums column t of the tile over the 8 warps (fixed order)
+  const int t = threadIdx.x, col = blockIdx.x * 256 + t;
+  if (col < d) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sg += red[0][w][t]; sb += red[1][w][t]; }
+    dgamma_part[static_cast<size_t>(blockIdx.y) * ld + col] = sg;
+    dbeta_part[static_cast<size_t>(blockIdx.y) * ld + col] = sb;
+  }
+}
+
+// out[k] = sum_s part[s * ld + k] in slot order (deterministic); one thread per column
+__global__ void sum_slots_f32_kernel(const float* __restrict__ part, int slots, int ld, int count, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  float acc = 0.f;
+  for (int s = 0; s < slots; ++s) acc += part[static_cast<size_t>(s) * ld + k];
+  out[k] = acc;
+}
+
+// ---- GELU (exact, erf) -------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+  return fmaf(v, pdf, cdf);
+}
+
+template <bool FP32, bool BWD>
+__global__ void gelu_kernel(const void* __restrict__ x, const void* __restrict__ gy, void* __restrict__ out, size_t total8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float f[8], o[8];
+    load8<FP32>(x, i * 8, f);
+    if (BWD) {
+      float g[8];
+      load8<FP32>(gy, i * 8, g);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = g[u] * gelu_grad_f(f[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = gelu_f(f[u]);
+    }
+    store8<FP32>(out, i * 8, o);
+  }
+}
+
+// ---- masked mean pooling over the token axis: y[b] = sum_l mask[b,l] x[b,l] / sum_l mask[b,l] ----
+// grid (B, ceil(D / 256)); 8 warps stride over the tokens, lane = 8 columns; mask == nullptr: plain mean
+template <bool FP32>
+__global__ void meanpool_fwd_kernel(const void* __restrict__ x, const float* __restrict__ mask, void* __restrict__ y,
+                                    float* __restrict__ inv_count, int L, int D) {
+  __shared__ float red[8][256 + 8];
+  __shared__ float cnt_s[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int k = blockIdx.y * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float cnt = 0.f;
+  for (int l = warp; l < L; l += 8) {
+    const float m = mask ? mask[static_cast<size_t>(b) * L + l] : 1.f;
+    cnt += m;
+    if (m != 0.f && k < D) {
+      float f[8];
+      load8<FP32>(x, (static_cast<size_t>(b) * L + l) * D + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(m, f[u], acc[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[warp][lane * 8 + u] = acc[u];
+  if (lane == 0) cnt_s[warp] = cnt;
+  __syncthreads();
+  float total = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) total += cnt_s[w];
+  const float inv = 1.f / total;            // all-masked rows give inf / nan like the reference's 0 / 0
+  if (threadIdx.x == 0 && blockIdx.y == 0) inv_count[b] = inv;
+  if (warp == 0 && k < D) {
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][lane * 8 + u];
+      o[u] = s * inv;
+    }
+    store8<FP32>(y, static_cast<size_t>(b) * D + k, o);
+  }
+}
+
+template <bool FP32>
+__global__ void meanpool_bwd_kernel(const void* __restrict__ gy, const float* __restrict__ mask, const float* __restrict__ inv_count,
+                                    void* __restrict__ gx, int L, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int k = blockIdx.y * 256 + lane * 8;
+  if (k >= D) return;
+  float g[8];
+  load8<FP32>(gy, static_cast<size_t>(b) * D + k, g);
+  const float inv = inv_count[b];
+  for (int l = warp; l < L; l += 8) {
+    const float m = (mask ? mask[static_cast<size_t>(b) * L + l] : 1.f) * inv;
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o[u] = m * g[u];
+    store8<FP32>(gx, (static_cast<size_t>(b) * L + l) * D + k, o);
+  }
+}
+
+}  // namespace oph
+
+namespace {
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+#define HD_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return opint::fail(ONEPROT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+int ln_row_chunks(int rows, int d) {
+  // enough (column tile, row chunk) blocks for ~2 per SM, at least 64 rows per chunk
+  const int tiles = cdiv(d, 256);
+  const int want = std::max(1, 2 * oneprot_num_sms() / tiles);
+  return std::max(1, std::min(cdiv(rows, 64), want));
+}
+}  // namespace
+
+extern "C" {
+
+int oneprot_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int d,
+                          int is_fp32, float eps, void* stream) {
+  if (!x || !gamma || !beta || !y || !mean || !rstd) return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: null pointer");
+  if (rows <= 0 || d <= 0 || d % 8 || d > 256 * oph::LN_MAXC)
+    return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: need d a positive multiple of 8, at most 2048");
+  if (!al16(x) || !al16(gamma) || !al16(beta) || !al16(y)) return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("layernorm_fwd x=%p gamma=%p beta=%p y=%p mean=%p rstd=%p rows=%d d=%d fp32=%d st=%p", x, gamma, beta, y, (void*)mean, (void*)rstd, rows, d, is_fp32, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const int blocks = std::min(cdiv(rows, 8), oneprot_num_sms() * 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) oph::layernorm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  else oph::layernorm_fwd_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+size_t oneprot_layernorm_bwd_scratch_bytes(int rows, int d) {
+  if (rows <= 0 || d <= 0) return 0;
+  const size_t ld = static_cast<size_t>(cdiv(d, 256)) * 256;
+  return 2 * static_cast<size_t>(ln_row_chunks(rows, d)) * ld * sizeof(float);
+}
+
+int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, const float* mean, const float* rstd, void* gx,
+                          float* dgamma, float* dbeta, void* scratch, size_t scratch_bytes, int rows, int d, int is_fp32,
+                          void* stream) {
+  if (!x || !gy || !gamma || !mean || !rstd) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: null pointer");
+  if (rows <= 0 || d <= 0 || d % 8 || d > 256 * oph::LN_MAXC)
+    return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: need d a positive multiple of 8, at most 2048");
+  if ((dgamma != nullptr) != (dbeta != nullptr)) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: dgamma and dbeta go together");
+  if (!gx && !dgamma) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: nothing to compute");
+  if (dgamma && (!scratch || scratch_bytes < oneprot_layernorm_bwd_scratch_bytes(rows, d)))
+    return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: scratch too small");
+  if (!al16(x) || !al16(gy) || !al16(gamma) || (gx && !al16(gx))) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("layernorm_bwd x=%p gy=%p gamma=%p mean=%p rstd=%p gx=%p dgamma=%p dbeta=%p scratch=%p rows=%d d=%d fp32=%d st=%p", x, gy, gamma, (const void*)mean, (const void*)rstd, gx, (void*)dgamma, (void*)dbeta, scratch, rows, d, is_fp32, stream);
+  opint::count_launch((gx ? 1 : 0) + (dgamma ? 3 : 0));
+  if (optrace::dry()) return ONEPROT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gx) {
+    const int blocks = std::min(cdiv(rows, 8), oneprot_num_sms() * 8);
+    if (is_fp32) oph::layernorm_bwd_rows_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+    else oph::layernorm_bwd_rows_kernel<false><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+    HD_CUDA(cudaGetLastError());
+  }
+  if (dgamma) {
+    const int chunks = ln_row_chunks(rows, d);
+    const int rpc = cdiv(rows, chunks);
+    const int ld = cdiv(d, 256) * 256;
+    float* pg = static_cast<float*>(scratch);
+    float* pb = pg + static_cast<size_t>(chunks) * ld;
+    const dim3 grid(cdiv(d, 256), chunks);
+    if (is_fp32) oph::layernorm_bwd_cols_kernel<true><<<grid, 256, 0, st>>>(x, gy, mean, rstd, rows, d, rpc, pg, pb, ld);
+    else oph::layernorm_bwd_cols_kernel<false><<<grid, 256, 0, st>>>(x, gy, mean, rstd, rows, d, rpc, pg, pb, ld);
+    oph::sum_slots_f32_kernel<<<cdiv(d, 256), 256, 0, st>>>(pg, chunks, ld, d, dgamma);
+    oph::sum_slots_f32_kernel<<<cdiv(d, 256), 256, 0, st>>>(pb, chunks, ld, d, dbeta);
+    HD_CUDA(cudaGetLastError());
+  }
+  return ONEPROT_OK;
+}
+
+int oneprot_gelu(const void* x, const void* gy, void* out, size_t count, int is_fp32, void* stream) {
+  if (!x || !out || count == 0 || count % 8) return opint::fail(ONEPROT_ERR_ARG, "gelu: need a positive element count that is a multiple of 8");
+  if (!al16(x) || !al16(out) || (gy && !al16(gy))) return opint::fail(ONEPROT_ERR_ARG, "gelu: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("gelu x=%p gy=%p out=%p count=%zu fp32=%d st=%p", x, gy, out, count, is_fp32, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const size_t total8 = count / 8;
+  const int blocks = static_cast<int>(std::min<size_t>((total8 + 255) / 256, static_cast<size_t>(oneprot_num_sms()) * 16));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gy) {
+    if (is_fp32) oph::gelu_kernel<true, true><<<blocks, 256, 0, st>>>(x, gy, out, total8);
+    else oph::gelu_kernel<false, true><<<blocks, 256, 0, st>>>(x, gy, out, total8);
+  } else {
+    if (is_fp32) oph::gelu_kernel<true, false><<<blocks, 256, 0, st>>>(x, nullptr, out, total8);
+    else oph::gelu_kernel<false, false><<<blocks, 256, 0, st>>>(x, nullptr, out, total8);
+  }
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_meanpool_fwd(const void* x, const float* mask, void* y, float* inv_count, int B, int L, int D, int is_fp32,
+                         void* stream) {
+  if (!x || !y || !inv_count || B <= 0 || L <= 0 || D <= 0 || D % 8) return opint::fail(ONEPROT_ERR_ARG, "meanpool_fwd: need D a positive multiple of 8");
+  if (!al16(x) || !al16(y)) return opint::fail(ONEPROT_ERR_ARG, "meanpool_fwd: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("meanpool_fwd x=%p mask=%p y=%p inv_count=%p B=%d L=%d D=%d fp32=%d st=%p", x, (const void*)mask, y, (void*)inv_count, B, L, D, is_fp32, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const dim3 grid(B, cdiv(D, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) oph::meanpool_fwd_kernel<true><<<grid, 256, 0, st>>>(x, mask, y, inv_count, L, D);
+  else oph::meanpool_fwd_kernel<false><<<grid, 256, 0, st>>>(x, mask, y, inv_count, L, D);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_meanpool_bwd(const void* gy, const float* mask, const float* inv_count, void* gx, int B, int L, int D, int is_fp32,
+                         void* stream) {
+  if (!gy || !inv_count || !gx || B <= 0 || L <= 0 || D <= 0 || D % 8) return opint::fail(ONEPROT_ERR_ARG, "meanpool_bwd: need D a positive multiple of 8");
+  if (!al16(gy) || !al16(gx)) return opint::fail(ONEPROT_ERR_ARG, "meanpool_bwd: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("meanpool_bwd gy=%p mask=%p inv_count=%p gx=%p B=%d L=%d D=%d fp32=%d st=%p", gy, (const void*)mask, (const void*)inv_count, gx, B, L, D, is_fp32, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const dim3 grid(B, cdiv(D, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) oph::meanpool_bwd_kernel<true><<<grid, 256, 0, st>>>(gy, mask, inv_count, gx, L, D);
+  else oph::meanpool_bwd_kernel<false><<<grid, 256, 0, st>>>(gy, mask, inv_count, gx, L, D);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+}  // extern "C"

@@ -298,6 +298,55 @@ def rowdot(x, y, out):
           "oneprot_rowdot")
 
 
+# ---- projection-head row kernels (pooling, LayerNorm, GELU) ---------------------------------
+def _is32(t):
+    if t.dtype not in (torch.bfloat16, torch.float32) or not t.is_contiguous():
+        raise ValueError(f"expected a contiguous bf16 / fp32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return int(t.dtype == torch.float32)
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps: float):
+    _need_cuda(x, gamma, beta, y, mean, rstd)
+    rows, d = x.shape
+    if gamma.dtype != x.dtype or beta.dtype != x.dtype:
+        raise ValueError("layernorm: gamma / beta must have the dtype of x")
+    check(_lib.load().oneprot_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, d, _is32(x),
+                                            eps, _stream()), "oneprot_layernorm_fwd")
+
+
+def layernorm_bwd(x, gy, gamma, mean, rstd, gx=None, dgamma=None, dbeta=None):
+    _need_cuda(x, gy, gamma, mean, rstd, gx, dgamma, dbeta)
+    rows, d = x.shape
+    scratch, nbytes = None, 0
+    if dgamma is not None:
+        nbytes = int(_lib.load().oneprot_layernorm_bwd_scratch_bytes(rows, d))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    if gy.dtype != x.dtype or not gy.is_contiguous():
+        raise ValueError("layernorm_bwd: gy must be contiguous with the dtype of x")
+    check(_lib.load().oneprot_layernorm_bwd(ptr(x), ptr(gy), ptr(gamma), ptr(mean), ptr(rstd), ptr(gx), ptr(dgamma), ptr(dbeta),
+                                            ptr(scratch), nbytes, rows, d, _is32(x), _stream()), "oneprot_layernorm_bwd")
+
+
+def gelu(x, out, gy=None):
+    """out = gelu(x), or gy * gelu'(x) when gy is given (flat, element count a multiple of 8)."""
+    _need_cuda(x, out, gy)
+    check(_lib.load().oneprot_gelu(ptr(x), ptr(gy), ptr(out), x.numel(), _is32(x), _stream()), "oneprot_gelu")
+
+
+def meanpool_fwd(x, mask, y, inv_count):
+    _need_cuda(x, mask, y, inv_count)
+    B, L, D = x.shape
+    check(_lib.load().oneprot_meanpool_fwd(ptr(x), ptr(mask), ptr(y), ptr(inv_count), B, L, D, _is32(x), _stream()),
+          "oneprot_meanpool_fwd")
+
+
+def meanpool_bwd(gy, mask, inv_count, gx):
+    _need_cuda(gy, mask, inv_count, gx)
+    B, L, D = gx.shape
+    check(_lib.load().oneprot_meanpool_bwd(ptr(gy), ptr(mask), ptr(inv_count), ptr(gx), B, L, D, _is32(gx), _stream()),
+          "oneprot_meanpool_bwd")
+
+
 # ---- NVLS (multimem) exchanges; *_mc arguments are raw multicast addresses (int) -------------
 def mc_store(src, dst_mc_addr: int, nbytes: int):
     _need_cuda(src)

@@ -144,9 +144,54 @@ def epilogue_cases():
     print("wrote epilogue")
 
 
+def head_cases():
+    """BaseEncoder heads of the unmodified reference (base_encoder.py:129-194) in float64 on
+    bf16-valued inputs and parameters: output + gradients w.r.t. the input and every parameter."""
+    sys.path.insert(0, REF)
+    from src.models.components.base_encoder import BaseEncoder
+    cases = [
+        # name, d_model, output_dim, proj_type, pooling, use_logit_scale, learnable, B, L
+        ("mlp_mean_scale", 64, 32, "mlp", "mean", True, True, 6, 9),        # sequence / text style head
+        ("linear_cls", 48, 40, "linear", "cls", False, False, 5, 7),
+        ("linear_identity_scale", 56, 24, "linear", "identity", True, False, 10, 0),   # struct-graph style: 2-D input
+        ("none_mean", 32, 32, None, "mean", False, False, 4, 5),
+    ]
+    for name, dm, do, proj, pool, uls, learn, B, L in cases:
+        g = torch.Generator().manual_seed(len(name) * 101 + dm)
+        enc = BaseEncoder(dm, do, proj_type=proj, use_logit_scale=uls, learnable_logit_scale=learn, pooling_type=pool).double()
+        with torch.no_grad():
+            for k, p in enc.state_dict().items():
+                if p.dim() >= 1:      # bf16-valued parameters away from the trivial LayerNorm init
+                    p.copy_((p + 0.3 * torch.randn(p.shape, generator=g).double()).to(torch.bfloat16).double())
+        x = torch.randn((B, L, dm) if L else (B, dm), generator=g).to(torch.bfloat16)
+        mask = None
+        if L and pool == "mean":
+            lens = torch.randint(1, L + 1, (B,), generator=g)
+            mask = (torch.arange(L)[None, :] < lens[:, None]).long()
+        gy = torch.randn(B, do, generator=g).to(torch.bfloat16)
+        X = x.double().requires_grad_(True)
+        # 'identity' pooling is nn.Identity, which takes no mask: the reference's encoders that use it call
+        # proj / norm themselves (struct_graph_encoder.py:41-42)
+        y = enc(X, mask) if pool != "identity" else enc.norm(enc.proj(X))
+        y.backward(gy.double())
+        rec = {"x_bf16": bf16_bits(x), "x_shape": np.array(x.shape), "gy_bf16": bf16_bits(gy),
+               "mask": np.zeros(0) if mask is None else mask.numpy(), "y_f64": y.detach().numpy(), "gx_f64": X.grad.numpy(),
+               "d_model": np.int64(dm), "output_dim": np.int64(do), "proj_type": np.bytes_(str(proj)),
+               "pooling_type": np.bytes_(pool), "use_logit_scale": np.bool_(uls), "learnable": np.bool_(learn)}
+        named = dict(enc.named_parameters())
+        for k, v in enc.state_dict().items():
+            rec["param:" + k] = v.detach().numpy()
+            if k in named and named[k].grad is not None:
+                rec["grad:" + k] = named[k].grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"head_{name}.npz"), **rec)
+        print("wrote head", name, sorted(k for k in rec if k.startswith("grad:")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    single_process_cases()
-    distributed_cases()
-    epilogue_cases()
+    if "--heads-only" not in sys.argv:
+        single_process_cases()
+        distributed_cases()
+        epilogue_cases()
+    head_cases()

@@ -214,3 +214,84 @@ def retrieval_ranks(S, M, label_dot, rank_s2m, rank_m2s, scratch=None):
     d = label_dot.double()
     rank_s2m.copy_(((Z > d[:, None]) & off).sum(1).float())
     rank_m2s.copy_(((Z > d[None, :]) & off).sum(0).float())
+
+
+# ---- projection-head row kernels + the normalise / scale epilogue (contracts of include/oneprot_clip.h) ----
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps):
+    CALLS.append("layernorm_fwd")
+    xd = x.double()
+    mu = xd.mean(-1, keepdim=True)
+    var = ((xd - mu) ** 2).mean(-1, keepdim=True)
+    rs = 1.0 / torch.sqrt(var + eps)
+    y.copy_((((xd - mu) * rs) * gamma.double() + beta.double()).to(y.dtype))
+    mean.copy_(mu.squeeze(-1).float())
+    rstd.copy_(rs.squeeze(-1).float())
+
+
+def layernorm_bwd(x, gy, gamma, mean, rstd, gx=None, dgamma=None, dbeta=None):
+    CALLS.append("layernorm_bwd")
+    xhat = (x.double() - mean.double()[:, None]) * rstd.double()[:, None]
+    g = gy.double() * gamma.double()
+    if gx is not None:
+        gx.copy_((rstd.double()[:, None] * (g - g.mean(-1, keepdim=True) - xhat * (g * xhat).mean(-1, keepdim=True))).to(gx.dtype))
+    if dgamma is not None:
+        dgamma.copy_((gy.double() * xhat).sum(0).float())
+        dbeta.copy_(gy.double().sum(0).float())
+
+
+def gelu(x, out, gy=None):
+    CALLS.append("gelu")
+    xd = x.double()
+    cdf = 0.5 * (1.0 + torch.erf(xd / math.sqrt(2.0)))
+    if gy is None:
+        out.copy_((xd * cdf).to(out.dtype))
+    else:
+        pdf = torch.exp(-0.5 * xd * xd) / math.sqrt(2.0 * math.pi)
+        out.copy_((gy.double() * (cdf + xd * pdf)).to(out.dtype))
+
+
+def meanpool_fwd(x, mask, y, inv_count):
+    CALLS.append("meanpool_fwd")
+    B, L, D = x.shape
+    m = torch.ones(B, L, dtype=torch.float64) if mask is None else mask.double()
+    cnt = m.sum(1)
+    y.copy_(((x.double() * m[:, :, None]).sum(1) / cnt[:, None]).to(y.dtype))
+    inv_count.copy_((1.0 / cnt).float())
+
+
+def meanpool_bwd(gy, mask, inv_count, gx):
+    CALLS.append("meanpool_bwd")
+    B, L, D = gx.shape
+    m = torch.ones(B, L, dtype=torch.float64) if mask is None else mask.double()
+    gx.copy_((gy.double()[:, None, :] * (m * inv_count.double()[:, None])[:, :, None]).to(gx.dtype))
+
+
+def l2norm_scale_fwd(x, y, inv_norm, scale_dev=None, eps=1e-12):
+    CALLS.append("l2norm_fwd")
+    xd = x.double()
+    inv = 1.0 / torch.clamp(xd.norm(dim=-1), min=eps)
+    s = 1.0 if scale_dev is None else float(scale_dev[0])
+    y.copy_((xd * (inv * s)[:, None]).to(y.dtype))
+    inv_norm.copy_(inv.float())
+
+
+def l2norm_scale_bwd(x, gy, inv_norm, gx, dscale_partial=None, scale_dev=None, eps=1e-12):
+    CALLS.append("l2norm_bwd")
+    inv = inv_norm.double()
+    yhat = x.double() * inv[:, None]
+    dot = (yhat * gy.double()).sum(-1)
+    if dscale_partial is not None:
+        dscale_partial.copy_(dot.float())
+    proj = torch.where(inv >= 1.0 / eps, torch.zeros_like(dot), dot)
+    s = 1.0 if scale_dev is None else float(scale_dev[0])
+    gx.copy_((s * inv[:, None] * (gy.double() - yhat * proj[:, None])).to(gx.dtype))
+
+
+def scale_rows(x, y, scale_dev):
+    CALLS.append("scale_rows")
+    y.copy_((x.double() * float(scale_dev[0])).to(y.dtype))
+
+
+def rowdot(x, y, out):
+    CALLS.append("rowdot_dense")
+    out.copy_((x.double() * y.double()).sum(-1).float())

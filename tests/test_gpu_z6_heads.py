@@ -1,0 +1,141 @@
+"""GPU: projection heads (oneprot_b200/heads.py + csrc/head_kernels.cu) - row kernels against a plain
+PyTorch fp32 reference of the same op, the BaseEncoder head against the reference-generated golden
+fixtures (tests/golden/head_*.npz) and against torch.nn modules at OneProt's sizes
+(d_model 1280 -> 1152 -> 1024, base_encoder.py:151-159).  Not yet run on hardware.
+Tolerances: fp32 modules 2e-4 (bf16 limb products, 2^-16 each; the reference's TF32 is 2^-11),
+bf16 modules 5e-2 on O(1..14) outputs, gradient cosine >= 0.999 (bf16) / 0.99999 (fp32)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from tests.helpers import GOLDEN, cosine
+from tests.test_heads_cpu import _load
+
+pytestmark = pytest.mark.gpu
+CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "head_*.npz")))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,d", [(1000, 1280), (37, 1152), (512, 64), (8, 2048)])
+def test_layernorm_kernels_vs_torch(rows, d, dtype):
+    from oneprot_b200.heads import LayerNorm
+    g = torch.Generator().manual_seed(rows + d)
+    x = (2.0 * torch.randn(rows, d, generator=g) + 0.5).to(dtype)
+    gy = torch.randn(rows, d, generator=g).to(dtype)
+    ours = LayerNorm(d).cuda().to(dtype)
+    ref = nn.LayerNorm(d).cuda().double()
+    with torch.no_grad():
+        w = (1.0 + 0.3 * torch.randn(d, generator=g)).to(dtype)
+        b = (0.2 * torch.randn(d, generator=g)).to(dtype)
+        ours.weight.copy_(w); ours.bias.copy_(b)
+        ref.weight.copy_(w.double()); ref.bias.copy_(b.double())
+    X = x.cuda().requires_grad_(True)
+    Xr = x.cuda().double().requires_grad_(True)
+    y = ours(X); y.backward(gy.cuda())
+    yr = ref(Xr); yr.backward(gy.cuda().double())
+    tol = 1e-5 if dtype == torch.float32 else 3e-2
+    assert torch.allclose(y.double(), yr, rtol=tol, atol=tol)
+    cmin = 0.99999 if dtype == torch.float32 else 0.999
+    assert cosine(X.grad.double().cpu().numpy(), Xr.grad.cpu().numpy()) >= cmin
+    assert cosine(ours.weight.grad.double().cpu().numpy(), ref.weight.grad.cpu().numpy()) >= cmin
+    assert cosine(ours.bias.grad.double().cpu().numpy(), ref.bias.grad.cpu().numpy()) >= cmin
+    assert abs(ours.bias.grad.double().norm().item() / ref.bias.grad.norm().item() - 1) < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gelu_and_meanpool_kernels_vs_torch(dtype):
+    from oneprot_b200.heads import GELU, MeanPooling
+    g = torch.Generator().manual_seed(5)
+    x = (3.0 * torch.randn(300, 1152, generator=g)).to(dtype)
+    gy = torch.randn(300, 1152, generator=g).to(dtype)
+    X = x.cuda().requires_grad_(True)
+    Xr = x.cuda().double().requires_grad_(True)
+    y = GELU()(X); y.backward(gy.cuda())
+    yr = nn.GELU()(Xr); yr.backward(gy.cuda().double())
+    tol = 1e-5 if dtype == torch.float32 else 3e-2
+    assert torch.allclose(y.double(), yr, rtol=tol, atol=tol) and torch.allclose(X.grad.double(), Xr.grad, rtol=tol, atol=tol)
+    # masked mean over ragged lengths (including a length-1 row) and the unmasked mean
+    B, L, D = 9, 77, 1280
+    f = torch.randn(B, L, D, generator=g).to(dtype)
+    lens = torch.tensor([1, 77, 5, 33, 64, 2, 76, 40, 13])
+    mask = (torch.arange(L)[None, :] < lens[:, None]).long()
+    gp = torch.randn(B, D, generator=g).to(dtype)
+    for m in (mask, None):
+        F = f.cuda().requires_grad_(True)
+        Fr = f.cuda().double().requires_grad_(True)
+        p = MeanPooling()(F, None if m is None else m.cuda()); p.backward(gp.cuda())
+        if m is None:
+            pr = Fr.mean(dim=1)
+        else:
+            md = m.cuda().double()
+            pr = (Fr * md.unsqueeze(2)).sum(1) / md.sum(1, keepdim=True)          # base_encoder.py:114-116
+        pr.backward(gp.cuda().double())
+        assert torch.allclose(p.double(), pr, rtol=tol, atol=tol)
+        assert torch.allclose(F.grad.double(), Fr.grad, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_base_encoder_head_vs_reference_golden(name, dtype):
+    from oneprot_b200.heads import BaseEncoder
+    g, cfg, x, gy, mask, params, grads = _load(name)
+    enc = BaseEncoder(cfg["d_model"], cfg["output_dim"], proj_type=cfg["proj_type"], use_logit_scale=cfg["use_logit_scale"],
+                      learnable_logit_scale=cfg["learnable"], pooling_type=cfg["pooling_type"])
+    enc.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in params.items()}, strict=True)
+    enc = enc.cuda().to(dtype)
+    X = x.to(dtype).cuda().requires_grad_(True)
+    m = None if mask is None else torch.from_numpy(mask).cuda()
+    y = enc(X, m) if cfg["pooling_type"] != "identity" else enc.norm(enc.proj(X))
+    y.backward(gy.to(dtype).cuda())
+    tol = 2e-4 if dtype == torch.float32 else 5e-2
+    assert np.allclose(y.detach().double().cpu().numpy(), g["y_f64"], rtol=tol, atol=tol)
+    cmin = 0.99999 if dtype == torch.float32 else 0.999
+    assert cosine(X.grad.double().cpu().numpy(), g["gx_f64"]) >= cmin
+    named = dict(enc.named_parameters())
+    for k, want in grads.items():
+        if np.ndim(want):
+            assert cosine(named[k].grad.double().cpu().numpy(), want) >= cmin, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_sequence_head_at_oneprot_sizes_vs_torch_modules(dtype):
+    """ESM-2 650M head: tokens (B, L, 1280) -> masked mean -> mlp 1280 -> 1152 -> 1024 -> normalise,
+    followed by the fused ClipLoss; torch.nn modules in float64 are the reference of the same ops."""
+    from oneprot_b200 import ClipLoss
+    from oneprot_b200.heads import BaseEncoder
+    B, L, dm, do = 256, 24, 1280, 1024
+    g = torch.Generator().manual_seed(11)
+    tok = torch.randn(B, L, dm, generator=g).to(dtype)
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    mask = (torch.arange(L)[None, :] < lens[:, None]).long()
+    other = torch.nn.functional.normalize(torch.randn(B, do, generator=g), dim=-1).mul(1 / 0.07).to(dtype)
+    enc = BaseEncoder(dm, do, proj_type="mlp", pooling_type="mean").cuda().to(dtype)
+    hid = (dm + do) // 2
+    ref = nn.Sequential(nn.LayerNorm(dm), nn.Linear(dm, hid, bias=False), nn.GELU(), nn.LayerNorm(hid),
+                        nn.Linear(hid, do, bias=False)).cuda().double()
+    with torch.no_grad():
+        for i in (0, 1, 3, 4):
+            for pn, p in ref[i].named_parameters():
+                p.copy_(getattr(enc.proj[i], pn).double())
+    T = tok.cuda().requires_grad_(True)
+    emb = enc(T, mask.cuda())
+    loss = ClipLoss(loss_dtype=torch.float32)(emb, other.cuda())
+    loss.backward()
+    Tr = tok.cuda().double().requires_grad_(True)
+    md = mask.cuda().double()
+    pooled = (Tr * md.unsqueeze(2)).sum(1) / md.sum(1, keepdim=True)
+    er = torch.nn.functional.normalize(ref(pooled), dim=-1)
+    z = er @ other.cuda().double().T
+    lab = torch.arange(B, device="cuda")
+    lr = (torch.nn.functional.cross_entropy(z, lab) + torch.nn.functional.cross_entropy(z.T, lab)) / 2
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < (2e-4 if dtype == torch.float32 else 3e-2) * abs(lr.item())
+    cmin = 0.9999 if dtype == torch.float32 else 0.99
+    assert cosine(T.grad.double().cpu().numpy(), Tr.grad.cpu().numpy()) >= cmin
+    for i in (0, 1, 3, 4):
+        for pn, p in ref[i].named_parameters():
+            assert cosine(getattr(enc.proj[i], pn).grad.double().cpu().numpy(), p.grad.cpu().numpy()) >= cmin, (i, pn)

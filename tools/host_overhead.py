@@ -1,27 +1,51 @@
-"""Host-side enqueue cost of one ClipLoss fwd+bwd (no device sync inside the loop) and the
-GPU-side time at a size where the device work is negligible."""
-import os, sys, time
+"""Host-side enqueue cost of one ClipLoss fwd+bwd (no device sync inside the loop) and the wall time
+per step at sizes where the device work is small, for the three hosts:
+
+    python tools/host_overhead.py [n] [d]
+      python   kernel-by-kernel Python host (default path)
+      seq      host-side step sequencer (ClipLoss(host_sequencer=True), csrc/clip_sequence.cu)
+      graph    CUDA-graph replay (ClipLoss(graph=True), oneprot_b200/graphed.py)
+"""
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-from oneprot_b200 import ClipLoss
-from tools import synthetic as oc
+import torch  # noqa: E402
+
+from oneprot_b200 import ClipLoss  # noqa: E402
+from tools import synthetic as oc  # noqa: E402
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-a, b = oc.synthetic_pair(n, 1024, seed=1)
-A = a.cuda().requires_grad_(True); B = b.cuda().requires_grad_(True)
-m = ClipLoss()
-def step():
-    A.grad = None; B.grad = None
-    m(A, B).backward()
-for _ in range(10): step()
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(200): step()
-t_enq = (time.perf_counter() - t0) / 200
-torch.cuda.synchronize()
-t_tot = (time.perf_counter() - t0) / 200
-print(f"n={n}: host enqueue {t_enq*1e6:.0f} us/step, wall incl. device {t_tot*1e6:.0f} us/step")
-import cProfile, pstats
-pr = cProfile.Profile(); pr.enable()
-for _ in range(100): step()
-pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+d = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+a, b = oc.synthetic_pair(n, d, seed=1)
+A = a.cuda().requires_grad_(True)
+B = b.cuda().requires_grad_(True)
+ref = None
+for name, kw in (("python", {}), ("seq", dict(host_sequencer=True)), ("graph", dict(graph=True))):
+    try:
+        m = ClipLoss(loss_dtype=torch.float32, **kw)
+
+        def step():
+            A.grad = None; B.grad = None
+            loss = m(A, B)
+            loss.backward()
+            return loss
+
+        for _ in range(10):
+            loss = step()
+        torch.cuda.synchronize()
+        val = (loss.item(), A.grad.clone(), B.grad.clone())
+        if ref is None:
+            ref = val
+        same = val[0] == ref[0] and torch.equal(val[1], ref[1]) and torch.equal(val[2], ref[2])
+        t0 = time.perf_counter()
+        for _ in range(300):
+            step()
+        t_enq = (time.perf_counter() - t0) / 300
+        torch.cuda.synchronize()
+        t_tot = (time.perf_counter() - t0) / 300
+        print(f"{name:7s} n={n} d={d}: host enqueue {t_enq * 1e6:7.1f} us/step, wall incl. device {t_tot * 1e6:7.1f} us/step, "
+              f"bit-identical to the python host: {same}", flush=True)
+    except Exception as e:   # keep going: the other hosts are still worth measuring
+        print(f"{name:7s} FAILED: {e!r}", flush=True)

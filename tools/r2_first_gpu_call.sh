@@ -1,0 +1,21 @@
+#!/bin/bash
+# First gpurun call of the next round: everything that was built after round 1's GPU budget was
+# spent, in one box visit (1 GPU).  Each step writes its own log under gpurun_out/ and never stops the
+# script, so that one failure does not hide the rest.
+#     gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_call.sh'
+set +e
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout ${T:-420} "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -3 gpurun_out/$name.log; }
+run t_validated   python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_multirank.py -k "not _z"
+for f in z1_prefetch z2_sequencer z3_retrieval z4_robust z5_graph z6_heads; do
+  run t_$f python -m pytest tests/test_gpu_$f.py -q -m gpu
+done
+run smoke         python __graft_entry__.py --smoke
+run bench_default python bench.py --steps 10 --warmup 3
+ONEPROT_SEQ=1 run bench_seq python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run host_1024     python tools/host_overhead.py 1024
+run host_4096     python tools/host_overhead.py 4096
+run eager_bar     python tests/perf_eager_bar.py --sizes 8192,32768 --reps 5
+run heads_bench   python tools/bench_heads.py
+grep -h '"metric"' gpurun_out/bench_default.log gpurun_out/bench_seq.log > gpurun_out/r2_bench_lines.json
+echo done

@@ -267,11 +267,29 @@ int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, cons
 int oneprot_gelu(const void* x, const void* gy, void* out, size_t count, int is_fp32, void* stream);
 /* MeanPooling.forward (base_encoder.py:107-118): y[b] = sum_l mask[b,l] x[b,l,:] / sum_l mask[b,l]
  * for x of shape B x L x D; mask fp32 B x L or NULL (plain mean); inv_count[b] = 1 / sum_l mask[b,l]. */
+/* normalize = 0: plain weighted sum y[b] = sum_l mask[b,l] x[b,l,:] (attention pooling; inv_count may be NULL) */
 int oneprot_meanpool_fwd(const void* x, const float* mask, void* y, float* inv_count, int B, int L, int D, int is_fp32,
-                         void* stream);
+                         int normalize, void* stream);
 /* gx[b,l,:] = mask[b,l] * inv_count[b] * gy[b,:] */
 int oneprot_meanpool_bwd(const void* gy, const float* mask, const float* inv_count, void* gx, int B, int L, int D, int is_fp32,
                          void* stream);
+
+/* Attention1dPooling (base_encoder.py:84-104): score[b,l] = <w, x[b,l,:]> + bias (a 1x1 conv to one
+ * channel), -inf where mask == 0, softmax over the tokens, weighted sum (oneprot_meanpool_fwd with
+ * the probabilities as weights and normalize = 0).
+ * oneprot_token_dot: out[b,l] = <vec, x[b,l,:]> + bias[0] (bias may be NULL); vec_per_batch = 0: one
+ * vector of D elements (the score layer), 1: B vectors (d p = <g[b], x[b,l]> in the backward);
+ * mask (fp32, may be NULL): out = -inf where mask == 0.  vec has the dtype of x. */
+int oneprot_token_dot(const void* x, const void* vec, int vec_per_batch, const float* bias, const float* mask, float* out, int B,
+                      int L, int D, int is_fp32, void* stream);
+/* p[b,:] = softmax(s[b,:]) over L (fp32; in place allowed);  ds = p * (dp - sum_k p_k dp_k) */
+int oneprot_softmax_rows(const float* s, float* p, int B, int L, void* stream);
+int oneprot_softmax_rows_bwd(const float* p, const float* dp, float* ds, int B, int L, void* stream);
+/* gx[b,l,:] = p[b,l] * g[b,:] + ds[b,l] * w[:]  (gradient w.r.t. the tokens) */
+int oneprot_attnpool_bwd_x(const void* g, const float* p, const float* ds, const void* w, void* gx, int B, int L, int D, int is_fp32,
+                           void* stream);
+/* out[k] = sum_s part[s * ld + k], k < count, in slot order (deterministic) */
+int oneprot_sum_slots_f32(const float* part, int slots, int ld, int count, float* out, void* stream);
 
 /* ---- host-side step sequencer (oneprot_b200/csrc/clip_sequence.cu) -------------------------------
  * One call enqueues a whole PHASE of ClipLoss.forward / its autograd backward (loss.py:103-114 and

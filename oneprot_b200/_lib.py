@@ -83,7 +83,12 @@ SIGNATURES = {
     "oneprot_layernorm_bwd_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_layernorm_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _sz, _i, _i, _i, _vp]),
     "oneprot_gelu": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
-    "oneprot_meanpool_fwd": (_i, [_vp, _fp, _vp, _fp, _i, _i, _i, _i, _vp]),
+    "oneprot_meanpool_fwd": (_i, [_vp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "oneprot_token_dot": (_i, [_vp, _vp, _i, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),
+    "oneprot_softmax_rows": (_i, [_fp, _fp, _i, _i, _vp]),
+    "oneprot_softmax_rows_bwd": (_i, [_fp, _fp, _fp, _i, _i, _vp]),
+    "oneprot_attnpool_bwd_x": (_i, [_vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "oneprot_sum_slots_f32": (_i, [_fp, _i, _i, _i, _fp, _vp]),
     "oneprot_meanpool_bwd": (_i, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _vp]),
     # host-side step sequencer + launch trace (csrc/clip_sequence.cu)
     "oneprot_seq_fwd_ws_bytes": (_sz, [_i, _i]),

@@ -235,7 +235,7 @@ __global__ void gelu_kernel(const void* __restrict__ x, const void* __restrict__
 // grid (B, ceil(D / 256)); 8 warps stride over the tokens, lane = 8 columns; mask == nullptr: plain mean
 template <bool FP32>
 __global__ void meanpool_fwd_kernel(const void* __restrict__ x, const float* __restrict__ mask, void* __restrict__ y,
-                                    float* __restrict__ inv_count, int L, int D) {
+                                    float* __restrict__ inv_count, int L, int D, int normalize) {
   __shared__ float red[8][256 + 8];
   __shared__ float cnt_s[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -260,8 +260,9 @@ __global__ void meanpool_fwd_kernel(const void* __restrict__ x, const float* __r
   float total = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) total += cnt_s[w];
-  const float inv = 1.f / total;            // all-masked rows give inf / nan like the reference's 0 / 0
-  if (threadIdx.x == 0 && blockIdx.y == 0) inv_count[b] = inv;
+  // normalize = 0: plain weighted sum (attention pooling, d weight of its score layer)
+  const float inv = normalize ? 1.f / total : 1.f;   // all-masked rows give inf / nan like the reference's 0 / 0
+  if (threadIdx.x == 0 && blockIdx.y == 0 && inv_count) inv_count[b] = inv;
   if (warp == 0 && k < D) {
     float o[8];
 #pragma unroll
@@ -290,6 +291,102 @@ __global__ void meanpool_bwd_kernel(const void* __restrict__ gy, const float* __
     float o[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) o[u] = m * g[u];
+    store8<FP32>(gx, (static_cast<size_t>(b) * L + l) * D + k, o);
+  }
+}
+
+// ---- Attention1dPooling (base_encoder.py:84-104): score_l = <w, x_l> + bias, masked softmax over the
+// tokens, weighted sum.  token_dot: one warp per token; vec_stride = 0: one vector for all batches
+// (the score layer), D: one vector per batch row (d p = <g_b, x_l> in the backward).
+template <bool FP32>
+__global__ void token_dot_kernel(const void* __restrict__ x, const void* __restrict__ vec, size_t vec_stride,
+                                 const float* __restrict__ bias, const float* __restrict__ mask, float* __restrict__ out,
+                                 int B, int L, int D) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int tokens = B * L;
+  const float bs = bias ? *bias : 0.f;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < tokens; t += gridDim.x * wpb) {
+    if (mask && mask[t] == 0.f) {          // masked_fill_(~mask, -inf), base_encoder.py:97-100
+      if (lane == 0) out[t] = -INFINITY;
+      continue;
+    }
+    const size_t vb = static_cast<size_t>(t / L) * vec_stride;
+    float acc = 0.f;
+    for (int k = lane * 8; k < D; k += 256) {
+      float fx[8], fv[8];
+      load8<FP32>(x, static_cast<size_t>(t) * D + k, fx);
+      load8<FP32>(vec, vb + k, fv);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(fx[u], fv[u], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[t] = acc + bs;
+  }
+}
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();               // red may still be read from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// one block per batch row: p = softmax(s) over L (fp32, any L)
+__global__ void softmax_rows_kernel(const float* __restrict__ s, float* __restrict__ p, int L) {
+  __shared__ float red[32];
+  const float* sr = s + static_cast<size_t>(blockIdx.x) * L;
+  float* pr = p + static_cast<size_t>(blockIdx.x) * L;
+  float m = -INFINITY;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) m = fmaxf(m, sr[l]);
+  m = block_reduce(m, true, red);
+  float z = 0.f;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) z += __expf(sr[l] - m);
+  z = block_reduce(z, false, red);
+  const float inv = 1.f / z;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) pr[l] = __expf(sr[l] - m) * inv;
+}
+
+// ds = p * (dp - sum_k p_k dp_k)
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds, int L) {
+  __shared__ float red[32];
+  const size_t base = static_cast<size_t>(blockIdx.x) * L;
+  float acc = 0.f;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const float pl = p[base + l];
+    if (pl != 0.f) acc = fmaf(pl, dp[base + l], acc);     // masked tokens: p = 0, dp may be anything
+  }
+  acc = block_reduce(acc, false, red);
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const float pl = p[base + l];
+    ds[base + l] = (pl != 0.f) ? pl * (dp[base + l] - acc) : 0.f;
+  }
+}
+
+// gx[b,l,:] = p[b,l] * g[b,:] + ds[b,l] * w[:]
+template <bool FP32>
+__global__ void attnpool_bwd_x_kernel(const void* __restrict__ g, const float* __restrict__ p, const float* __restrict__ ds,
+                                      const void* __restrict__ w, void* __restrict__ gx, int L, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int k = blockIdx.y * 256 + lane * 8;
+  if (k >= D) return;
+  float fg[8], fw[8];
+  load8<FP32>(g, static_cast<size_t>(b) * D + k, fg);
+  load8<FP32>(w, k, fw);
+  for (int l = warp; l < L; l += 8) {
+    const float pl = p[static_cast<size_t>(b) * L + l], dl = ds[static_cast<size_t>(b) * L + l];
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o[u] = fmaf(pl, fg[u], dl * fw[u]);
     store8<FP32>(gx, (static_cast<size_t>(b) * L + l) * D + k, o);
   }
 }
@@ -396,16 +493,16 @@ int oneprot_gelu(const void* x, const void* gy, void* out, size_t count, int is_
 }
 
 int oneprot_meanpool_fwd(const void* x, const float* mask, void* y, float* inv_count, int B, int L, int D, int is_fp32,
-                         void* stream) {
-  if (!x || !y || !inv_count || B <= 0 || L <= 0 || D <= 0 || D % 8) return opint::fail(ONEPROT_ERR_ARG, "meanpool_fwd: need D a positive multiple of 8");
+                         int normalize, void* stream) {
+  if (!x || !y || (normalize && !inv_count) || B <= 0 || L <= 0 || D <= 0 || D % 8) return opint::fail(ONEPROT_ERR_ARG, "meanpool_fwd: need D a positive multiple of 8");
   if (!al16(x) || !al16(y)) return opint::fail(ONEPROT_ERR_ARG, "meanpool_fwd: pointers must be 16-byte aligned");
-  if (optrace::recording()) optrace::add("meanpool_fwd x=%p mask=%p y=%p inv_count=%p B=%d L=%d D=%d fp32=%d st=%p", x, (const void*)mask, y, (void*)inv_count, B, L, D, is_fp32, stream);
+  if (optrace::recording()) optrace::add("meanpool_fwd x=%p mask=%p y=%p inv_count=%p B=%d L=%d D=%d fp32=%d normalize=%d st=%p", x, (const void*)mask, y, (void*)inv_count, B, L, D, is_fp32, normalize, stream);
   opint::count_launch(1);
   if (optrace::dry()) return ONEPROT_OK;
   const dim3 grid(B, cdiv(D, 256));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_fp32) oph::meanpool_fwd_kernel<true><<<grid, 256, 0, st>>>(x, mask, y, inv_count, L, D);
-  else oph::meanpool_fwd_kernel<false><<<grid, 256, 0, st>>>(x, mask, y, inv_count, L, D);
+  if (is_fp32) oph::meanpool_fwd_kernel<true><<<grid, 256, 0, st>>>(x, mask, y, inv_count, L, D, normalize);
+  else oph::meanpool_fwd_kernel<false><<<grid, 256, 0, st>>>(x, mask, y, inv_count, L, D, normalize);
   HD_CUDA(cudaGetLastError());
   return ONEPROT_OK;
 }
@@ -421,6 +518,68 @@ int oneprot_meanpool_bwd(const void* gy, const float* mask, const float* inv_cou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_fp32) oph::meanpool_bwd_kernel<true><<<grid, 256, 0, st>>>(gy, mask, inv_count, gx, L, D);
   else oph::meanpool_bwd_kernel<false><<<grid, 256, 0, st>>>(gy, mask, inv_count, gx, L, D);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_token_dot(const void* x, const void* vec, int vec_per_batch, const float* bias, const float* mask, float* out, int B,
+                      int L, int D, int is_fp32, void* stream) {
+  if (!x || !vec || !out || B <= 0 || L <= 0 || D <= 0 || D % 8) return opint::fail(ONEPROT_ERR_ARG, "token_dot: need D a positive multiple of 8");
+  if (!al16(x) || !al16(vec)) return opint::fail(ONEPROT_ERR_ARG, "token_dot: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("token_dot x=%p vec=%p per_batch=%d bias=%p mask=%p out=%p B=%d L=%d D=%d fp32=%d st=%p", x, vec, vec_per_batch, (const void*)bias, (const void*)mask, (void*)out, B, L, D, is_fp32, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const long long tokens = static_cast<long long>(B) * L;
+  const int blocks = static_cast<int>(std::min<long long>((tokens + 7) / 8, static_cast<long long>(oneprot_num_sms()) * 16));
+  const size_t stride = vec_per_batch ? static_cast<size_t>(D) : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) oph::token_dot_kernel<true><<<blocks, 256, 0, st>>>(x, vec, stride, bias, mask, out, B, L, D);
+  else oph::token_dot_kernel<false><<<blocks, 256, 0, st>>>(x, vec, stride, bias, mask, out, B, L, D);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_softmax_rows(const float* s, float* p, int B, int L, void* stream) {
+  if (!s || !p || B <= 0 || L <= 0) return opint::fail(ONEPROT_ERR_ARG, "softmax_rows: bad argument");
+  if (optrace::recording()) optrace::add("softmax_rows s=%p p=%p B=%d L=%d st=%p", (const void*)s, (void*)p, B, L, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  oph::softmax_rows_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, p, L);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_softmax_rows_bwd(const float* p, const float* dp, float* ds, int B, int L, void* stream) {
+  if (!p || !dp || !ds || B <= 0 || L <= 0) return opint::fail(ONEPROT_ERR_ARG, "softmax_rows_bwd: bad argument");
+  if (optrace::recording()) optrace::add("softmax_rows_bwd p=%p dp=%p ds=%p B=%d L=%d st=%p", (const void*)p, (const void*)dp, (void*)ds, B, L, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  oph::softmax_rows_bwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, dp, ds, L);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_attnpool_bwd_x(const void* g, const float* p, const float* ds, const void* w, void* gx, int B, int L, int D, int is_fp32,
+                           void* stream) {
+  if (!g || !p || !ds || !w || !gx || B <= 0 || L <= 0 || D <= 0 || D % 8) return opint::fail(ONEPROT_ERR_ARG, "attnpool_bwd_x: need D a positive multiple of 8");
+  if (!al16(g) || !al16(w) || !al16(gx)) return opint::fail(ONEPROT_ERR_ARG, "attnpool_bwd_x: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("attnpool_bwd_x g=%p p=%p ds=%p w=%p gx=%p B=%d L=%d D=%d fp32=%d st=%p", g, (const void*)p, (const void*)ds, w, gx, B, L, D, is_fp32, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const dim3 grid(B, cdiv(D, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) oph::attnpool_bwd_x_kernel<true><<<grid, 256, 0, st>>>(g, p, ds, w, gx, L, D);
+  else oph::attnpool_bwd_x_kernel<false><<<grid, 256, 0, st>>>(g, p, ds, w, gx, L, D);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_sum_slots_f32(const float* part, int slots, int ld, int count, float* out, void* stream) {
+  if (!part || !out || slots <= 0 || count <= 0 || ld < count) return opint::fail(ONEPROT_ERR_ARG, "sum_slots_f32: bad argument");
+  if (optrace::recording()) optrace::add("sum_slots_f32 part=%p slots=%d ld=%d count=%d out=%p st=%p", (const void*)part, slots, ld, count, (void*)out, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  oph::sum_slots_f32_kernel<<<cdiv(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(part, slots, ld, count, out);
   HD_CUDA(cudaGetLastError());
   return ONEPROT_OK;
 }

@@ -4,7 +4,7 @@ Drop-in for the reference's ``BaseEncoder`` head (``src/models/components/base_e
 ``pooling -> proj -> norm`` with the same constructor, the same sub-module names and the same
 parameter names, so that a reference checkpoint's ``pooling.* / proj.* / norm.*`` keys load:
 
-    pooling   MeanPooling (masked mean, :107-118) | CLSTokenPooling (:121-126) | Identity
+    pooling   MeanPooling (masked mean, :107-118) | CLSTokenPooling (:121-126) | Attention1dPooling (:84-104) | Identity
     proj      Identity | LayerNorm -> Linear(no bias)                                ('linear', :146-150)
                        | LayerNorm -> Linear -> GELU -> LayerNorm -> Linear         ('mlp',    :151-159)
     norm      Normalize(dim=-1) [-> LearnableLogitScaling]                           (:166-176, epilogue.py)
@@ -19,8 +19,9 @@ bf16 operands with fp32 accumulation; fp32 modules (the reference's default prec
 ``src/train.py:98``) split both operands into bf16 limbs (hh + hm + mh, error 2^-16 per product -
 tighter than TF32's 2^-11) exactly as ``ClipLoss`` does for fp32 features.  No eager fallback.
 
-``Attention1dPooling`` (:84-104, used by one experiment config) is not built yet: asking for it
-raises ``NotImplementedError`` instead of silently running eager PyTorch.
+``Attention1dPooling`` (:84-104, the sequence tower of ``configs/experiment/train_ddp_1.yaml``): one dot
+product per token (warp per token), a masked softmax over the tokens (block per batch row) and the
+weighted sum through the pooling kernel; its backward reuses the same three kernels.
 """
 from __future__ import annotations
 
@@ -274,6 +275,83 @@ class MeanPooling(nn.Module):
         return _MeanPoolFn.apply(features, input_mask)
 
 
+class _AttnPoolFn(torch.autograd.Function):
+    """out[b] = sum_l softmax_l(<w, x[b,l]> + bias, masked)[l] * x[b,l]   (base_encoder.py:84-104)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask):
+        K = _KERNELS
+        x3 = x.detach().contiguous()
+        B, L, D = x3.shape
+        if D % 8:
+            raise ValueError("oneprot_b200.Attention1dPooling: the feature dim must be a multiple of 8")
+        w = weight.detach().reshape(D).to(x3.dtype).contiguous()
+        bs = bias.detach().reshape(1).to(device=x.device, dtype=torch.float32)
+        m = None if mask is None else mask.detach().to(device=x.device, dtype=torch.float32).reshape(B, L).contiguous()
+        p = torch.empty(B, L, dtype=torch.float32, device=x.device)
+        K.token_dot(x3, w, p, bias=bs, mask=m)
+        K.softmax_rows(p, p)
+        y = torch.empty(B, D, dtype=x3.dtype, device=x.device)
+        K.meanpool_fwd(x3, p, y, None, normalize=False)
+        ctx.saved = (x3, w, p)
+        ctx.meta = (weight.shape, weight.dtype, bias.shape, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        K = _KERNELS
+        x3, w, p = ctx.saved
+        wshape, wdt, bshape, bdt = ctx.meta
+        B, L, D = x3.shape
+        g = (gy.to(x3.dtype) if gy.dtype != x3.dtype else gy).contiguous()
+        dp = torch.empty(B, L, dtype=torch.float32, device=g.device)
+        K.token_dot(x3, g, dp)                         # d p[b,l] = <g[b], x[b,l]>
+        ds = torch.empty_like(dp)
+        K.softmax_rows_bwd(p, dp, ds)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x3)
+            K.attnpool_bwd_x(g, p, ds, w, gx)          # p[b,l] g[b] + ds[b,l] w
+        if ctx.needs_input_grad[1]:
+            # d w = sum_{b,l} ds[b,l] x[b,l]: per-batch weighted sums, then a fixed-order sum over the batch
+            part = torch.empty(B, D, dtype=x3.dtype, device=g.device)
+            K.meanpool_fwd(x3, ds, part, None, normalize=False)
+            gwv = torch.empty(D, dtype=torch.float32, device=g.device)
+            K.sum_slots_f32(part if part.dtype == torch.float32 else part.float(), gwv)
+            gw = gwv.reshape(wshape).to(wdt)
+        if ctx.needs_input_grad[2]:
+            t = torch.empty(1, dtype=torch.float32, device=g.device)
+            K.sum_f32(ds.reshape(-1), t)
+            gb = t.reshape(bshape).to(bdt)
+        return gx, gw, gb, None
+
+
+class _ScoreLayer(nn.Module):
+    """Parameters of the reference's ``MaskedConv1d(hidden_size, 1, 1)`` (base_encoder.py:40-81,87): a
+    1x1 convolution to one channel = one dot product per token.  Same names, shapes and initialisation
+    as ``torch.nn.Conv1d`` so that ``pooling.layer.weight / bias`` of a reference checkpoint load."""
+
+    def __init__(self, hidden_size: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(1, hidden_size, 1))
+        self.bias = nn.Parameter(torch.empty(1))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(hidden_size)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class Attention1dPooling(nn.Module):
+    """base_encoder.py:84-104: learned scores, masked softmax over the tokens, weighted sum."""
+
+    def __init__(self, hidden_size: int):
+        super().__init__()
+        self.layer = _ScoreLayer(hidden_size)
+
+    def forward(self, x, input_mask=None):
+        _check_dtype(x, "Attention1dPooling")
+        return _AttnPoolFn.apply(x, self.layer.weight, self.layer.bias, input_mask)
+
+
 class CLSTokenPooling(nn.Module):
     """base_encoder.py:121-126 (a strided view; no arithmetic)."""
 
@@ -330,7 +408,7 @@ class BaseEncoder(nn.Module):
         elif pooling_type == 'cls':
             return CLSTokenPooling()
         elif pooling_type == 'attention1d':
-            raise NotImplementedError("oneprot_b200.BaseEncoder: attention1d pooling (base_encoder.py:84-104) is not built yet")
+            return Attention1dPooling(hidden_size)
         else:
             return _IdentityPooling()
 

@@ -333,11 +333,49 @@ def gelu(x, out, gy=None):
     check(_lib.load().oneprot_gelu(ptr(x), ptr(gy), ptr(out), x.numel(), _is32(x), _stream()), "oneprot_gelu")
 
 
-def meanpool_fwd(x, mask, y, inv_count):
+def meanpool_fwd(x, mask, y, inv_count, normalize: bool = True):
+    """y[b] = sum_l mask[b,l] x[b,l,:] (/ sum_l mask[b,l] when normalize)."""
     _need_cuda(x, mask, y, inv_count)
     B, L, D = x.shape
-    check(_lib.load().oneprot_meanpool_fwd(ptr(x), ptr(mask), ptr(y), ptr(inv_count), B, L, D, _is32(x), _stream()),
-          "oneprot_meanpool_fwd")
+    check(_lib.load().oneprot_meanpool_fwd(ptr(x), ptr(mask), ptr(y), ptr(inv_count), B, L, D, _is32(x), int(normalize),
+                                           _stream()), "oneprot_meanpool_fwd")
+
+
+def token_dot(x, vec, out, bias=None, mask=None):
+    """out[b,l] = <vec, x[b,l,:]> + bias; vec: (D,) shared or (B, D) per batch row; -inf where mask == 0."""
+    _need_cuda(x, vec, out, bias, mask)
+    B, L, D = x.shape
+    if vec.dtype != x.dtype or not vec.is_contiguous():
+        raise ValueError("token_dot: vec must be contiguous with the dtype of x")
+    check(_lib.load().oneprot_token_dot(ptr(x), ptr(vec), int(vec.dim() == 2), ptr(bias), ptr(mask), ptr(out), B, L, D, _is32(x),
+                                        _stream()), "oneprot_token_dot")
+
+
+def softmax_rows(s, p):
+    _need_cuda(s, p)
+    B, L = s.shape
+    check(_lib.load().oneprot_softmax_rows(ptr(s), ptr(p), B, L, _stream()), "oneprot_softmax_rows")
+
+
+def softmax_rows_bwd(p, dp, ds):
+    _need_cuda(p, dp, ds)
+    B, L = p.shape
+    check(_lib.load().oneprot_softmax_rows_bwd(ptr(p), ptr(dp), ptr(ds), B, L, _stream()), "oneprot_softmax_rows_bwd")
+
+
+def attnpool_bwd_x(g, p, ds, w, gx):
+    _need_cuda(g, p, ds, w, gx)
+    B, L, D = gx.shape
+    check(_lib.load().oneprot_attnpool_bwd_x(ptr(g), ptr(p), ptr(ds), ptr(w), ptr(gx), B, L, D, _is32(gx), _stream()),
+          "oneprot_attnpool_bwd_x")
+
+
+def sum_slots_f32(part, out):
+    """out[k] = sum_s part[s, k] (part: slots x count fp32, fixed order)."""
+    _need_cuda(part, out)
+    slots, count = part.shape
+    check(_lib.load().oneprot_sum_slots_f32(ptr(part), slots, part.stride(0), count, ptr(out), _stream()),
+          "oneprot_sum_slots_f32")
 
 
 def meanpool_bwd(gy, mask, inv_count, gx):

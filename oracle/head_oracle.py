@@ -4,7 +4,7 @@
 Numpy float64 restatement, forward AND backward, of the reference's ``BaseEncoder`` head
 (/root/reference/src/models/components/base_encoder.py:107-194):
 
-    pooling (MeanPooling :107-118 | CLSTokenPooling :121-126 | identity)
+    pooling (MeanPooling :107-118 | CLSTokenPooling :121-126 | Attention1dPooling :84-104 | identity)
     -> proj ('linear': LayerNorm, Linear(no bias) :146-150 | 'mlp': LayerNorm, Linear, GELU, LayerNorm, Linear :151-159)
     -> norm (F.normalize(dim=-1) :6-12 [-> clip(exp(log_s), max) * x :15-33])
 
@@ -39,6 +39,24 @@ def meanpool_bwd(gy, mask, shape):
         return np.broadcast_to(gy[:, None, :] / L, shape).copy()
     m = mask.astype(np.float64)
     return gy[:, None, :] * (m / m.sum(axis=1, keepdims=True))[:, :, None]
+
+
+def attnpool_fwd(x, mask, w, bias):
+    """Attention1dPooling.forward (base_encoder.py:89-104): x (B, L, D), w (D,), bias scalar."""
+    s = x @ w + bias
+    if mask is not None:
+        s = np.where(mask.astype(bool), s, -np.inf)
+    s = s - s.max(axis=1, keepdims=True)
+    p = np.exp(s)
+    p = p / p.sum(axis=1, keepdims=True)
+    return (p[:, :, None] * x).sum(axis=1), p
+
+
+def attnpool_bwd(gy, x, w, p):
+    dp = (x * gy[:, None, :]).sum(axis=2)
+    ds = p * (dp - (p * dp).sum(axis=1, keepdims=True))
+    gx = p[:, :, None] * gy[:, None, :] + ds[:, :, None] * w[None, None, :]
+    return gx, (ds[:, :, None] * x).sum(axis=(0, 1)), ds.sum()
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-5):
@@ -91,6 +109,9 @@ def head_forward_backward(x, mask, params, *, proj_type, pooling_type, use_logit
         h0 = meanpool_fwd(x, mask)
     elif pooling_type == "cls":
         h0 = x[:, 0]
+    elif pooling_type == "attention1d":
+        aw = P["pooling.layer.weight"].reshape(-1)
+        h0, ap = attnpool_fwd(x, mask, aw, float(P["pooling.layer.bias"].reshape(-1)[0]))
     else:
         h0 = x
     grads = {}
@@ -136,6 +157,10 @@ def head_forward_backward(x, mask, params, *, proj_type, pooling_type, use_logit
         gx = np.zeros_like(x)
         gx[:, 0] = gh0
         grads["x"] = gx
+    elif pooling_type == "attention1d":
+        grads["x"], gw, gb = attnpool_bwd(gh0, x, aw, ap)
+        grads["pooling.layer.weight"] = gw.reshape(P["pooling.layer.weight"].shape)
+        grads["pooling.layer.bias"] = np.asarray(gb).reshape(P["pooling.layer.bias"].shape)
     else:
         grads["x"] = gh0
     return y, grads

@@ -155,6 +155,8 @@ def head_cases():
         ("linear_cls", 48, 40, "linear", "cls", False, False, 5, 7),
         ("linear_identity_scale", 56, 24, "linear", "identity", True, False, 10, 0),   # struct-graph style: 2-D input
         ("none_mean", 32, 32, None, "mean", False, False, 4, 5),
+        # attention1d pooling has its hidden size hard-wired to 1280 (base_encoder.py:179); train_ddp_1.yaml's sequence head
+        ("linear_attn1d", 1280, 16, "linear", "attention1d", False, False, 3, 6),
     ]
     for name, dm, do, proj, pool, uls, learn, B, L in cases:
         g = torch.Generator().manual_seed(len(name) * 101 + dm)
@@ -165,7 +167,7 @@ def head_cases():
                     p.copy_((p + 0.3 * torch.randn(p.shape, generator=g).double()).to(torch.bfloat16).double())
         x = torch.randn((B, L, dm) if L else (B, dm), generator=g).to(torch.bfloat16)
         mask = None
-        if L and pool == "mean":
+        if L and pool in ("mean", "attention1d"):
             lens = torch.randint(1, L + 1, (B,), generator=g)
             mask = (torch.arange(L)[None, :] < lens[:, None]).long()
         gy = torch.randn(B, do, generator=g).to(torch.bfloat16)

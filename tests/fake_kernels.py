@@ -250,13 +250,46 @@ def gelu(x, out, gy=None):
         out.copy_((gy.double() * (cdf + xd * pdf)).to(out.dtype))
 
 
-def meanpool_fwd(x, mask, y, inv_count):
+def meanpool_fwd(x, mask, y, inv_count, normalize=True):
     CALLS.append("meanpool_fwd")
     B, L, D = x.shape
     m = torch.ones(B, L, dtype=torch.float64) if mask is None else mask.double()
-    cnt = m.sum(1)
+    cnt = m.sum(1) if normalize else torch.ones(B, dtype=torch.float64)
     y.copy_(((x.double() * m[:, :, None]).sum(1) / cnt[:, None]).to(y.dtype))
-    inv_count.copy_((1.0 / cnt).float())
+    if inv_count is not None:
+        inv_count.copy_((1.0 / cnt).float())
+
+
+def token_dot(x, vec, out, bias=None, mask=None):
+    CALLS.append("token_dot")
+    v = vec.double()
+    s = (x.double() * (v[:, None, :] if v.dim() == 2 else v)).sum(-1)
+    if bias is not None:
+        s = s + float(bias[0])
+    if mask is not None:
+        s = torch.where(mask != 0, s, torch.full_like(s, float("-inf")))
+    out.copy_(s.float())
+
+
+def softmax_rows(s, p):
+    CALLS.append("softmax_rows")
+    p.copy_(torch.softmax(s.double(), dim=1).float())
+
+
+def softmax_rows_bwd(p, dp, ds):
+    CALLS.append("softmax_rows_bwd")
+    pd, dd = p.double(), torch.where(p != 0, dp.double(), torch.zeros_like(dp.double()))
+    ds.copy_((pd * (dd - (pd * dd).sum(1, keepdim=True))).float())
+
+
+def attnpool_bwd_x(g, p, ds, w, gx):
+    CALLS.append("attnpool_bwd_x")
+    gx.copy_((p.double()[:, :, None] * g.double()[:, None, :] + ds.double()[:, :, None] * w.double()[None, None, :]).to(gx.dtype))
+
+
+def sum_slots_f32(part, out):
+    CALLS.append("sum_slots_f32")
+    out.copy_(part.double().sum(0).float())
 
 
 def meanpool_bwd(gy, mask, inv_count, gx):

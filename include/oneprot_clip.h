@@ -141,6 +141,26 @@ int oneprot_clip_loss_finalize_ex(const float* rowsum_all, const float* colsum_a
 int oneprot_retrieval_ranks(const void* S, const void* M, int N, int d, const float* label_dot, float* rank_s2m,
                             float* rank_m2s, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- SigLipLoss (loss.py:204-311), the other objective behind OneProt's loss_fn switch
+ * (oneprot_module.py:57-62):  value_r = -(1/n) sum_{i in rank r, j} logsigmoid(y_ij z_ij),
+ * z_ij = logit_scale <a_i, b_j> + logit_bias, y = +1 on the global diagonal and -1 elsewhere.
+ * Since -logsigmoid(-z) = softplus(z) and -logsigmoid(z) = softplus(z) - z, the tile epilogue only
+ * sums softplus(z) and the label term comes from the diag of oneprot_clip_rowstats:
+ *   oneprot_siglip_fwd       rowsum[i] = sum_j log2(1 + 2^x_ij), x = log2(e) z (same tensor-core mainloop
+ *                            as the ClipLoss forward; scratch of oneprot_clip_fwd_scratch_bytes(n, N))
+ *   oneprot_siglip_finalize  loss_out[0] = (ln2 sum_i rowsum[i] - sum_i (logit_scale diag[i] + bias)) / n
+ *   oneprot_siglip_dz_panel  Wz_ij = wr[i] sigma(z_ij) - [grow0 + i == j] dg[i]  (bf16 panel, as
+ *                            oneprot_clip_dz_panel; dL/dz_ij = (g / n) (sigma(z_ij) - [i == j]))
+ * The ring of neighbour exchanges of the reference (loss.py:258-309) becomes the all-gather of the
+ * second operand + reduce-scatter of its partial gradient that the ClipLoss path already uses.
+ * bias_dev may be NULL (no logit_bias). */
+int oneprot_siglip_fwd(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev, const float* bias_dev,
+                       float* rowsum, void* scratch, size_t scratch_bytes, void* stream);
+int oneprot_siglip_finalize(const float* rowsum, const float* diag, int n, const float* scale_dev, const float* bias_dev,
+                            float* loss_out, void* stream);
+int oneprot_siglip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0, const float* scale_dev,
+                            const float* bias_dev, const float* wr, const float* dg, void* Wz, int ldw, void* stream);
+
 /* ---- backward ----------------------------------------------------------------------------- */
 
 /* Per-row / per-column / diagonal coefficients of dL/dZ for the panel of this rank:

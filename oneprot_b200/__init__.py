@@ -20,6 +20,9 @@ def __getattr__(name):
     if name in ("RetrievalMetric", "retrieval_ranks"):
         from . import retrieval
         return getattr(retrieval, name)
+    if name == "SigLipLoss":
+        from . import siglip_loss
+        return siglip_loss.SigLipLoss
     if name in ("BaseEncoder", "LayerNorm", "Linear", "GELU", "MeanPooling", "CLSTokenPooling"):
         from . import heads
         return getattr(heads, name)

@@ -272,12 +272,14 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
   }
 }
 
-enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4 };   // RCMAX: row/col maxima; RANK: retrieval ranks
+enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4,    // RCMAX: row/col maxima; RANK: retrieval ranks
+       EPI_SFWD = 5, EPI_SDZ = 6 };   // SigLIP: row sums of softplus(z) / dL/dZ panel sigma(z) wr_i - [i == j] dg_i
 
 template <int EPI>
 struct SCfg {
   static constexpr int NS = 4;                                             // operand ring depth
-  static constexpr int STAGING = (EPI == EPI_DZ) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX need none
+  static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ);            // writes a bf16 dL/dZ panel by TMA stores
+  static constexpr int STAGING = PANEL ? STORE_STAGING_BYTES : 0;             // FWD / MAX / RCMAX / RANK / SFWD need none
   static constexpr int SMEM = smem_bytes(NS, STAGING);
 };
 
@@ -392,8 +394,14 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int lane = lane_id();
     const int r = q * 32 + lane; // row inside the tile
     float c, negG;
+    constexpr bool PANEL = SCfg<EPI>::PANEL;
     if (EPI == EPI_MAX || EPI == EPI_RCMAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
     else if (EPI == EPI_RANK) { c = 1.f; negG = 0.f; }
+    else if (EPI == EPI_SFWD || EPI == EPI_SDZ) {
+      // SigLIP: x = log2(e) (logit_scale <a, b> + logit_bias); the bias pointer travels in p.wc (no column weights here)
+      c = __ldg(p.scale) * LOG2E;
+      negG = p.wc ? __ldg(p.wc) * LOG2E : 0.f;
+    }
     else load_c_and_G(p, c, negG);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -426,7 +434,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const bool edge = (ib * BM + BM > p.rows) || (jb * BN + BN > p.N);
         float wr_i = 0.f, dg_i = 0.f;
         bool diag_tile = false;
-        if (EPI == EPI_DZ) {
+        if (PANEL) {
           if (rowok) { wr_i = __ldg(p.wr + i); dg_i = __ldg(p.dg + i); }
           const int g0 = p.grow0 + ib * BM;       // global rows [g0, g0+128)
           diag_tile = (g0 < j0 + 128) && (j0 < g0 + BM);
@@ -437,8 +445,8 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         float rsum = 0.f;
         // DZ keeps no per-column accumulators, so the whole 128-column row slice fits in registers:
         // read it at once and hand the TMEM buffer back before the (store-paced) rest of the epilogue.
-        float vall[EPI == EPI_DZ ? 4 : 1][32];
-        if (EPI == EPI_DZ) {
+        float vall[PANEL ? 4 : 1][32];
+        if (PANEL) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(taddr + cc * 32, vall[cc]);
           tmem_ld_wait();
@@ -449,7 +457,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           float vbuf[32];
-          if (EPI != EPI_DZ) {
+          if (!PANEL) {
             tmem_ld_32x32(taddr + cc * 32, vbuf);
             tmem_ld_wait();
             if (cc == 3) {
@@ -459,7 +467,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               if (lane == 0) mbar_arrive(&s.tail->tempty[acc]);
             }
           }
-          float (&v)[32] = (EPI == EPI_DZ) ? vall[cc] : vbuf;
+          float (&v)[32] = PANEL ? vall[cc] : vbuf;
           if (EPI == EPI_MAX) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
@@ -500,6 +508,17 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
             continue;
           }
+          if (EPI == EPI_SFWD) {
+            // softplus in log2 units, overflow-free: log2(1 + 2^x) = max(x, 0) + log2(1 + 2^-|x|)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const bool ok = rowok && (j0 + cc * 32 + k < p.N);
+              const float x = fmaf(v[k], c, negG);
+              const float sp = fmaxf(x, 0.f) + __log2f(1.f + ex2(-fabsf(x)));
+              rsum += ok ? sp : 0.f;
+            }
+            continue;
+          }
           if (EPI == EPI_FWD) {
             if (!edge) {
 #pragma unroll
@@ -526,14 +545,20 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             uint32_t packed[16];
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) {
-              const float4 w4 = ld_shared_f4(colvec_s + (h * 128 + cc * 32 + k4 * 4) * 4);
-              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
               float dz[4];
+              if (EPI == EPI_SDZ) {
+                // sigma(z) = 1 / (1 + 2^-x): 0 for x -> -inf (2^-x = inf), 1 for x -> +inf
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int k = k4 * 4 + u;
-                const float e = ex2(fmaf(v[k], c, negG));
-                dz[u] = e * (wr_i + wv[u]);
+                for (int u = 0; u < 4; ++u) dz[u] = __fdividef(wr_i, 1.f + ex2(-fmaf(v[k4 * 4 + u], c, negG)));
+              } else {
+                const float4 w4 = ld_shared_f4(colvec_s + (h * 128 + cc * 32 + k4 * 4) * 4);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int k = k4 * 4 + u;
+                  const float e = ex2(fmaf(v[k], c, negG));
+                  dz[u] = e * (wr_i + wv[u]);
+                }
               }
               if (diag_tile) {
 #pragma unroll
@@ -560,7 +585,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
           }
         }
-        if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) {
+        if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD) {
           p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -577,7 +602,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
       }
     }
-    if (EPI == EPI_DZ && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
+    if (PANEL && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
     if (EPI == EPI_MAX) {
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
@@ -1129,6 +1154,26 @@ __global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const flo
     for (unsigned b = 0; b < gridDim.x; ++b) t += *(volatile double*)(partial + b);
     loss_out[0] = static_cast<float>(t / (2.0 * (hi - lo)));
     *counter = 0;   // ready for the next launch
+  }
+}
+
+// SigLIP value of this rank: (ln2 * sum_i rowsum[i] - sum_i (s * diag[i] + bias)) / n with
+// rowsum[i] = sum_j log2(1 + 2^x_ij): the label term -logsigmoid(+z_ii) = softplus(z_ii) - z_ii.
+// One block, double accumulation in a fixed order (deterministic).
+__global__ void siglip_finalize_kernel(const float* __restrict__ rowsum, const float* __restrict__ diag, int n,
+                                       const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ loss_out) {
+  __shared__ double red[32];
+  const float s = *scale, b = bias ? *bias : 0.f;
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x)
+    acc += static_cast<double>(LN2) * static_cast<double>(rowsum[k]) - static_cast<double>(fmaf(s, diag[k], b));
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    loss_out[0] = static_cast<float>(t / n);
   }
 }
 
@@ -1797,6 +1842,78 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
   if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
   op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_siglip_fwd(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev, const float* bias_dev,
+                       float* rowsum, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!A || !B_all || !scale_dev || !rowsum || !scratch) return fail(ONEPROT_ERR_ARG, "siglip_fwd: null pointer");
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "siglip_fwd: need n, N > 0 and d a positive multiple of 8");
+  if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "siglip_fwd: scratch too small");
+  if (optrace::recording())
+    optrace::add("siglip_fwd A=%p B=%p n=%d N=%d d=%d scale=%p bias=%p rowsum=%p scratch=%p st=%p", A, B_all, n, N, d, (const void*)scale_dev,
+                 (const void*)bias_dev, (void*)rowsum, scratch, stream);
+  if (optrace::dry()) { g_launches += 2; return ONEPROT_OK; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  op::SParams p{};
+  s_schedule(n, N, 2, p);
+  p.rows = n; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = 0;
+  p.scale = scale_dev; p.wc = bias_dev;
+  p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
+  p.rowpart = static_cast<float*>(scratch);
+  CUtensorMap mapA, mapB;
+  int rc;
+  if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_SFWD>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_SFWD>, smem))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_SFWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+  op::reduce_slots_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
+  g_launches += 2;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_siglip_finalize(const float* rowsum, const float* diag, int n, const float* scale_dev, const float* bias_dev,
+                            float* loss_out, void* stream) {
+  if (!rowsum || !diag || !scale_dev || !loss_out || n <= 0) return fail(ONEPROT_ERR_ARG, "siglip_finalize: bad argument");
+  if (optrace::recording())
+    optrace::add("siglip_finalize rowsum=%p diag=%p n=%d scale=%p bias=%p loss=%p st=%p", (const void*)rowsum, (const void*)diag, n,
+                 (const void*)scale_dev, (const void*)bias_dev, (void*)loss_out, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
+  op::siglip_finalize_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rowsum, diag, n, scale_dev, bias_dev, loss_out);
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_siglip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0, const float* scale_dev,
+                            const float* bias_dev, const float* wr, const float* dg, void* Wz, int ldw, void* stream) {
+  if (!A_rows || !B_all || !scale_dev || !wr || !dg || !Wz) return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: null pointer");
+  if (rows <= 0 || N <= 0 || d <= 0 || d % 8 || ldw < N || ldw % 8) return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: bad sizes");
+  if (reinterpret_cast<uintptr_t>(Wz) & 15) return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: Wz must be 16-byte aligned");
+  if (optrace::recording())
+    optrace::add("siglip_dz_panel A=%p B=%p rows=%d N=%d d=%d grow0=%d scale=%p bias=%p wr=%p dg=%p Wz=%p ldw=%d st=%p", A_rows, B_all, rows,
+                 N, d, grow0, (const void*)scale_dev, (const void*)bias_dev, (const void*)wr, (const void*)dg, Wz, ldw, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
+  op::SParams p{};
+  s_schedule(rows, N, 1, p);
+  p.rows = rows; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = grow0;
+  p.scale = scale_dev; p.wc = bias_dev;
+  p.wr = wr; p.dg = dg;
+  p.Wz = static_cast<__nv_bfloat16*>(Wz); p.ldw = ldw;
+  CUtensorMap mapA, mapB, mapW;
+  int rc;
+  if ((rc = make_map(&mapA, A_rows, d, rows, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  if ((rc = make_map(&mapW, Wz, N, rows, ldw, op::BM))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_SDZ>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_SDZ>, smem))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_SDZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

@@ -223,6 +223,38 @@ def dz_panel(A_rows, B_all, grow0: int, scale_dev, stats, wr, wc, dg, Wz):
           "oneprot_clip_dz_panel")
 
 
+def siglip_fwd(A, B_all, scale_dev, bias_dev, rowsum, scratch=None):
+    """rowsum[i] = sum_j log2(1 + 2^x_ij), x = log2(e) (scale <a_i, b_j> + bias)  (SigLIP forward)."""
+    _need_cuda(A, B_all, scale_dev, bias_dev, rowsum)
+    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
+    n, d = A.shape
+    N = B_all.shape[0]
+    need = fwd_scratch_bytes(n, N)
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=A.device)
+    check(_lib.load().oneprot_siglip_fwd(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(bias_dev), ptr(rowsum), ptr(scratch),
+                                         scratch.numel() * scratch.element_size(), _stream()), "oneprot_siglip_fwd")
+    return scratch
+
+
+def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
+    _need_cuda(rowsum, diag, scale_dev, bias_dev, loss_out)
+    check(_lib.load().oneprot_siglip_finalize(ptr(rowsum), ptr(diag), rowsum.numel(), ptr(scale_dev), ptr(bias_dev), ptr(loss_out),
+                                              _stream()), "oneprot_siglip_finalize")
+
+
+def siglip_dz_panel(A_rows, B_all, grow0: int, scale_dev, bias_dev, wr, dg, Wz):
+    """Wz[i, j] = wr[i] sigma(z_ij) - [grow0 + i == j] dg[i]  (bf16 panel, rows x ldw)."""
+    _need_cuda(A_rows, B_all, scale_dev, bias_dev, wr, dg, Wz)
+    _need(A_rows, torch.bfloat16, "A_rows"); _need(B_all, torch.bfloat16, "B_all"); _need(Wz, torch.bfloat16, "Wz")
+    rows, d = A_rows.shape
+    N = B_all.shape[0]
+    if Wz.shape[0] < rows:
+        raise ValueError("Wz panel has fewer rows than A_rows")
+    check(_lib.load().oneprot_siglip_dz_panel(ptr(A_rows), ptr(B_all), rows, N, d, grow0, ptr(scale_dev), ptr(bias_dev), ptr(wr),
+                                              ptr(dg), ptr(Wz), Wz.stride(0), _stream()), "oneprot_siglip_dz_panel")
+
+
 def gemm_rowdot_scratch_floats(M: int, Nc: int) -> int:
     return int(_lib.load().oneprot_gemm_rowdot_scratch_bytes(M, Nc)) // 4
 

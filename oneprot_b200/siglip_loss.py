@@ -1,0 +1,182 @@
+"""Drop-in ``SigLipLoss`` for OneProt on B200 - the other objective behind the reference's ``loss_fn``
+switch (``src/models/oneprot_module.py:57-62``; reference class ``src/models/components/loss.py:204-311``).
+
+Same constructor ``SigLipLoss(cache_labels, rank, world_size, bidir, use_horovod)`` and
+``forward(modality_features, sequence_features, logit_scale=1.0, logit_bias=None, output_dict=False)``.
+
+    value_r = -(1/n) sum_{i in rank r} sum_{j} logsigmoid(y_ij z_ij),   z = logit_scale <a_i, b_j> + logit_bias,
+    y = +1 on the global diagonal, -1 elsewhere.
+
+The reference visits the blocks of other ranks by passing the second operand round a ring of
+``batch_isend_irecv`` neighbour exchanges (loss.py:258-309), W - 1 hops of one n x n block each.  Here
+rank r computes its whole n x N row panel in one pass of the tensor-core mainloop of the ClipLoss
+path (``clip_s_kernel<SFWD>``: softplus row sums, nothing stored per logit) on the all-gathered second
+operand; the backward recomputes the panel into the bounded bf16 dL/dZ workspace
+(``clip_s_kernel<SDZ>``: (g/n)(sigma(z) - [i == j])), dA = Wz B_all is local and the partial
+dB = Wz^T A is reduce-scattered - which is what the autograd of the ring (loss.py:169-201) adds up.
+``bidir`` only changes the reference's hop schedule, not the result; it is accepted and ignored.
+
+Scope of this first version: ``logit_scale`` / ``logit_bias`` as Python floats or tensors WITHOUT
+gradient (OneProt calls the loss with the defaults, oneprot_module.py:100); asking for their gradient
+raises.  Exchanges go through torch.distributed (all-gather / reduce-scatter).  No eager fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import clip_loss as _cl
+from .comm import _all_gather_rows, _reduce_scatter_rows
+
+try:
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    dist = None
+
+
+def _K():
+    return _cl._KERNELS          # the kernel provider of the ClipLoss path (tests swap it there)
+
+
+def _scalar_dev(v, device) -> Optional[torch.Tensor]:
+    if v is None:
+        return None
+    if torch.is_tensor(v):
+        if v.numel() != 1:
+            raise ValueError("logit_scale / logit_bias must be scalars")
+        if v.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("SigLipLoss on B200: gradients w.r.t. logit_scale / logit_bias are not built yet")
+        return v.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+    return _cl._float_scale_on(device, float(v))
+
+
+class _SigLipFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, A, B, scale_dev, bias_dev, cfg):
+        with _K().stream_scope():
+            K = _K()
+            W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
+            ops = _cl._Operands(A, B)
+            n, off = ops.n, rank * ops.n
+            dev = A.device
+            B_all = ops.B if W == 1 else _all_gather_rows(ops.B, W, group)
+            diag = torch.empty(n, dtype=torch.float32, device=dev)
+            stats = torch.zeros(4, dtype=torch.float32, device=dev)
+            K.rowstats(ops.A, B_all, off, diag, stats)                  # diag[i] = <a_i, b_{off+i}>: the label logits
+            rowsum = torch.empty(n, dtype=torch.float32, device=dev)
+            K.siglip_fwd(ops.A, B_all, scale_dev, bias_dev, rowsum)
+            loss32 = torch.empty(1, dtype=torch.float32, device=dev)
+            K.siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss32)
+            ctx.cfg, ctx.ops, ctx.B_all, ctx.scale_dev, ctx.bias_dev = cfg, ops, B_all, scale_dev, bias_dev
+            ctx.set_materialize_grads(False)
+            loss_f32 = loss32.reshape(()).clone()
+            ctx.mark_non_differentiable(loss_f32)
+            return loss32.reshape(()).to(cfg["loss_dtype"] or ops.in_dtype), loss_f32
+
+    @staticmethod
+    def backward(ctx, g_loss, _g32):
+        with _K().stream_scope():
+            K = _K()
+            cfg, ops, B_all = ctx.cfg, ctx.ops, ctx.B_all
+            W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
+            n, d = ops.n, ops.d
+            N, off = W * n, rank * n
+            dev = ops.A.device
+            need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
+                   else g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1))
+            # dL/dz_ij = (g / n) (sigma(z_ij) - [i == j]); the panel carries the logit_scale of d z / d <a, b> as well
+            coef = (ctx.scale_dev * g32 / n).expand(n).contiguous()
+            want_a, want_b = bool(need_a), bool(need_b or W > 1)       # with W > 1 every rank enters the reduce-scatter
+            grad_dtype = torch.float32 if ops.split else torch.bfloat16
+            ldw = (N + 63) // 64 * 64
+            rows_cap = max(128, (cfg["panel_bytes"] // (2 * ldw)) // 128 * 128)
+            if rows_cap < n:                                           # balanced, wave-aligned panels (as clip_loss.py)
+                unit = K.panel_row_unit(d)
+                n_panels = -(-n // rows_cap)
+                target = -(-n // n_panels)
+                if unit <= rows_cap:
+                    up = -(-target // unit) * unit
+                    rows_cap = up if up <= rows_cap else rows_cap // unit * unit
+                else:
+                    rows_cap = min(rows_cap, -(-target // 128) * 128)
+            panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
+            Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
+            n_bp = 2 if ops.split else 1
+            dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
+            dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
+            chain_b = _cl._GemmChain(N, d, dBp, None, len(panels) * n_bp) if want_b else None
+            b_pieces = ops.b_pieces(B_all)
+            for r0, rows in panels:
+                A_rows = ops.A[r0:r0 + rows]
+                K.siglip_dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.bias_dev, coef[r0:r0 + rows], coef[r0:r0 + rows], Wz)
+                Wp = Wz[:rows]
+                if want_b:
+                    for Ap in ops.a_pieces(A_rows):
+                        chain_b.add(Wp, True, Ap, True, rows)
+                if want_a:
+                    chain_a = _cl._GemmChain(rows, d, dA[r0:r0 + rows], None, n_bp)
+                    for Bp in b_pieces:
+                        chain_a.add(Wp, False, Bp, True, N)
+            if want_b and W > 1:
+                dBp = _reduce_scatter_rows(dBp, rank, W, group)
+            return _cl._finish_grad(dA, ops, need_a), _cl._finish_grad(dBp, ops, need_b), None, None, None
+
+
+class SigLipLoss(nn.Module):
+    """B200-native drop-in for the reference ``SigLipLoss`` (loss.py:204-311).
+
+    Extra keyword-only arguments: ``loss_dtype`` (dtype of the returned scalar, default = input dtype
+    like the reference), ``panel_bytes`` (bound of the bf16 dL/dZ panel), ``group`` (process group)."""
+
+    def __init__(self, cache_labels=False, rank=0, world_size=1, bidir=True, use_horovod=False, *,
+                 loss_dtype: Optional[torch.dtype] = None, panel_bytes: int = _cl.DEFAULT_PANEL_BYTES, group=None):
+        super().__init__()
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        assert not use_horovod  # as the reference (loss.py:229)
+        self.use_horovod = use_horovod
+        self.bidir = bidir
+        self.loss_dtype = loss_dtype
+        self.panel_bytes = int(panel_bytes)
+        self.group = group
+        self.prev_num_logits = 0
+        self.labels = {}
+        self.last_loss_fp32 = None
+
+    def get_ground_truth(self, device, dtype, num_logits, negative_only=False) -> torch.Tensor:
+        """loss.py:237-241 (API parity; the fused kernels use the diagonal implicitly)."""
+        labels = -torch.ones((num_logits, num_logits), device=device, dtype=dtype)
+        if not negative_only:
+            labels = 2 * torch.eye(num_logits, device=device, dtype=dtype) + labels
+        return labels
+
+    def get_logits(self, modality_features, sequence_features, logit_scale, logit_bias=None):
+        """Materialised logits as in loss.py:243-247 - DEBUG ONLY (tcgen05 GEMM, fp32 accumulators)."""
+        z = _cl.ClipLoss(world_size=1).get_logits(modality_features, sequence_features, logit_scale)[0]
+        if logit_bias is not None:
+            z = z + (logit_bias.to(z.dtype) if torch.is_tensor(logit_bias) else logit_bias)
+        return z
+
+    def forward(self, modality_features, sequence_features, logit_scale=1.0, logit_bias=None, output_dict=False):
+        A, B = modality_features, sequence_features
+        if A.dim() != 2 or B.dim() != 2 or A.shape != B.shape:
+            raise ValueError(f"SigLipLoss expects two (n, d) tensors of equal shape, got {tuple(A.shape)} and {tuple(B.shape)}")
+        if A.dtype != B.dtype or A.device != B.device:
+            raise ValueError("SigLipLoss expects both feature tensors on one device with one dtype")
+        if A.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+            raise ValueError(f"unsupported feature dtype {A.dtype}")
+        if self.world_size > 1:
+            if dist is None or not dist.is_initialized():
+                raise RuntimeError("SigLipLoss(world_size > 1) needs an initialised torch.distributed process group")
+            if dist.get_world_size(self.group) != self.world_size:
+                raise RuntimeError("SigLipLoss world_size does not match the process group")
+        cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, loss_dtype=self.loss_dtype,
+                   panel_bytes=self.panel_bytes)
+        loss, loss32 = _SigLipFunction.apply(A, B, _scalar_dev(logit_scale, A.device), _scalar_dev(logit_bias, A.device), cfg)
+        self.last_loss_fp32 = loss32
+        return {"contrastive_loss": loss} if output_dict else loss

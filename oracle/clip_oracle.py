@@ -247,3 +247,35 @@ def clip_loss_port_distributed(a_loc, b_loc, logit_scale, *, rank, world_size, l
 # import the oracle), re-exported here for the tests
 # ----------------------------------------------------------------------------------------------
 from tools.synthetic import synthetic_pair  # noqa: E402,F401
+
+
+# ----------------------------------------------------------------------------------------------
+# SigLipLoss (src/models/components/loss.py:204-311) - numpy float64 closed form
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SigLipResult:
+    loss: float          # value returned on this rank (loss.py:256-311)
+    dA: np.ndarray       # gradient w.r.t. this rank's first positional feature tensor
+    dB: np.ndarray       # gradient w.r.t. this rank's second positional feature tensor (ring backward: all ranks' losses)
+
+
+def siglip_closed_form(A_all: np.ndarray, B_all: np.ndarray, scale: float, bias: float = 0.0, *, rank: int = 0,
+                       world_size: int = 1, grad_outputs: Optional[np.ndarray] = None) -> SigLipResult:
+    """Rank ``rank`` scores its own rows against the second operand of EVERY rank - its own block with
+    labels 2I - 1 (loss.py:256), every other block with labels -1 (``negative_only``, loss.py:272-309;
+    the uni- and bidirectional rings visit the same blocks) - and divides each block's sum by the local
+    batch (loss.py:253).  The autograd of the neighbour exchanges (loss.py:169-201) returns to a rank
+    the gradient of ITS second operand from every rank's loss, each times that rank's upstream
+    gradient."""
+    N, W = A_all.shape[0], world_size
+    n = N // W
+    g = np.ones(W) if grad_outputs is None else np.asarray(grad_outputs, dtype=np.float64)
+    Z = scale * (A_all @ B_all.T) + bias
+    Y = -np.ones((N, N))
+    Y[np.arange(N), np.arange(N)] = 1.0
+    M = -Y * Z
+    lossmat = np.maximum(M, 0.0) + np.log1p(np.exp(-np.abs(M)))            # -logsigmoid(Y Z) = softplus(-Y Z)
+    rows = slice(rank * n, (rank + 1) * n)
+    dZ = (1.0 / (1.0 + np.exp(-Z)) - np.eye(N)) / n                         # d loss_r / d z_ij for i in rank r
+    dZ = dZ * np.repeat(g, n)[:, None]
+    return SigLipResult(loss=float(lossmat[rows].sum() / n), dA=scale * (dZ[rows] @ B_all), dB=scale * (dZ[:, rows].T @ A_all))

@@ -144,6 +144,61 @@ def epilogue_cases():
     print("wrote epilogue")
 
 
+def _siglip_worker(rank, world, port, n, d, bidir, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    sys.path.insert(0, REF)
+    from src.models.components.loss import SigLipLoss
+    from oracle.clip_oracle import synthetic_pair
+    a, b = synthetic_pair(n, d, seed=777, pair_id=0, rank=rank, correlated=True, temperature_into_b=False, dtype="bf16")
+    A = a.double().requires_grad_(True)
+    B = b.double().requires_grad_(True)
+    loss = SigLipLoss(rank=rank, world_size=world, bidir=bidir)(A, B, 10.0, -10.0)
+    (loss * (1.0 + 0.5 * rank)).backward()
+    results[rank] = {"A_bf16": bf16_bits(a), "B_bf16": bf16_bits(b), "loss": np.float64(loss.item()),
+                     "dA": A.grad.numpy().copy(), "dB": B.grad.numpy().copy()}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def siglip_cases():
+    """SigLipLoss of the unmodified reference (loss.py:204-311): single process (with / without
+    logit_bias) and the neighbour-exchange rings on 2 and 3 gloo ranks, uni- and bidirectional, with a
+    distinct upstream gradient per rank."""
+    sys.path.insert(0, REF)
+    from src.models.components.loss import SigLipLoss
+    from oracle.clip_oracle import synthetic_pair
+    rec = {}
+    for tag, n, d, scale, bias in (("train", 40, 64, 1.0, None), ("paper", 96, 128, 10.0, -10.0), ("odd", 25, 72, 3.0, 0.5)):
+        a, b = synthetic_pair(n, d, seed=2468, pair_id=0, rank=0, correlated=True, temperature_into_b=(tag == "train"), dtype="bf16")
+        A = a.double().requires_grad_(True)
+        B = b.double().requires_grad_(True)
+        loss = SigLipLoss(world_size=1)(A, B, scale, bias)
+        loss.backward()
+        rec.update({f"{tag}_A_bf16": bf16_bits(a), f"{tag}_B_bf16": bf16_bits(b), f"{tag}_scale": np.float64(scale),
+                    f"{tag}_bias": np.float64(0.0 if bias is None else bias), f"{tag}_has_bias": np.bool_(bias is not None),
+                    f"{tag}_loss": np.float64(loss.item()), f"{tag}_dA": A.grad.numpy().copy(), f"{tag}_dB": B.grad.numpy().copy()})
+        lb = SigLipLoss(world_size=1)(a.clone(), b.clone(), scale, bias)
+        rec[f"{tag}_loss_bf16"] = np.float64(lb.double().item())
+        rec[f"{tag}_loss_bf16_dtype"] = np.bytes_(str(lb.dtype))
+    np.savez_compressed(os.path.join(OUT, "siglip_single.npz"), **rec)
+    print("wrote siglip single", {k: float(v) for k, v in rec.items() if k.endswith("_loss")})
+    for world, bidir, port in ((2, True, 29631), (3, True, 29633), (3, False, 29635)):
+        n, d = 12, 32
+        mgr = mp.Manager()
+        results = mgr.dict()
+        mp.spawn(_siglip_worker, args=(world, port, n, d, bidir, results), nprocs=world, join=True)
+        flat = {"world": np.int64(world), "n": np.int64(n), "d": np.int64(d), "scale": np.float64(10.0), "bias": np.float64(-10.0),
+                "grad_outputs": np.array([1.0 + 0.5 * r for r in range(world)])}
+        for r in range(world):
+            for k, v in results[r].items():
+                flat[f"r{r}_{k}"] = v
+        np.savez_compressed(os.path.join(OUT, f"siglip_dist_w{world}_{'bidir' if bidir else 'ring'}.npz"), **flat)
+        print("wrote siglip dist", world, bidir, [float(flat[f"r{r}_loss"]) for r in range(world)])
+
+
 def head_cases():
     """BaseEncoder heads of the unmodified reference (base_encoder.py:129-194) in float64 on
     bf16-valued inputs and parameters: output + gradients w.r.t. the input and every parameter."""
@@ -192,8 +247,12 @@ def head_cases():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    if "--heads-only" not in sys.argv:
+    only = [a for a in sys.argv[1:] if a.startswith("--") and a.endswith("-only")]
+    if not only:
         single_process_cases()
         distributed_cases()
         epilogue_cases()
-    head_cases()
+    if not only or "--heads-only" in only:
+        head_cases()
+    if not only or "--siglip-only" in only:
+        siglip_cases()

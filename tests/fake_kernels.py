@@ -328,3 +328,30 @@ def scale_rows(x, y, scale_dev):
 def rowdot(x, y, out):
     CALLS.append("rowdot_dense")
     out.copy_((x.double() * y.double()).sum(-1).float())
+
+
+# ---- SigLIP (contracts of oneprot_siglip_* in include/oneprot_clip.h) ----
+def siglip_fwd(A, B_all, scale_dev, bias_dev, rowsum, scratch=None):
+    CALLS.append("siglip_fwd")
+    b = 0.0 if bias_dev is None else float(bias_dev[0])
+    x = LOG2E * (float(scale_dev[0]) * (A.double() @ B_all.double().T) + b)
+    rowsum.copy_((torch.clamp(x, min=0) + torch.log2(1 + torch.exp2(-x.abs()))).sum(1).float())
+    return scratch
+
+
+def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
+    CALLS.append("siglip_finalize")
+    b = 0.0 if bias_dev is None else float(bias_dev[0])
+    n = rowsum.numel()
+    loss_out[0] = float((math.log(2.0) * rowsum.double().sum() - (float(scale_dev[0]) * diag.double() + b).sum()) / n)
+
+
+def siglip_dz_panel(A_rows, B_all, grow0, scale_dev, bias_dev, wr, dg, Wz):
+    CALLS.append("siglip_dz_panel")
+    b = 0.0 if bias_dev is None else float(bias_dev[0])
+    rows, N = A_rows.shape[0], B_all.shape[0]
+    z = float(scale_dev[0]) * (A_rows.double() @ B_all.double().T) + b
+    Wd = torch.sigmoid(z) * wr.double()[:, None]
+    idx = torch.arange(rows)
+    Wd[idx, grow0 + idx] -= dg.double()
+    Wz[:rows, :N] = Wd.to(torch.bfloat16)

@@ -1,0 +1,53 @@
+"""CPU: bench.py prints exactly ONE well-formed JSON line - through the pipelined e2e leg and through its
+fallback - when its GPU arm is driven by stand-ins (tests/bench_cpu_harness.py), and the reference arm
+(`--impl reference`) does the same for real on the host cores."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+        "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"}
+
+
+def _json_lines(out):
+    return [json.loads(ln) for ln in out.splitlines() if ln.startswith("{")]
+
+
+@pytest.mark.parametrize("mode", ["fallback", "pipelined"])
+def test_gpu_arm_control_flow_prints_one_line(mode):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_cpu_harness.py"), mode], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = _json_lines(p.stdout)
+    assert len(lines) == 1, p.stdout
+    ln = lines[0]
+    assert KEYS <= set(ln), KEYS - set(ln)
+    assert ln["metric"] == "cliploss_fwd_bwd_samples_per_s" and ln["unit"] == "samples/s" and ln["n_gpus"] == 1
+    assert ln["steps"] == 3 and ln["warmup"] == 3 and ln["scaling"] == "strong" and ln["vs_baseline"] is None
+    assert "workload" in ln["config"] and ln["config"]["warmup_steps_run"] == 3
+    r = ln["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "tensor"
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(ln["cpu_baseline"]) and ln["cpu_baseline"]["kind"] == "port"
+    e = ln["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "mode", "serial_value"} <= set(e)
+    assert e["h2d_bytes_per_step"] == 2 * 256 * 64 * 2 and e["d2h_bytes_per_step"] == 4
+    if mode == "pipelined":
+        assert e["mode"].startswith("pipelined")
+    else:
+        assert e["mode"].startswith("serial") and "pipelined leg failed" in e["mode"]
+
+
+def test_reference_arm_prints_one_line():
+    env = dict(os.environ, ONEPROT_BENCH_N="512", ONEPROT_BENCH_D="64")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = _json_lines(p.stdout)
+    assert len(lines) == 1
+    ln = lines[0]
+    assert ln["impl"] == "reference" and ln["e2e"]["h2d_bytes_per_step"] == 0 and ln["cpu_baseline"]["kind"] == "port"
+    assert ln["e2e"]["value"] == ln["value"] == ln["cpu_baseline"]["value"]

@@ -447,8 +447,11 @@ def run_ours(args):
 
         step_e2e_pipelined()
         torch.cuda.synchronize()
-        if abs(float(host_loss) - loss_val) > 1e-3 * abs(loss_val):
-            raise RuntimeError(f"pipelined e2e loss {float(host_loss)} != device-resident loss {loss_val}")
+        # same inputs, deterministic kernels: the fp32 loss must equal the device-resident steps' loss
+        # (host_loss itself carries the loss in the features' dtype, bf16: ~3e-3 relative spacing)
+        got = float(loss_mod.last_loss_fp32.item())
+        if abs(got - loss_val) > 1e-5 * abs(loss_val) or abs(float(host_loss) - loss_val) > 1e-2 * abs(loss_val):
+            raise RuntimeError(f"pipelined e2e loss {got} (host copy {float(host_loss)}) != device-resident loss {loss_val}")
     except Exception as e:      # a rank that cannot pipeline makes every rank fall back (collectives stay matched)
         pipe_ok.zero_()
         pipe_err = repr(e)

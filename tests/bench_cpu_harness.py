@@ -92,6 +92,11 @@ if mode == "pipelined":
                                     "empty": staticmethod(lambda *a, device=None, **k: torch.empty(*a, **k))})
 
 import bench  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
-sys.argv = ["bench.py", "--gpus", "1", "--steps", "3", "--warmup", "3"]
+world = int(os.environ.get("WORLD_SIZE", 1))
+if world > 1:      # launched by torch.distributed.run: NCCL -> gloo
+    _init = dist.init_process_group
+    dist.init_process_group = lambda backend=None, device_id=None, **k: _init("gloo", **k)
+sys.argv = ["bench.py", "--gpus", str(world), "--steps", "3", "--warmup", "3"]
 bench.main()

@@ -41,6 +41,20 @@ def test_gpu_arm_control_flow_prints_one_line(mode):
         assert e["mode"].startswith("serial") and "pipelined leg failed" in e["mode"]
 
 
+def test_two_rank_control_flow_over_gloo():
+    """The driver's multi-GPU launch line with 2 ranks: rank 0 prints the one line, both exit 0."""
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29671", os.path.join(ROOT, "tests", "bench_cpu_harness.py"), "pipelined"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = _json_lines(p.stdout)
+    assert len(lines) == 1, p.stdout
+    ln = lines[0]
+    assert ln["n_gpus"] == 2 and ln["config"]["rows_per_gpu"] == 128 and ln["config"]["warmup_steps_run"] == 6 and ln["warmup"] == 3
+    assert "cpu_baseline" not in ln                      # rank 0 at N = 1 only
+    assert ln["e2e"]["mode"].startswith("pipelined") and ln["e2e"]["h2d_bytes_per_step"] == 2 * 128 * 64 * 2
+
+
 def test_reference_arm_prints_one_line():
     env = dict(os.environ, ONEPROT_BENCH_N="512", ONEPROT_BENCH_D="64")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],

@@ -119,8 +119,9 @@ int oneprot_clip_loss_finalize(const float* rowsum_all, const float* colsum_all,
  * common reference.  (1) oneprot_clip_rowcol_max: per-row maxima of the panel (complete) and
  * per-column maxima over this rank's rows (max them across ranks), in log2 units, same
  * tensor-core mainloop as the forward.  (2) oneprot_augment_bf16 appends 8 columns to an operand:
- * [x | e | 0..0] with e = bf16(-ref/c) or 1, so that a GEMM over d + 8 columns yields
- * x_ij - ref'_i with ref'_i = -c * float(e) (returned in ref_q).  The forward / dz / GEMM kernels
+ * [x | e_h | e_m | 0..0] with e_h + e_m = -ref/c in two bf16 limbs, or e_h = e_m = 1, so that a GEMM
+ * over d + 8 columns yields x_ij - ref'_i with ref'_i = -c * (float(e_h) + float(e_m)) (returned in
+ * ref_q; within 2^-17 |ref| of ref).  The forward / dz / GEMM kernels
  * then run unchanged on the augmented operands with G = 0 (stats = [*, *, 0, 1]), once per softmax
  * direction.  (3) oneprot_clip_loss_finalize_ex adds the per-element references back:
  * LSE_row_i = ln2 * (row_ref[i] + log2 rowsum_i). */

@@ -1072,10 +1072,12 @@ __global__ void reduce_slots_max_kernel(const float* __restrict__ part, int slot
   }
 }
 
-// Operand augmentation for the two-reference (robust) path: out = [in | e | 0 x 7] (row pitch d + 8)
-// with e = bf16(-ref[i] / c) (ref != nullptr) or 1.  The GEMM over d + 8 columns against an operand
-// augmented with 1 (resp. e) then yields x_ij - ref'_i, where ref'_i = -c * float(e) is returned in
-// ref_q: the reference actually applied, exact in fp32 although e is rounded to bf16.
+// Operand augmentation for the two-reference (robust) path: out = [in | e_h | e_m | 0 x 6] (row pitch
+// d + 8) with e_h + e_m = -ref[i] / c split into two bf16 limbs (ref != nullptr) or e_h = e_m = 1.  The
+// GEMM over d + 8 columns against an operand augmented with ones (resp. limbs) then yields
+// x_ij - ref'_i, where ref'_i = -c * (float(e_h) + float(e_m)) is returned in ref_q: the reference
+// actually applied, exact in fp32.  Two limbs keep ref' within 2^-17 |ref| of ref, so references of
+// 10^5 log2 units (unnormalised features times a large logit_scale) still leave every term <= 2^1.
 __global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, int d, const float* __restrict__ ref,
                                const float* __restrict__ scale, __nv_bfloat16* __restrict__ out, float* __restrict__ ref_q) {
   const int lane = threadIdx.x & 31;
@@ -1087,15 +1089,18 @@ __global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, i
     uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ld);
     for (int k = lane; k < d / 8; k += 32) dst[k] = src[k];
     if (lane == 0) {
-      __nv_bfloat16 e = __float2bfloat16_rn(1.f);
+      __nv_bfloat16 eh = __float2bfloat16_rn(1.f), em = __float2bfloat16_rn(1.f);
       if (ref) {
-        e = __float2bfloat16_rn(-ref[row] / c);
-        if (ref_q) ref_q[row] = -c * __bfloat162float(e);
+        const float t = -ref[row] / c;
+        eh = __float2bfloat16_rn(t);
+        em = __float2bfloat16_rn(t - __bfloat162float(eh));
+        if (ref_q) ref_q[row] = -c * (__bfloat162float(eh) + __bfloat162float(em));
       }
       __nv_bfloat16 tail[8];
-      tail[0] = e;
+      tail[0] = eh;
+      tail[1] = em;
 #pragma unroll
-      for (int u = 1; u < 8; ++u) tail[u] = __float2bfloat16_rn(0.f);
+      for (int u = 2; u < 8; ++u) tail[u] = __float2bfloat16_rn(0.f);
       dst[d / 8] = *reinterpret_cast<uint4*>(tail);
     }
   }

@@ -189,7 +189,7 @@ def rowcol_max(A, B_all, scale_dev, rowmax, colmax, scratch=None):
 
 
 def augment(x, ref, scale_dev, out, ref_q=None):
-    """out = [x | bf16(-ref/c) or 1 | 0 x 7]; ref_q = reference actually applied (see oneprot_augment_bf16)."""
+    """out = [x | e_h | e_m | 0 x 6] with e_h + e_m = -ref/c (two bf16 limbs) or 1, 1; ref_q = reference actually applied."""
     _need_cuda(x, ref, scale_dev, out, ref_q)
     _need(x, torch.bfloat16, "x"); _need(out, torch.bfloat16, "out")
     rows, d = x.shape

@@ -104,11 +104,15 @@ def augment(x, ref, scale_dev, out, ref_q=None):
     out[:, :d] = x
     if ref is None:
         out[:, d] = 1.0
+        out[:, d + 1] = 1.0
     else:
-        e = (-ref.double() / c).to(torch.bfloat16)
-        out[:, d] = e
+        t = (-ref.double() / c).float()
+        eh = t.to(torch.bfloat16)
+        em = (t - eh.float()).to(torch.bfloat16)
+        out[:, d] = eh
+        out[:, d + 1] = em
         if ref_q is not None:
-            ref_q.copy_((-c * e.double()).float())
+            ref_q.copy_((-c * (eh.float() + em.float())).float())
 
 
 def bwd_weights(inv_rowsum, inv_colsum, n, row_offset, mode, use_gsum, part, world, rank, gvec, scale_dev, wr, wc, dg,

@@ -273,12 +273,14 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
 }
 
 enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4,    // RCMAX: row/col maxima; RANK: retrieval ranks
-       EPI_SFWD = 5, EPI_SDZ = 6 };   // SigLIP: row sums of softplus(z) / dL/dZ panel sigma(z) wr_i - [i == j] dg_i
+       EPI_SFWD = 5, EPI_SDZ = 6,     // SigLIP: row sums of softplus(z) / dL/dZ panel sigma(z) wr_i - [i == j] dg_i
+       EPI_DZ_L2 = 7 };               // EPI_DZ with L2 hints: panel stores evict-first, operand loads evict-last (A/B experiment)
 
 template <int EPI>
 struct SCfg {
   static constexpr int NS = 4;                                             // operand ring depth
-  static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ);            // writes a bf16 dL/dZ panel by TMA stores
+  static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ || EPI == EPI_DZ_L2);   // writes a bf16 dL/dZ panel by TMA stores
+  static constexpr bool L2_HINTS = (EPI == EPI_DZ_L2);
   static constexpr int STAGING = PANEL ? STORE_STAGING_BYTES : 0;             // FWD / MAX / RCMAX / RANK / SFWD need none
   static constexpr int SMEM = smem_bytes(NS, STAGING);
 };
@@ -304,6 +306,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     reg_dealloc<56>();   // the 4 control warps hand registers to the 8 epilogue warps
     if (lane_id() == 0) {
       PipeState<NS> ps;
+      const uint64_t pol_keep = SCfg<EPI>::L2_HINTS ? l2_policy_evict_last() : 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
@@ -318,7 +321,14 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           for (int kb = 0; kb < p.nK; ++kb) {
             mbar_wait(&s.tail->empty[ps.stage], ps.phase ^ 1);
             uint8_t* sa = s.stages + ps.stage * STAGE_BYTES;
-            load_stage<0, 0>(sa, sa + A_STAGE_BYTES, &mapA, &mapB, &s.tail->full[ps.stage], ib * BM, jb * BN, kb * BK);
+            if (SCfg<EPI>::L2_HINTS) {
+              // operands are re-read by every CTA sweeping the same blocks: keep them in L2 against the streamed panel
+              mbar_arrive_expect_tx(&s.tail->full[ps.stage], STAGE_BYTES);
+              tma_load_2d_hint(sa, &mapA, &s.tail->full[ps.stage], kb * BK, ib * BM, pol_keep);
+              tma_load_2d_hint(sa + A_STAGE_BYTES, &mapB, &s.tail->full[ps.stage], kb * BK, jb * BN, pol_keep);
+            } else {
+              load_stage<0, 0>(sa, sa + A_STAGE_BYTES, &mapA, &mapB, &s.tail->full[ps.stage], ib * BM, jb * BN, kb * BK);
+            }
             ps.advance();
           }
         }
@@ -412,6 +422,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t colvec_s = smem_u32(&s.tail->colvec[0]);
     const uint32_t stage_s = smem_u32(s.staging) + h * 16384;
     const bool store_issuer = (q == 0) && (lane == 0);
+    const uint64_t pol_stream = SCfg<EPI>::L2_HINTS ? l2_policy_evict_first() : 0;   // the panel is written once, read once later
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
@@ -420,7 +431,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 128; ++k) colacc[k] = (EPI == EPI_RCMAX) ? -INFINITY : 0.f;
       }
-      if (EPI == EPI_DZ || EPI == EPI_RANK) {
+      if (EPI == EPI_DZ || EPI == EPI_DZ_L2 || EPI == EPI_RANK) {
         // stage the per-column weights of this item's 256 columns
         named_bar_sync(1, EPI_THREADS);
         const int t = threadIdx.x - EPI_WARP0 * 32;
@@ -579,7 +590,8 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               fence_proxy_async();            // generic-proxy smem writes -> visible to the TMA engine
               named_bar_sync(2 + h, 128);
               if (store_issuer) {
-                tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
+                if (SCfg<EPI>::L2_HINTS) tma_store_2d_hint(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM, pol_stream);
+                else tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
                 bulk_commit();
               }
             }
@@ -1844,9 +1856,15 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
   CUtensorMap mapW;   // store side: boxes {64 cols, 128 rows}; columns >= N and rows >= `rows` are clipped
   if ((rc = make_map(&mapW, Wz, N, rows, ldw, op::BM))) return rc;
   constexpr int smem = op::SCfg<op::EPI_DZ>::SMEM;
-  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
-  op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
+  static const bool l2_hints = getenv("ONEPROT_DZ_L2_HINTS") != nullptr;    // experiment knob
+  if (l2_hints) {
+    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ_L2>, smem))) return rc;
+    op::clip_s_kernel<op::EPI_DZ_L2><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
+  } else {
+    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
+    op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
+  }
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

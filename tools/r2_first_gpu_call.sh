@@ -7,12 +7,15 @@ set +e
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name"; timeout ${T:-420} "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -3 gpurun_out/$name.log; }
 run t_validated   python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_multirank.py -k "not _z"
-for f in z1_prefetch z2_sequencer z3_retrieval z4_robust z5_graph z6_heads z7_siglip; do
+for f in z1_prefetch z2_sequencer z3_retrieval z4_robust z5_graph z6_heads z7_siglip z8_dz_l2_hints; do
   run t_$f python -m pytest tests/test_gpu_$f.py -q -m gpu
 done
 run smoke         python __graft_entry__.py --smoke
 run bench_default python bench.py --steps 10 --warmup 3
 ONEPROT_SEQ=1 run bench_seq python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run dz_default    python tools/run_kernel.py dz 16384 32768 1024 10
+ONEPROT_DZ_L2_HINTS=1 run dz_l2_hints python tools/run_kernel.py dz 16384 32768 1024 10
+ONEPROT_DZ_L2_HINTS=1 run bench_dz_l2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run host_1024     python tools/host_overhead.py 1024
 run host_4096     python tools/host_overhead.py 4096
 run eager_bar     python tests/perf_eager_bar.py --sizes 8192,32768 --reps 5

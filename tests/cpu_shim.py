@@ -1,4 +1,4 @@
-"""Optional CPU shim for the GPU test files (ONEPROT_CPU_SHIM=1 python -m pytest tests/test_gpu_z6_heads.py -m gpu ...).
+"""Optional CPU shim for the GPU test files (ONEPROT_CPU_SHIM=1 python -m pytest tests/test_gpu_z3_heads.py -m gpu ...).
 
 Purpose: shake Python-level mistakes (shapes, argument order, API misuse, impossible tolerances)
 out of GPU tests BEFORE they cost GPU minutes.  Every "cuda" device becomes the CPU, streams /

@@ -82,5 +82,8 @@ def install():
     torch.cuda.Event = _Event
     torch.cuda.stream = lambda s: contextlib.nullcontext()
     torch.cuda.device_count = lambda: 1
+    torch.cuda.max_memory_allocated = lambda *a, **k: 0
+    torch.cuda.reset_peak_memory_stats = lambda *a, **k: None
+    torch.cuda.empty_cache = lambda: None
     for mod in (clip_loss, epilogue, heads, retrieval):
         mod._KERNELS = fake_kernels

@@ -199,6 +199,50 @@ def siglip_cases():
         print("wrote siglip dist", world, bidir, [float(flat[f"r{r}_loss"]) for r in range(world)])
 
 
+def retrieval_cases():
+    """RetrievalMetric.update / compute of the unmodified reference (retrieval_metric.py:71-102).
+    torchmetrics is not installed in the build container, so its ``Metric`` base class and helpers are
+    replaced by minimal stand-ins that only keep the list states (``add_state`` / ``dim_zero_cat``) -
+    the arithmetic under test (similarity, argsort, rank of the label, median, R@k) is the reference's."""
+    import types
+    if "torchmetrics" not in sys.modules:
+        class Metric:
+            def __init__(self, **kwargs):
+                pass
+
+            def add_state(self, name, default, dist_reduce_fx=None):
+                setattr(self, name, list(default))
+        tm = types.ModuleType("torchmetrics")
+        mods = {"torchmetrics": tm, "torchmetrics.metric": types.ModuleType("torchmetrics.metric"),
+                "torchmetrics.utilities": types.ModuleType("torchmetrics.utilities"),
+                "torchmetrics.utilities.data": types.ModuleType("torchmetrics.utilities.data"),
+                "torchmetrics.utilities.imports": types.ModuleType("torchmetrics.utilities.imports"),
+                "torchmetrics.utilities.plot": types.ModuleType("torchmetrics.utilities.plot")}
+        mods["torchmetrics.metric"].Metric = Metric
+        mods["torchmetrics.utilities"].rank_zero_warn = lambda *a, **k: None
+        mods["torchmetrics.utilities.data"].dim_zero_cat = lambda x: torch.cat(list(x), dim=0) if isinstance(x, (list, tuple)) else x
+        mods["torchmetrics.utilities.imports"]._MATPLOTLIB_AVAILABLE = False
+        mods["torchmetrics.utilities.plot"]._AX_TYPE = object
+        mods["torchmetrics.utilities.plot"]._PLOT_OUT_TYPE = object
+        sys.modules.update(mods)
+    sys.path.insert(0, REF)
+    from src.models.components.retrieval_metric import RetrievalMetric
+    rec = {}
+    g = torch.Generator().manual_seed(99)
+    for tag, n, d, noise in (("easy", 300, 64, 0.5), ("hard", 257, 32, 2.5)):
+        S = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1).to(torch.bfloat16)
+        M = torch.nn.functional.normalize(S.float() + noise * torch.randn(n, d, generator=g), dim=-1).to(torch.bfloat16)
+        m = RetrievalMetric()
+        for lo in range(0, n, 100):                      # several update() calls, as the validation loop does
+            m.update(S[lo:lo + 100].double(), M[lo:lo + 100].double())
+        out = m.compute()
+        rec[f"{tag}_S_bf16"], rec[f"{tag}_M_bf16"] = bf16_bits(S), bf16_bits(M)
+        for k, v in out.items():
+            rec[f"{tag}:{k}"] = np.float64(v)
+    np.savez_compressed(os.path.join(OUT, "retrieval_metric.npz"), **rec)
+    print("wrote retrieval", {k: float(v) for k, v in rec.items() if ":" in k})
+
+
 def head_cases():
     """BaseEncoder heads of the unmodified reference (base_encoder.py:129-194) in float64 on
     bf16-valued inputs and parameters: output + gradients w.r.t. the input and every parameter."""
@@ -256,3 +300,5 @@ if __name__ == "__main__":
         head_cases()
     if not only or "--siglip-only" in only:
         siglip_cases()
+    if not only or "--retrieval-only" in only:
+        retrieval_cases()

@@ -37,3 +37,21 @@ def test_retrieval_metric_rank_count_kernel():
             # near-ties resolve differently in bf16 products: allow one rank of slack in the median, 1 % in R@k
             tol = 1.0 if "median" in k else 0.01
             assert abs(float(got[k]) - float(want[k])) <= tol, (k, got[k], want[k])
+
+
+def test_retrieval_metric_vs_reference_golden():
+    """Against the reference's own RetrievalMetric output (tests/golden/retrieval_metric.npz)."""
+    from oneprot_b200 import RetrievalMetric
+    from tests.helpers import bf16_from_bits, load_golden
+    g = load_golden("retrieval_metric.npz")
+    for tag in ("easy", "hard"):
+        S, M = bf16_from_bits(g[f"{tag}_S_bf16"]), bf16_from_bits(g[f"{tag}_M_bf16"])
+        m = RetrievalMetric()
+        for lo in range(0, S.shape[0], 100):
+            m.update(S[lo:lo + 100].cuda(), M[lo:lo + 100].cuda())
+        got = m.compute()
+        for k, v in g.items():
+            if k.startswith(tag + ":"):
+                name = k.split(":", 1)[1]
+                tol = 1.0 if "median" in name else 0.01      # fp32-accumulated bf16 products: near-ties may swap
+                assert abs(float(got[name]) - float(v)) <= tol, (tag, name, got[name], float(v))

@@ -234,3 +234,19 @@ def test_retrieval_metric_matches_reference_restatement(monkeypatch):
         assert abs(float(got[k]) - float(want[k])) < 1e-9, k
     m.reset()
     assert len(m.preds) == 0 and len(m.target) == 0
+
+
+def test_retrieval_metric_host_logic_vs_reference_golden(monkeypatch):
+    from oneprot_b200 import clip_loss, retrieval
+    monkeypatch.setattr(clip_loss, "_KERNELS", fake_kernels)
+    monkeypatch.setattr(retrieval, "_KERNELS", fake_kernels)
+    g = load_golden("retrieval_metric.npz")
+    for tag in ("easy", "hard"):
+        S, M = bf16_from_bits(g[f"{tag}_S_bf16"]), bf16_from_bits(g[f"{tag}_M_bf16"])
+        m = retrieval.RetrievalMetric()
+        for lo in range(0, S.shape[0], 100):
+            m.update(S[lo:lo + 100], M[lo:lo + 100])
+        got = m.compute()
+        for k, v in g.items():
+            if k.startswith(tag + ":"):
+                assert float(got[k.split(":", 1)[1]]) == float(v), (tag, k)

@@ -99,3 +99,17 @@ def test_panel_port_is_the_row_restriction_of_the_port():
     got = oc.clip_loss_port_panel(a, b, 16, 1.0)
     assert abs(got.item() - want.item()) < 1e-6
     assert abs(oc.clip_loss_port_panel(a, b, 64, 1.0).item() - oc.clip_loss_port(a, b, 1.0).item()) < 1e-6
+
+
+def test_retrieval_metric_oracle_matches_reference_golden():
+    """retrieval_metric_closed_form against the reference's RetrievalMetric (retrieval_metric.py:71-102;
+    torchmetrics' Metric base replaced by a list-state stand-in when the fixture was generated)."""
+    g = load_golden("retrieval_metric.npz")
+    for tag in ("easy", "hard"):
+        S = bf16_from_bits(g[f"{tag}_S_bf16"]).double().numpy()
+        M = bf16_from_bits(g[f"{tag}_M_bf16"]).double().numpy()
+        got = oc.retrieval_metric_closed_form(S, M)
+        want = {k.split(":", 1)[1]: float(v) for k, v in g.items() if k.startswith(tag + ":")}
+        assert set(got) == set(want)
+        for k in want:
+            assert float(got[k]) == want[k], (tag, k)

@@ -528,16 +528,20 @@ class ClipLoss(nn.Module):
                    ONEPROT_SEQ=1) instead of kernel by kernel from Python.
       graph        replay the forward / backward launch sequences as CUDA graphs (world_size == 1);
                    removes the ~0.4 ms of host enqueue per step that dominates at OneProt's batch sizes.
-      robust       "off" (default): one common reference, validated window, device flag;
+      robust       "off": one common reference, validated window, device flag;
                    "always": per-row / per-column references for arbitrary inputs (2.25x the work);
                    "auto": run the normal path, read the device flag (one host sync per forward)
                    and fall back to the two-reference path only when it is raised.
+                   Default (None): "off" while gradients are enabled (training: no host sync), "auto"
+                   under torch.no_grad() - the reference's test_step scales the already scaled modality
+                   features a second time (oneprot_module.py:142), which spreads the logits
+                   over +-200 nats, beyond what one common reference can hold in fp32.
     """
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
                  panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
-                 robust: str = "off", graph: bool = False):
+                 robust: Optional[str] = None, graph: bool = False):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -549,8 +553,8 @@ class ClipLoss(nn.Module):
         self.panel_bytes = int(panel_bytes)
         self.group = group
         self.host_sequencer = bool(host_sequencer)
-        if robust not in ("off", "auto", "always"):
-            raise ValueError("robust must be 'off', 'auto' or 'always'")
+        if robust not in (None, "off", "auto", "always"):
+            raise ValueError("robust must be None, 'off', 'auto' or 'always'")
         self.robust = robust
         if graph and (world_size != 1 or robust == "auto"):
             raise ValueError("graph=True needs world_size == 1 and a robust mode that is decided on the host side up front")
@@ -626,7 +630,11 @@ class ClipLoss(nn.Module):
             scale_t = _float_scale_on(A.device, logit_scale)   # cached: no host-to-device copy per call
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
-                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer, robust=self.robust)
+                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer)
+        if self.robust is None:     # training: never sync; evaluation: fall back to the two-reference path when flagged
+            cfg["robust"] = "off" if (torch.is_grad_enabled() or self.graph) else "auto"
+        else:
+            cfg["robust"] = self.robust
         if self.graph and A.is_cuda:
             from .graphed import GraphedClipFunction, GraphedStep
             needs = (bool(A.requires_grad and torch.is_grad_enabled()), bool(B.requires_grad and torch.is_grad_enabled()))

@@ -199,32 +199,178 @@ def siglip_cases():
         print("wrote siglip dist", world, bidir, [float(flat[f"r{r}_loss"]) for r in range(world)])
 
 
+def _stub_torchmetrics():
+    """Minimal stand-ins for the parts of torchmetrics the reference imports (not installed here): list
+    states for Metric, running mean / min for MeanMetric / MinMetric.  No arithmetic of the path."""
+    import types
+    if "torchmetrics" in sys.modules:
+        return
+
+    class Metric:
+        def __init__(self, **kwargs):
+            self._defaults = {}
+
+        def add_state(self, name, default, dist_reduce_fx=None):
+            self._defaults[name] = default
+            setattr(self, name, list(default))
+
+        def reset(self):
+            for k, v in self._defaults.items():
+                setattr(self, k, list(v))
+
+    class MeanMetric:
+        def __init__(self):
+            self.reset()
+
+        def reset(self):
+            self.total, self.count = 0.0, 0
+
+        def __call__(self, v):
+            self.total += float(v)
+            self.count += 1
+
+        def compute(self):
+            return torch.tensor(self.total / max(self.count, 1))
+
+    class MinMetric(MeanMetric):
+        def reset(self):
+            self.best = float("inf")
+
+        def __call__(self, v):
+            self.best = min(self.best, float(v))
+
+        def compute(self):
+            return torch.tensor(self.best)
+
+    tm = types.ModuleType("torchmetrics")
+    tm.MeanMetric, tm.MinMetric = MeanMetric, MinMetric
+    mods = {"torchmetrics": tm, "torchmetrics.metric": types.ModuleType("torchmetrics.metric"),
+            "torchmetrics.utilities": types.ModuleType("torchmetrics.utilities"),
+            "torchmetrics.utilities.data": types.ModuleType("torchmetrics.utilities.data"),
+            "torchmetrics.utilities.imports": types.ModuleType("torchmetrics.utilities.imports"),
+            "torchmetrics.utilities.plot": types.ModuleType("torchmetrics.utilities.plot")}
+    mods["torchmetrics.metric"].Metric = Metric
+    mods["torchmetrics.utilities"].rank_zero_warn = lambda *a, **k: None
+    mods["torchmetrics.utilities.data"].dim_zero_cat = lambda x: torch.cat(list(x), dim=0) if isinstance(x, (list, tuple)) else x
+    mods["torchmetrics.utilities.imports"]._MATPLOTLIB_AVAILABLE = False
+    mods["torchmetrics.utilities.plot"]._AX_TYPE = object
+    mods["torchmetrics.utilities.plot"]._PLOT_OUT_TYPE = object
+    sys.modules.update(mods)
+
+
+def _stub_lightning():
+    """pytorch_lightning is not installed here: a LightningModule stand-in with exactly the plumbing
+    OneProtLitModule uses in manual-optimisation mode (oneprot_module.py:22-24,82,105-108):
+    save_hyperparameters, optimizers(), manual_backward, clip_gradients (norm), log, global_step."""
+    import inspect
+    import types
+    if "pytorch_lightning" in sys.modules:
+        return
+
+    class LightningModule(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._opt, self.global_step, self.logged = None, 0, {}
+
+        def save_hyperparameters(self, logger=False):
+            loc = inspect.currentframe().f_back.f_locals
+            self.hparams = types.SimpleNamespace(**{k: v for k, v in loc.items() if k not in ("self", "__class__")})
+
+        def optimizers(self):
+            if self._opt is None:
+                cfg = self.configure_optimizers()
+                self._opt = cfg["optimizer"] if isinstance(cfg, dict) else cfg
+            return self._opt
+
+        def manual_backward(self, loss):
+            loss.backward()
+
+        def clip_gradients(self, opt, gradient_clip_val=None, gradient_clip_algorithm=None):
+            assert gradient_clip_algorithm == "norm"
+            params = [p for grp in opt.param_groups for p in grp["params"]]
+            torch.nn.utils.clip_grad_norm_(params, gradient_clip_val)
+
+        def log(self, name, value, **kw):
+            self.logged[name] = value
+    pl = types.ModuleType("pytorch_lightning")
+    pl.LightningModule = LightningModule
+    sys.modules["pytorch_lightning"] = pl
+
+
+def module_cases():
+    """The reference's OWN OneProtLitModule (oneprot_module.py) - training_step with the L1 term,
+    validation_step with RetrievalMetric, test_step with the tensor logit_scale - over the reference's
+    BaseEncoder heads, in float64, world_size 1.  Lightning / torchmetrics plumbing is stubbed (above);
+    ClipLoss, BaseEncoder, RetrievalMetric and the step logic are the unmodified reference."""
+    import functools
+    _stub_torchmetrics()
+    _stub_lightning()
+    os.environ["RANK"], os.environ["WORLD_SIZE"] = "0", "1"
+    sys.path.insert(0, REF)
+    from src.models.components.base_encoder import BaseEncoder
+    from src.models.oneprot_module import OneProtLitModule
+    g = torch.Generator().manual_seed(4242)
+    spec = {"sequence": (64, "mlp", False, "mean"), "text": (48, "mlp", True, "cls"), "struct_graph": (56, "linear", True, "mean")}
+    comps = {k: BaseEncoder(dm, 32, proj_type=pt, use_logit_scale=uls, learnable_logit_scale=False, pooling_type=pool).double()
+             for k, (dm, pt, uls, pool) in spec.items()}
+    with torch.no_grad():
+        for enc in comps.values():
+            for p in enc.parameters():
+                p.copy_((p + 0.2 * torch.randn(p.shape, generator=g).double()).to(torch.bfloat16).double())
+    module = OneProtLitModule(comps, optimizer=functools.partial(torch.optim.SGD, lr=0.02, momentum=0.9), loss_fn="CLIP",
+                              use_l1_regularization=True, local_loss=True, gather_with_grad=True)
+    rec = {"spec": np.bytes_(repr(spec)), "lr": np.float64(0.02), "momentum": np.float64(0.9)}
+    for k, v in module.network.state_dict().items():
+        rec["init:" + k] = v.numpy().copy()
+    B, L, steps = 12, 5, 4
+
+    def make_batch(tag):
+        b = {}
+        for mod in ("text", "struct_graph"):
+            seq = torch.randn(B, L, 64, generator=g).to(torch.bfloat16)
+            x = torch.randn((B, L, 48) if mod == "text" else (B, 56), generator=g).to(torch.bfloat16)
+            x = x + 0.5 * seq.float().mean(1)[:, :x.shape[-1]].reshape((B, 1, -1) if x.dim() == 3 else (B, -1)).to(torch.bfloat16)
+            rec[f"{tag}:{mod}:seq_bf16"], rec[f"{tag}:{mod}:mod_bf16"] = bf16_bits(seq), bf16_bits(x)
+            rec[f"{tag}:{mod}:seq_shape"], rec[f"{tag}:{mod}:mod_shape"] = np.array(seq.shape), np.array(x.shape)
+            b[mod] = (seq.double(), x.double(), None, None)
+        return b
+
+    # the reference's training_step only logs the running mean: capture each call's loss value
+    losses = []
+    orig = module.train_loss.__call__
+    module.train_loss = type("Tap", (), {"__call__": lambda self, v: losses.append(float(v)), "reset": lambda self: None})()
+    for s in range(steps):
+        module.training_step(make_batch(f"train{s}"))
+        module.global_step += 1
+    rec["train_losses"] = np.array(losses)                       # order: step-major, (text, struct_graph)
+    for k, v in module.network.state_dict().items():
+        rec["final:" + k] = v.numpy().copy()
+    vb = make_batch("val")
+    vals = []
+    module.val_loss = type("Tap", (), {"__call__": lambda self, v: vals.append(float(v)), "reset": lambda self: None})()
+    with torch.no_grad():
+        for mod in ("text", "struct_graph"):
+            seq, x, _, _ = vb[mod]
+            module.validation_step((seq, x, mod, None), 0)
+    rec["val_losses"] = np.array(vals)
+    for mod in ("text", "struct_graph"):
+        for k, v in module.metrics["val_" + mod].compute().items():
+            rec[f"valmetric:{mod}:{k}"] = np.float64(v)
+    tests = []
+    module.test_loss = type("Tap", (), {"__call__": lambda self, v: tests.append(float(v)), "reset": lambda self: None})()
+    with torch.no_grad():
+        module.test_step(vb, 0)
+    rec["test_losses"] = np.array(tests)
+    np.savez_compressed(os.path.join(OUT, "module_steps.npz"), **rec)
+    print("wrote module", losses, vals, tests)
+
+
 def retrieval_cases():
     """RetrievalMetric.update / compute of the unmodified reference (retrieval_metric.py:71-102).
     torchmetrics is not installed in the build container, so its ``Metric`` base class and helpers are
     replaced by minimal stand-ins that only keep the list states (``add_state`` / ``dim_zero_cat``) -
     the arithmetic under test (similarity, argsort, rank of the label, median, R@k) is the reference's."""
-    import types
-    if "torchmetrics" not in sys.modules:
-        class Metric:
-            def __init__(self, **kwargs):
-                pass
-
-            def add_state(self, name, default, dist_reduce_fx=None):
-                setattr(self, name, list(default))
-        tm = types.ModuleType("torchmetrics")
-        mods = {"torchmetrics": tm, "torchmetrics.metric": types.ModuleType("torchmetrics.metric"),
-                "torchmetrics.utilities": types.ModuleType("torchmetrics.utilities"),
-                "torchmetrics.utilities.data": types.ModuleType("torchmetrics.utilities.data"),
-                "torchmetrics.utilities.imports": types.ModuleType("torchmetrics.utilities.imports"),
-                "torchmetrics.utilities.plot": types.ModuleType("torchmetrics.utilities.plot")}
-        mods["torchmetrics.metric"].Metric = Metric
-        mods["torchmetrics.utilities"].rank_zero_warn = lambda *a, **k: None
-        mods["torchmetrics.utilities.data"].dim_zero_cat = lambda x: torch.cat(list(x), dim=0) if isinstance(x, (list, tuple)) else x
-        mods["torchmetrics.utilities.imports"]._MATPLOTLIB_AVAILABLE = False
-        mods["torchmetrics.utilities.plot"]._AX_TYPE = object
-        mods["torchmetrics.utilities.plot"]._PLOT_OUT_TYPE = object
-        sys.modules.update(mods)
+    _stub_torchmetrics()
     sys.path.insert(0, REF)
     from src.models.components.retrieval_metric import RetrievalMetric
     rec = {}
@@ -302,3 +448,5 @@ if __name__ == "__main__":
         siglip_cases()
     if not only or "--retrieval-only" in only:
         retrieval_cases()
+    if not only or "--module-only" in only:
+        module_cases()

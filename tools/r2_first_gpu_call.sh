@@ -7,7 +7,7 @@ set +e
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name"; timeout ${T:-420} "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -3 gpurun_out/$name.log; }
 run t_validated   python -m pytest tests -q -m gpu -x --deselect tests/test_gpu_multirank.py -k "not _z"
-for f in z1_prefetch z2_sequencer z3_heads z4_siglip z5_dz_l2_hints z6_retrieval z7_robust z8_graph; do
+for f in z1_prefetch z2_sequencer z3_heads z4_siglip z5_dz_l2_hints z6_retrieval z7_robust z8_graph z9_module_replica; do
   run t_$f python -m pytest tests/test_gpu_$f.py -q -m gpu
 done
 run smoke         python __graft_entry__.py --smoke

@@ -235,8 +235,9 @@ def test_sequencer_is_not_used_outside_its_scope(streams):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (8, 5)])
 @pytest.mark.parametrize("local_loss,gwg", [(False, True), (False, False), (True, True)])
-@pytest.mark.parametrize("n,panel_rows", [(512, None), (1024, 384)])
-def test_nvls_sequence_equals_python_path(streams, world, rank, local_loss, gwg, n, panel_rows):
+@pytest.mark.parametrize("n,panel_rows,need", [(512, None, (True, True)), (1024, 384, (True, True)), (1024, 384, (False, True)),
+                                               (512, None, (True, False))])
+def test_nvls_sequence_equals_python_path(streams, world, rank, local_loss, gwg, n, panel_rows, need):
     d = 64
     A, B, scale = _pair(n, d)
     N = world * n
@@ -245,7 +246,7 @@ def test_nvls_sequence_equals_python_path(streams, world, rank, local_loss, gwg,
     traces = []
     for seq in (False, True):
         comm = FakeNvlsComm(world, rank, streams)
-        lines, reg = _run(streams, A, B, scale, _cfg(world, rank, local_loss, gwg, pb, seq), comm)
+        lines, reg = _run(streams, A, B, scale, _cfg(world, rank, local_loss, gwg, pb, seq), comm, need)
         traces.append((lines, reg + _sym_regions(comm), comm))
     (py, rpy, _), (cs, rcs, comm) = traces
     cpy, ccs = _canon(py, rpy), _canon(cs, rcs)

@@ -2,7 +2,7 @@
 # First gpurun call of the next round: everything that was built after round 1's GPU budget was
 # spent, in one box visit (1 GPU).  Each step writes its own log under gpurun_out/ and never stops the
 # script, so that one failure does not hide the rest.
-#     gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_call.sh'
+#     gpurun --timeout 2400 -- 'bash tools/r2_first_gpu_call.sh'
 set +e
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name"; timeout ${T:-420} "$@" > gpurun_out/$name.log 2>&1; echo "exit $? ($name)"; tail -3 gpurun_out/$name.log; }

@@ -387,7 +387,9 @@ def run_ours(args):
                                    f"gather_with_grad=True, {GLOBAL_N // world} rows per GPU",
                        "global_batch": GLOBAL_N, "dim": DIM, "rows_per_gpu": n, "warmup_steps_run": warmup,
                        "l2": "256 MiB buffer written between timed steps (L2 flush); inputs 128 MiB",
-                       "loss": loss_val, "ms_steps_rank0": ms_steps_rank0},
+                       "loss": loss_val, "ms_steps_rank0": ms_steps_rank0,
+                       "host": "C step sequencer (ONEPROT_SEQ=1)" if os.environ.get("ONEPROT_SEQ") == "1" else "python",
+                       "knobs": {k: v for k, v in os.environ.items() if k.startswith("ONEPROT_") and k not in ("ONEPROT_BENCH_N", "ONEPROT_BENCH_D")}},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": dk["tflops"], "peak": peaks["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": dk["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
                          "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",

@@ -31,7 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import kernels as _cuda_kernels
-from .epilogue import LearnableLogitScaling, Normalize
+from .epilogue import LearnableLogitScaling, Normalize, _NormScaleFn
 
 _KERNELS = _cuda_kernels
 
@@ -366,6 +366,20 @@ class _IdentityPooling(nn.Identity):
         return features
 
 
+class _NormSequential(nn.Sequential):
+    """The reference's ``norm`` Sequential (base_encoder.py:171-178) with the same children and
+    state_dict keys (``norm.1.log_logit_scale``).  [Normalize(dim=-1), LearnableLogitScaling] run as ONE
+    fused kernel (one read and one write of the embedding instead of two of each); anything else runs
+    child by child.  Encoders that call ``self.norm(projected)`` themselves (sequence_encoder.py:81) get
+    the fusion as well."""
+
+    def forward(self, x):
+        if (len(self) == 2 and isinstance(self[0], Normalize) and isinstance(self[1], LearnableLogitScaling)
+                and self[0].dim in (-1, x.dim() - 1)):
+            return _NormScaleFn.apply(x, self[1].effective_scale(), 1e-12)
+        return super().forward(x)
+
+
 # ---------------------------------------------------------------------------------------------
 # BaseEncoder head
 # ---------------------------------------------------------------------------------------------
@@ -400,7 +414,7 @@ class BaseEncoder(nn.Module):
         layers = [Normalize(dim=-1)]
         if use_logit_scale:
             layers.append(LearnableLogitScaling(learnable=bool(learnable_logit_scale)))
-        return nn.Sequential(*layers)
+        return _NormSequential(*layers)
 
     def _create_pooling(self, pooling_type, hidden_size=1280):
         if pooling_type == 'mean':

@@ -178,3 +178,19 @@ def test_sequence_head_at_oneprot_sizes_vs_torch_modules(dtype):
     for i in (0, 1, 3, 4):
         for pn, p in ref[i].named_parameters():
             assert cosine(getattr(enc.proj[i], pn).grad.double().cpu().numpy(), p.grad.cpu().numpy()) >= cmin, (i, pn)
+
+
+def test_fused_normalize_and_scale_matches_the_two_reference_modules():
+    from oneprot_b200 import NormalizeAndScale
+    from tests.helpers import bf16_from_bits, load_golden
+    g = load_golden("epilogue_normalize_scale.npz")
+    x = bf16_from_bits(g["x_bf16"]).cuda().float().requires_grad_(True)
+    gy = bf16_from_bits(g["gy_bf16"]).cuda().float()
+    m = NormalizeAndScale(logit_scale_init=1 / 0.07, learnable=True).cuda()
+    y = m(x)
+    assert np.allclose(y.detach().cpu().numpy(), g["ys_f32"], rtol=1e-5, atol=1e-6)
+    y.backward(gy)
+    s = float(np.exp(g["log_logit_scale"]))
+    assert np.allclose(x.grad.cpu().numpy(), s * g["gx_f64"], rtol=1e-4, atol=1e-5)
+    want_dlog = s * float((gy.double().cpu().numpy() * g["y_f64"]).sum())
+    assert abs(float(m.scaling.log_logit_scale.grad) - want_dlog) < 1e-3 * abs(want_dlog) + 1e-5

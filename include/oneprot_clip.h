@@ -274,7 +274,8 @@ int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int
 
 /* torch.nn.LayerNorm over the last dim (base_encoder.py:148,154,157): y = (x - mean) * rstd * gamma + beta
  * with the biased variance and eps inside the root; mean / rstd (fp32, one per row) are saved for
- * the backward.  d: multiple of 8, at most 2048. */
+ * the backward.  d: multiple of 8 (rows of up to 2048 elements stay in registers; longer rows -
+ * ESM-2 3B / 15B: 2560 / 5120 - are re-read from L1 / L2). */
 int oneprot_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int d,
                           int is_fp32, float eps, void* stream);
 /* gx = rstd * (g - mean(g) - xhat * mean(g * xhat)) with g = gy * gamma (gx may be NULL);

@@ -156,6 +156,82 @@ __global__ void layernorm_bwd_rows_kernel(const void* __restrict__ x, const void
   }
 }
 
+// ---- rows longer than 2048 elements (ESM-2 3B / 15B: 2560 / 5120): same math, the row is re-read from
+// L1 / L2 instead of being held in registers (two extra passes forward, one backward)
+template <bool FP32>
+__global__ void layernorm_fwd_long_kernel(const void* __restrict__ x, const void* __restrict__ gamma, const void* __restrict__ beta,
+                                          void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows, int d,
+                                          float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    float s = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float f[8];
+      load8<FP32>(x, base + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += f[u];
+    }
+    const float mu = warp_sum(s) * inv_d;
+    float q = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float f[8];
+      load8<FP32>(x, base + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const float t = f[u] - mu; q = fmaf(t, t, q); }
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    for (int k = lane * 8; k < d; k += 256) {
+      float f[8], g[8], b[8], o[8];
+      load8<FP32>(x, base + k, f);
+      load8<FP32>(gamma, k, g);
+      load8<FP32>(beta, k, b);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = fmaf((f[u] - mu) * rs, g[u], b[u]);
+      store8<FP32>(y, base + k, o);
+    }
+  }
+}
+
+template <bool FP32>
+__global__ void layernorm_bwd_rows_long_kernel(const void* __restrict__ x, const void* __restrict__ gy, const void* __restrict__ gamma,
+                                               const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ gx,
+                                               int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float inv_d = 1.f / static_cast<float>(d);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fg[8], gm[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(gy, base + k, fg);
+      load8<FP32>(gamma, k, gm);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float g = fg[u] * gm[u];
+        s1 += g;
+        s2 = fmaf(g, (fx[u] - mu) * rs, s2);
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fg[8], gm[8], o[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(gy, base + k, fg);
+      load8<FP32>(gamma, k, gm);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = rs * (fg[u] * gm[u] - c1 - (fx[u] - mu) * rs * c2);
+      store8<FP32>(gx, base + k, o);
+    }
+  }
+}
+
 // ---- LayerNorm backward, column part: partial d gamma = sum_rows gy * xhat, d beta = sum_rows gy.
 // grid (ceil(d / 256), row chunks); block = 8 warps x (32 lanes x 8 columns); slot = blockIdx.y.
 template <bool FP32>
@@ -415,15 +491,17 @@ extern "C" {
 int oneprot_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int d,
                           int is_fp32, float eps, void* stream) {
   if (!x || !gamma || !beta || !y || !mean || !rstd) return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: null pointer");
-  if (rows <= 0 || d <= 0 || d % 8 || d > 256 * oph::LN_MAXC)
-    return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: need d a positive multiple of 8, at most 2048");
+  if (rows <= 0 || d <= 0 || d % 8) return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: need d a positive multiple of 8");
   if (!al16(x) || !al16(gamma) || !al16(beta) || !al16(y)) return opint::fail(ONEPROT_ERR_ARG, "layernorm_fwd: pointers must be 16-byte aligned");
   if (optrace::recording()) optrace::add("layernorm_fwd x=%p gamma=%p beta=%p y=%p mean=%p rstd=%p rows=%d d=%d fp32=%d st=%p", x, gamma, beta, y, (void*)mean, (void*)rstd, rows, d, is_fp32, stream);
   opint::count_launch(1);
   if (optrace::dry()) return ONEPROT_OK;
   const int blocks = std::min(cdiv(rows, 8), oneprot_num_sms() * 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_fp32) oph::layernorm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  if (d > 256 * oph::LN_MAXC) {       // row does not fit the register-resident kernel
+    if (is_fp32) oph::layernorm_fwd_long_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+    else oph::layernorm_fwd_long_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  } else if (is_fp32) oph::layernorm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
   else oph::layernorm_fwd_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
   HD_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -439,8 +517,7 @@ int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, cons
                           float* dgamma, float* dbeta, void* scratch, size_t scratch_bytes, int rows, int d, int is_fp32,
                           void* stream) {
   if (!x || !gy || !gamma || !mean || !rstd) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: null pointer");
-  if (rows <= 0 || d <= 0 || d % 8 || d > 256 * oph::LN_MAXC)
-    return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: need d a positive multiple of 8, at most 2048");
+  if (rows <= 0 || d <= 0 || d % 8) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: need d a positive multiple of 8");
   if ((dgamma != nullptr) != (dbeta != nullptr)) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: dgamma and dbeta go together");
   if (!gx && !dgamma) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: nothing to compute");
   if (dgamma && (!scratch || scratch_bytes < oneprot_layernorm_bwd_scratch_bytes(rows, d)))
@@ -452,7 +529,10 @@ int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (gx) {
     const int blocks = std::min(cdiv(rows, 8), oneprot_num_sms() * 8);
-    if (is_fp32) oph::layernorm_bwd_rows_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+    if (d > 256 * oph::LN_MAXC) {
+      if (is_fp32) oph::layernorm_bwd_rows_long_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+      else oph::layernorm_bwd_rows_long_kernel<false><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+    } else if (is_fp32) oph::layernorm_bwd_rows_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
     else oph::layernorm_bwd_rows_kernel<false><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
     HD_CUDA(cudaGetLastError());
   }

@@ -89,8 +89,8 @@ class LayerNorm(nn.Module):
         super().__init__()
         if not isinstance(normalized_shape, int):
             (normalized_shape,) = tuple(normalized_shape)
-        if normalized_shape % 8 or normalized_shape > 2048:
-            raise ValueError("oneprot_b200.LayerNorm: the normalised dim must be a multiple of 8, at most 2048")
+        if normalized_shape % 8:
+            raise ValueError("oneprot_b200.LayerNorm: the normalised dim must be a multiple of 8")
         self.normalized_shape = (normalized_shape,)
         self.eps = eps
         self.weight = nn.Parameter(torch.ones(normalized_shape))

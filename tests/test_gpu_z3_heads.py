@@ -20,7 +20,7 @@ CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "head
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("rows,d", [(1000, 1280), (37, 1152), (512, 64), (8, 2048)])
+@pytest.mark.parametrize("rows,d", [(1000, 1280), (37, 1152), (512, 64), (8, 2048), (100, 2560), (33, 5120)])
 def test_layernorm_kernels_vs_torch(rows, d, dtype):
     from oneprot_b200.heads import LayerNorm
     g = torch.Generator().manual_seed(rows + d)

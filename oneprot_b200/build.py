@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRCS = [os.path.join(HERE, "csrc", "clip_kernels.cu"),     # kernels + one entry point per kernel
         os.path.join(HERE, "csrc", "clip_sequence.cu"),    # host-side step sequencer + launch trace
         os.path.join(HERE, "csrc", "head_kernels.cu")]     # projection-head row kernels (pooling, LayerNorm, GELU)
-DEPS = SRCS + [os.path.join(HERE, "csrc", "ptx.cuh"), os.path.join(HERE, "csrc", "host_trace.h"),
+DEPS = SRCS + [os.path.join(HERE, "csrc", "ptx.cuh"), os.path.join(HERE, "csrc", "vector_kernels.cuh"), os.path.join(HERE, "csrc", "host_trace.h"),
                os.path.join(HERE, "..", "include", "oneprot_clip.h")]
 LIB = os.path.join(HERE, "liboneprot_clip.so")
 

@@ -1,0 +1,444 @@
+// HBM-bound vector / row kernels of the ClipLoss path (no tensor cores, no inline PTX): row statistics,
+// slot reductions, loss finalisation, backward weights, row dots, L2-normalise / scale epilogue, bf16
+// slot sums, fp32 limb split, operand augmentation.  Included by clip_kernels.cu inside namespace op
+// (which provides LOG2E, LN2, G_MARGIN, pack_bf16x2 and the ONEPROT_MODE_* constants) and - as plain
+// source - by the CPU SIMT emulation of the tests (tests/emu), which checks these kernel bodies against
+// numpy where no GPU exists.
+#pragma once
+// ------------------------------------------------------------------------------------------
+// Small HBM-bound kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// one warp per row index; rows of A (n) and of B_all (N) share the index space
+__global__ void rowstats_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int n, int N,
+                                int d, int row_offset, float* __restrict__ diag, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int total = max(n, N);
+  float maxa = 0.f, maxb = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < total; row += gridDim.x * wpb) {
+    float sa = 0.f, sb = 0.f, sab = 0.f;
+    const bool has_a = row < n, has_b = row < N;
+    const __nv_bfloat16* ap = A + static_cast<size_t>(has_a ? row : 0) * d;
+    const __nv_bfloat16* bp = B + static_cast<size_t>(has_b ? row : 0) * d;
+    const __nv_bfloat16* bd = B + static_cast<size_t>(has_a ? row_offset + row : 0) * d;  // label column of row
+    for (int k = lane * 8; k < d; k += 256) {      // d % 8 == 0
+      float fa[8], fb[8], fd[8];
+      if (has_a) {
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(ap + k), fa);
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(bd + k), fd);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { sa = fmaf(fa[u], fa[u], sa); sab = fmaf(fa[u], fd[u], sab); }
+      }
+      if (has_b) {
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(bp + k), fb);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sb = fmaf(fb[u], fb[u], sb);
+      }
+    }
+    sa = warp_sum(sa); sb = warp_sum(sb); sab = warp_sum(sab);
+    if (has_a) { maxa = fmaxf(maxa, sa); if (lane == 0) diag[row] = sab; }
+    if (has_b) maxb = fmaxf(maxb, sb);
+  }
+  if (lane == 0) {
+    // non-negative floats order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned int*>(stats), __float_as_uint(maxa));
+    atomicMax(reinterpret_cast<unsigned int*>(stats + 1), __float_as_uint(maxb));
+  }
+}
+
+// out[k] = sum_s part[s*ld + k]; block = 32 outputs x 8 slot groups, fixed summation order (deterministic)
+__global__ void reduce_slots_kernel(const float* __restrict__ part, int slots, int ld, int count, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (k < count)
+    for (int s = grp; s < slots; s += 8) acc += part[static_cast<size_t>(s) * ld + k];
+  red[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && k < count) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][lane];
+    out[k] = t;
+  }
+}
+
+// out[k] = max_s part[s*ld + k]
+__global__ void reduce_slots_max_kernel(const float* __restrict__ part, int slots, int ld, int count, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  float acc = -INFINITY;
+  if (k < count)
+    for (int s = grp; s < slots; s += 8) acc = fmaxf(acc, part[static_cast<size_t>(s) * ld + k]);
+  red[grp][lane] = acc;
+  __syncthreads();
+  if (grp == 0 && k < count) {
+    float t = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t = fmaxf(t, red[g][lane]);
+    out[k] = t;
+  }
+}
+
+// Operand augmentation for the two-reference (robust) path: out = [in | e_h | e_m | 0 x 6] (row pitch
+// d + 8) with e_h + e_m = -ref[i] / c split into two bf16 limbs (ref != nullptr) or e_h = e_m = 1.  The
+// GEMM over d + 8 columns against an operand augmented with ones (resp. limbs) then yields
+// x_ij - ref'_i, where ref'_i = -c * (float(e_h) + float(e_m)) is returned in ref_q: the reference
+// actually applied, exact in fp32.  Two limbs keep ref' within 2^-17 |ref| of ref, so references of
+// 10^5 log2 units (unnormalised features times a large logit_scale) still leave every term <= 2^1.
+__global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, int d, const float* __restrict__ ref,
+                               const float* __restrict__ scale, __nv_bfloat16* __restrict__ out, float* __restrict__ ref_q) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float c = *scale * LOG2E;
+  const int ld = d + 8;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * d);
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ld);
+    for (int k = lane; k < d / 8; k += 32) dst[k] = src[k];
+    if (lane == 0) {
+      __nv_bfloat16 eh = __float2bfloat16_rn(1.f), em = __float2bfloat16_rn(1.f);
+      if (ref) {
+        const float t = -ref[row] / c;
+        eh = __float2bfloat16_rn(t);
+        em = __float2bfloat16_rn(t - __bfloat162float(eh));
+        if (ref_q) ref_q[row] = -c * (__bfloat162float(eh) + __bfloat162float(em));
+      }
+      __nv_bfloat16 tail[8];
+      tail[0] = eh;
+      tail[1] = em;
+#pragma unroll
+      for (int u = 2; u < 8; ++u) tail[u] = __float2bfloat16_rn(0.f);
+      dst[d / 8] = *reinterpret_cast<uint4*>(tail);
+    }
+  }
+}
+
+// loss value, reciprocal sums, hazard flag.  FIN_BLOCKS blocks each reduce a fixed slice in double
+// precision; the last block to finish adds the per-block partials in index order (deterministic).
+constexpr int FIN_BLOCKS = 32;
+__global__ void loss_finalize_kernel(const float* __restrict__ rowsum, const float* __restrict__ colsum,
+                                     const float* __restrict__ diag, int N, int n, int row_offset, int mode,
+                                     const float* __restrict__ scale, const float* __restrict__ stats,
+                                     float* __restrict__ loss_out, float* __restrict__ inv_rs, float* __restrict__ inv_cs,
+                                     int* __restrict__ flag, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                                     const float* __restrict__ row_ref, const float* __restrict__ col_ref) {
+  __shared__ double red[32];
+  __shared__ int bad_s;
+  __shared__ bool is_last;
+  const float s = *scale;
+  const float c = s * LOG2E;
+  const float U = fabsf(c) * sqrtf(stats[0] * stats[1]);
+  const float G = (stats[3] != 0.f) ? fmaxf(0.f, stats[2] - G_MARGIN) : fmaxf(0.f, U - G_MARGIN);
+  if (threadIdx.x == 0) bad_s = 0;
+  __syncthreads();
+  const int lo = (mode == ONEPROT_MODE_LOCAL) ? row_offset : 0;
+  const int hi = (mode == ONEPROT_MODE_LOCAL) ? row_offset + n : N;
+  double acc = 0.0;
+  int bad = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+    const float rs = rowsum[k], cs = colsum[k];
+    // validated window: sums must be finite and not have lost their leading terms to flush-to-zero
+    if (!(rs >= 1e-27f && rs <= 3e38f) || !(cs >= 1e-27f && cs <= 3e38f)) bad = 1;   // 2^-90: flushed mass <= N 2^-126 stays below 2^-20 relative
+    inv_rs[k] = 1.f / rs;
+    inv_cs[k] = 1.f / cs;
+    if (k >= lo && k < hi) {
+      const float zd = s * diag[k];
+      const float gr = row_ref ? row_ref[k] : G, gc = col_ref ? col_ref[k] : G;   // two-reference path: per-element G
+      acc += static_cast<double>(LN2 * (gr + log2f(rs)) - zd) + static_cast<double>(LN2 * (gc + log2f(cs)) - zd);
+    }
+  }
+  if (bad) bad_s = 1;
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    if (bad_s) atomicOr(flag, 1);
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += *(volatile double*)(partial + b);
+    loss_out[0] = static_cast<float>(t / (2.0 * (hi - lo)));
+    *counter = 0;   // ready for the next launch
+  }
+}
+
+// SigLIP value of this rank: (ln2 * sum_i rowsum[i] - sum_i (s * diag[i] + bias)) / n with
+// rowsum[i] = sum_j log2(1 + 2^x_ij): the label term -logsigmoid(+z_ii) = softplus(z_ii) - z_ii.
+// One block, double accumulation in a fixed order (deterministic).
+__global__ void siglip_finalize_kernel(const float* __restrict__ rowsum, const float* __restrict__ diag, int n,
+                                       const float* __restrict__ scale, const float* __restrict__ bias, float* __restrict__ loss_out) {
+  __shared__ double red[32];
+  const float s = *scale, b = bias ? *bias : 0.f;
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x)
+    acc += static_cast<double>(LN2) * static_cast<double>(rowsum[k]) - static_cast<double>(fmaf(s, diag[k], b));
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    loss_out[0] = static_cast<float>(t / n);
+  }
+}
+
+__global__ void bwd_weights_kernel(const float* __restrict__ inv_rs, const float* __restrict__ inv_cs, int N, int n,
+                                   int row_offset, int mode, int use_gsum, int part, int world, int rank,
+                                   const float* __restrict__ gvec, const float* __restrict__ scale,
+                                   float* __restrict__ wr, float* __restrict__ wc, float* __restrict__ dg,
+                                   float* __restrict__ out_scale_a, float* __restrict__ out_scale_b, int what) {
+  // what: 0 = everything, 1 = panel weights only (wr, wc, dg), 2 = output scales only
+  const bool do_w = what != 2, do_s = what != 1;
+  const float s = *scale;
+  float gsum = 0.f;
+  for (int r = 0; r < world; ++r) gsum += gvec[r];
+  const float g_own = gvec[rank];
+  const float fr = (part == 2) ? 0.f : 1.f;   // row-softmax half enabled
+  const float fc = (part == 1) ? 0.f : 1.f;   // column-softmax half enabled
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npr = N / world;                  // rows per rank
+  if (mode == ONEPROT_MODE_GLOBAL) {
+    // unit-gradient panel; the upstream gradients are applied to the GEMM outputs:
+    //   dA_r *= (use_gsum ? sum_r g_r : g_own),  dB_partial[j] *= (use_gsum ? sum_r g_r : g_owner(j))
+    const float coef = s / (2.f * N);
+    if (k < n) {
+      if (do_w) { wr[k] = fr * coef * inv_rs[row_offset + k]; dg[k] = (fr + fc) * coef; }
+      if (do_s) out_scale_a[k] = use_gsum ? gsum : g_own;
+    }
+    if (k < N) {
+      if (do_w) wc[k] = fc * coef * inv_cs[k];
+      if (do_s) out_scale_b[k] = use_gsum ? gsum : gvec[k / npr];
+    }
+  } else {
+    // local loss: row i of rank r carries g_r (row softmax), column j carries g_owner(j)
+    if (k < n) {
+      const float coef = s * g_own / (2.f * n);
+      if (do_w) { wr[k] = fr * coef * inv_rs[row_offset + k]; dg[k] = (fr + fc) * coef; }
+      if (do_s) out_scale_a[k] = 1.f;
+    }
+    if (k < N) {
+      if (do_w) wc[k] = fc * s * gvec[k / npr] / (2.f * n) * inv_cs[k];
+      if (do_s) out_scale_b[k] = 1.f;
+    }
+  }
+}
+
+// rowdot[i] = <x_i, y_i> for bf16 matrices (one warp per row)
+__global__ void rowdot_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ y, int ldy,
+                              int rows, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    float acc = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fy[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx + k), fx);
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(y + static_cast<size_t>(row) * ldy + k), fy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(fx[u], fy[u], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
+// out[0] = sum_k v[k] (single block, fixed order => deterministic)
+__global__ void sum_kernel(const float* __restrict__ v, int count, float* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < count; k += blockDim.x) acc += v[k];
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    out[0] = static_cast<float>(t);
+  }
+}
+
+// ---- L2 normalise (+ logit scale) ---------------------------------------------------------
+template <bool FP32>
+__device__ __forceinline__ void load8(const void* base, size_t idx, float (&f)[8]) {
+  if (FP32) {
+    const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + idx), f);
+  }
+}
+template <bool FP32>
+__device__ __forceinline__ void store8(void* base, size_t idx, const float (&f)[8]) {
+  if (FP32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + idx + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + idx) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
+// one warp per row; the row is read once (kept in registers for d <= 2048) and written once
+template <bool FP32>
+__global__ void l2norm_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, float* __restrict__ inv_norm,
+                                  int rows, int d, const float* __restrict__ scale, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float sc = scale ? *scale : 1.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    float ss = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float f[8];
+      load8<FP32>(x, base + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ss = fmaf(f[u], f[u], ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+    const float m = inv * sc;
+    for (int k = lane * 8; k < d; k += 256) {   // second read hits L1/L2 (row <= 8 KiB)
+      float f[8];
+      load8<FP32>(x, base + k, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] *= m;
+      store8<FP32>(y, base + k, f);
+    }
+  }
+}
+
+template <bool FP32>
+__global__ void l2norm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ gy,
+                                  const float* __restrict__ inv_norm, void* __restrict__ gx,
+                                  float* __restrict__ dscale_partial, int rows, int d, const float* __restrict__ scale,
+                                  float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float sc = scale ? *scale : 1.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    const float inv = inv_norm[row];
+    float dot = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fg[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(gy, base + k, fg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dot = fmaf(fx[u] * inv, fg[u], dot);
+    }
+    dot = warp_sum(dot);                      // <yhat, gy>
+    if (lane == 0 && dscale_partial) dscale_partial[row] = dot;
+    // below the eps clamp F.normalize is x / eps: the projection term vanishes
+    const bool clamped = inv >= 1.f / eps;
+    const float proj = clamped ? 0.f : dot;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fg[8], o[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(gy, base + k, fg);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = sc * inv * (fg[u] - fx[u] * inv * proj);
+      store8<FP32>(gx, base + k, o);
+    }
+  }
+}
+
+// y = scale * x, flat over rows*d elements (8 per thread per step)
+template <bool FP32>
+__global__ void scale_kernel(const void* __restrict__ x, void* __restrict__ y, size_t total8,
+                             const float* __restrict__ scale) {
+  const float sc = *scale;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8<FP32>(x, i * 8, f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] *= sc;
+    store8<FP32>(y, i * 8, f);
+  }
+}
+
+// out[row] = <x_row, y_row>, contiguous rows of d elements
+template <bool FP32>
+__global__ void rowdot_dense_kernel(const void* __restrict__ x, const void* __restrict__ y, int rows, int d,
+                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    float acc = 0.f;
+    for (int k = lane * 8; k < d; k += 256) {
+      float fx[8], fy[8];
+      load8<FP32>(x, base + k, fx);
+      load8<FP32>(y, base + k, fy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fmaf(fx[u], fy[u], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+  }
+}
+
+// out[i] = bf16( sum_w slots[w][i] ) with fp32 accumulation in slot order (deterministic); 8 per thread
+__global__ void sum_slots_bf16_kernel(const uint4* __restrict__ slots, int W, size_t n16, uint4* __restrict__ out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int w = 0; w < W; ++w) {
+      float f[8];
+      bf16x8_to_float(slots[static_cast<size_t>(w) * n16 + i], f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += f[u];
+    }
+    out[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                        pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// fp32 -> bf16 limbs: x = h + m + l (each bf16).  side 0 (left operand):  [h h m | h m l]
+//                                                   side 1 (right operand): [h m h | l m h]
+// terms = 3 keeps the first three limb products (h.h + h.m + m.h), terms = 6 all six of order <= 2.
+__global__ void split_fp32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int d,
+                                  int side, int terms) {
+  const size_t total = static_cast<size_t>(rows) * d;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = idx / d, col = idx % d;
+    const float v = x[idx];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    const __nv_bfloat16 L[6] = {h, h, m, h, m, l};
+    const __nv_bfloat16 R[6] = {h, m, h, l, m, h};
+    __nv_bfloat16* o = out + row * static_cast<size_t>(terms) * d + col;
+    for (int t = 0; t < terms; ++t) o[static_cast<size_t>(t) * d] = side ? R[t] : L[t];
+  }
+}

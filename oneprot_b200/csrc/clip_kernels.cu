@@ -15,8 +15,15 @@
 //                       variant that TMA-stores finished tiles into the owner GPU's memory
 //   gemm2_kernel        the same GEMM on CTA pairs (tcgen05.mma cta_group::2), opt-in
 // plus the HBM-bound vector kernels and the multimem (NVLS) exchange kernels at the end.
+// ONEPROT_KERNEL_EMULATION (tests/emu): the kernel bodies of this file are also compiled for the CPU, with
+// ptx_emu.h supplying functional stand-ins for the TMA / mbarrier / tcgen05 / TMEM primitives of ptx.cuh.
+#ifndef ONEPROT_KERNEL_EMULATION
 #include "ptx.cuh"
 #include "host_trace.h"
+#define OP_DYNAMIC_SMEM(name) extern __shared__ uint8_t name[]
+#else
+#include "ptx_emu.h"
+#endif
 #include "../../include/oneprot_clip.h"
 
 #include <cuda_bf16.h>
@@ -225,6 +232,9 @@ struct SParams {
   int ag_rank, ag_world, ag_chunks, ag_chunk16, ag_rows, ag_bpc;   // chunk16: 16-byte vectors per chunk; bpc: column blocks per chunk
 };
 
+#ifdef ONEPROT_KERNEL_EMULATION
+__device__ __forceinline__ void wait_flag(const unsigned int*, unsigned int) {}   // single-GPU emulation: no exchange
+#else
 __device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int epoch) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
@@ -236,6 +246,7 @@ __device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int ep
     if (clock64() - t0 > ONEPROT_WAIT_TRAP_CYCLES) __trap();
   } while (v != epoch);
 }
+#endif
 
 // logical column-block index -> actual column block: chunk-major (arrival order), own rank first
 __device__ __forceinline__ int map_jb(const SParams& p, int jl) {
@@ -295,7 +306,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const float U = fabsf(__ldg(p.scale) * LOG2E) * sqrtf(__ldg(p.stats) * __ldg(p.stats + 1));
     if (U <= G_MARGIN) return;     // uniform over the grid, before any barrier / TMEM allocation
   }
-  extern __shared__ uint8_t smem_raw[];
+  OP_DYNAMIC_SMEM(smem_raw);
   const Smem s = carve_smem<NS, SCfg<EPI>::STAGING>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
   const int warp = threadIdx.x >> 5;
@@ -363,6 +374,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
   } else if (warp < EPI_WARP0) {
     reg_dealloc<56>();
+#ifndef ONEPROT_KERNEL_EMULATION
     if (EPI == EPI_FWD && warp == 3 && p.ag_src) {
       // ---------------------------------------------- all-gather push (spare warp)
       const int lane = lane_id();
@@ -395,6 +407,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
       }
     }
+#endif
   } else {
     // ------------------------------------------------ epilogue (8 warps)
     reg_alloc<224>();
@@ -525,7 +538,11 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int k = 0; k < 32; ++k) {
               const bool ok = rowok && (j0 + cc * 32 + k < p.N);
               const float x = fmaf(v[k], c, negG);
-              const float sp = fmaxf(x, 0.f) + __log2f(1.f + ex2(-fabsf(x)));
+              // log2(1 + e), e = 2^-|x|: below 2^-10 the rounding of 1 + e would cost up to eps / e relative
+              // (and bias the sum of N tiny terms), so use e log2(e) (1 - e / 2) there
+              const float e = ex2(-fabsf(x));
+              const float l = (e < 9.765625e-4f) ? e * fmaf(-0.72134752f, e, LOG2E) : __log2f(1.f + e);
+              const float sp = fmaxf(x, 0.f) + l;
               rsum += ok ? sp : 0.f;
             }
             continue;
@@ -660,7 +677,7 @@ template <int A_MN, int B_MN, bool PUSH>
 __global__ void __maxnreg__(128)   // 384 x 128 registers: leaves 16 K registers per SM for a co-resident exchange kernel
 gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
             const __grid_constant__ OwnerMaps om, const GParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  OP_DYNAMIC_SMEM(smem_raw);
   const Smem s = carve_smem<GEMM_NS, PUSH ? STORE_STAGING_BYTES : 0>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
   const int warp = threadIdx.x >> 5;
@@ -814,6 +831,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
   kernel_epilogue_dealloc(tmem_base);
 }
 
+#ifndef ONEPROT_KERNEL_EMULATION   // CTA pairs and the multimem exchanges below are not emulated
 // ------------------------------------------------------------------------------------------
 // CTA-pair GEMM (cta_group::2): two CTAs of a cluster own one 256 x 256 tile.  Each loads its own
 // 128 rows of A and HALF of the B tile (the tensor cores of both SMs share the halves), so the
@@ -826,7 +844,7 @@ constexpr int GEMM2_SMEM = P_NS * P_STAGE_BYTES + 1024 + static_cast<int>(sizeof
 template <int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  OP_DYNAMIC_SMEM(smem_raw);
   const uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023);
   uint8_t* stages = reinterpret_cast<uint8_t*>(base);
   SmemTail* tail = reinterpret_cast<SmemTail*>(base + P_NS * P_STAGE_BYTES);
@@ -991,9 +1009,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
+#endif  // ONEPROT_KERNEL_EMULATION
 
 #include "vector_kernels.cuh"   // the non-tensor-core kernels (also compiled for the CPU emulation of the tests)
 
+#ifndef ONEPROT_KERNEL_EMULATION
 // ---- NVLink SHARP (multimem) exchanges over a symmetric-memory multicast mapping ---------------
 // dst_mc is the multicast alias of one buffer that exists on every GPU of the node: a
 // multimem.st lands in all copies (all-gather by push), a multimem.ld_reduce returns the
@@ -1042,8 +1062,10 @@ __global__ void mc_reduce_bf16_kernel(const uint4* src_mc, uint4* __restrict__ d
   }
 }
 
+#endif  // ONEPROT_KERNEL_EMULATION
 }  // namespace op
 
+#ifndef ONEPROT_KERNEL_EMULATION
 // ==========================================================================================
 // Host side: C ABI
 // ==========================================================================================
@@ -1751,3 +1773,4 @@ int oneprot_split_fp32(const float* x, void* out, int rows, int d, int side, int
 }
 
 }  // extern "C"
+#endif  // ONEPROT_KERNEL_EMULATION (host side)

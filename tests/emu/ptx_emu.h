@@ -1,0 +1,201 @@
+// Functional CPU stand-ins for the primitives of oneprot_b200/csrc/ptx.cuh (mbarrier, TMA loads / stores
+// with SWIZZLE_128B, tcgen05.mma with shared-memory descriptors, TMEM, named barriers), so that the
+// SOURCE of the tensor-core kernels in clip_kernels.cu - warp roles, pipelines, tile scheduling, every
+// epilogue variant - runs on the CPU in the tests (one OS thread per CUDA thread, one CTA at a time).
+// Layout semantics follow the PTX ISA: 128-byte swizzle = 16-byte chunk index XOR (row mod 8) inside
+// 1024-byte atoms; K-major / MN-major canonical layouts addressed through start / LBO / SBO of the
+// descriptor; instruction descriptor fields M, N, a_major, b_major.  Arithmetic: bf16 products
+// accumulated in fp32 (order differs from the hardware's).  Test infrastructure only.
+#pragma once
+#include "cuda_emu.h"
+
+#include <cuda.h>
+
+#include <condition_variable>
+#include <map>
+#include <mutex>
+
+#define ONEPROT_WAIT_TRAP_CYCLES (1ll << 37)
+#define OP_DYNAMIC_SMEM(name) uint8_t* name = op::emu_smem()
+#define __grid_constant__
+#define __maxnreg__(n)
+#define __cluster_dims__(...)
+#define __syncwarp() pthread_barrier_wait(emu::tls.wbar)
+#define __fdividef(a, b) ((a) / (b))
+
+namespace op {
+
+// ---- shared memory of the (single) running CTA ------------------------------------------------------
+inline uint8_t* emu_smem() {
+  alignas(1024) static uint8_t mem[240 * 1024];
+  return mem;
+}
+inline uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(static_cast<const uint8_t*>(p) - emu_smem()); }
+inline uint32_t swz128(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
+inline uint32_t lane_id() { return static_cast<uint32_t>(emu::tls.lin & 31); }
+inline bool elect_one() { return lane_id() == 0; }
+
+// ---- mbarrier ------------------------------------------------------------------------------------------
+struct MBarState { int init = 0, pending = 0; long tx = 0; uint32_t phase = 0; };
+inline std::mutex& mbar_mu() { static std::mutex m; return m; }
+inline std::map<const void*, MBarState>& mbar_tab() { static std::map<const void*, MBarState> t; return t; }
+inline void mbar_check(MBarState& s) {
+  if (s.pending == 0 && s.tx == 0) { s.phase ^= 1u; s.pending = s.init; }
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  std::lock_guard<std::mutex> lk(mbar_mu());
+  MBarState s; s.init = s.pending = static_cast<int>(count);
+  mbar_tab()[bar] = s;
+}
+inline void fence_mbar_init() {}
+inline void fence_proxy_async() {}
+inline void mbar_arrive(uint64_t* bar) {
+  std::lock_guard<std::mutex> lk(mbar_mu());
+  MBarState& s = mbar_tab()[bar];
+  --s.pending; mbar_check(s);
+}
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> lk(mbar_mu());
+  MBarState& s = mbar_tab()[bar];
+  s.tx += bytes; --s.pending; mbar_check(s);
+}
+inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> lk(mbar_mu());
+  MBarState& s = mbar_tab()[bar];
+  s.tx -= bytes; mbar_check(s);
+}
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  std::lock_guard<std::mutex> lk(mbar_mu());
+  return mbar_tab()[bar].phase != parity;      // the phase with this parity has completed
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) std::this_thread::yield();
+}
+
+// ---- TMA -------------------------------------------------------------------------------------------------
+struct EmuMap {          // lives inside the 128 opaque bytes of a CUtensorMap
+  const uint16_t* ptr;   // bf16 bit patterns
+  uint64_t inner, outer, ld;
+  uint32_t box_outer;
+};
+inline const EmuMap& emap(const CUtensorMap* m) { return *reinterpret_cast<const EmuMap*>(m); }
+inline void prefetch_tmap(const CUtensorMap*) {}
+
+// box {64 elements, box_outer rows}, SWIZZLE_128B, out-of-bounds elements read as zero
+inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+  const EmuMap& e = emap(m);
+  uint8_t* dst = static_cast<uint8_t*>(smem_dst);
+  const uint32_t base = smem_u32(dst);
+  for (uint32_t r = 0; r < e.box_outer; ++r)
+    for (uint32_t x = 0; x < 64; ++x) {
+      const int64_t row = static_cast<int64_t>(c1) + r, col = static_cast<int64_t>(c0) + x;
+      uint16_t v = 0;
+      if (row >= 0 && col >= 0 && row < static_cast<int64_t>(e.outer) && col < static_cast<int64_t>(e.inner)) v = e.ptr[row * e.ld + col];
+      std::memcpy(emu_smem() + swz128(base + r * 128 + x * 2), &v, 2);
+    }
+  mbar_complete_tx(bar, e.box_outer * 128);
+}
+inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  const EmuMap& e = emap(m);
+  const uint32_t base = smem_u32(smem_src);
+  uint16_t* out = const_cast<uint16_t*>(e.ptr);
+  for (uint32_t r = 0; r < e.box_outer; ++r)
+    for (uint32_t x = 0; x < 64; ++x) {
+      const int64_t row = static_cast<int64_t>(c1) + r, col = static_cast<int64_t>(c0) + x;
+      if (row < 0 || col < 0 || row >= static_cast<int64_t>(e.outer) || col >= static_cast<int64_t>(e.inner)) continue;   // clipped
+      std::memcpy(&out[row * e.ld + col], emu_smem() + swz128(base + r * 128 + x * 2), 2);
+    }
+}
+inline uint64_t l2_policy_evict_first() { return 1; }
+inline uint64_t l2_policy_evict_last() { return 2; }
+inline void tma_load_2d_hint(void* d, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, uint64_t) { tma_load_2d(d, m, bar, c0, c1); }
+inline void tma_store_2d_hint(const CUtensorMap* m, const void* s, int32_t c0, int32_t c1, uint64_t) { tma_store_2d(m, s, c0, c1); }
+inline void bulk_commit() {}
+template <int N> inline void bulk_wait_read() {}
+template <int N> inline void bulk_wait() {}
+
+inline void st_shared_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  const uint32_t v[4] = {x, y, z, w};
+  std::memcpy(emu_smem() + a, v, 16);
+}
+inline float4 ld_shared_f4(uint32_t a) { float4 v; std::memcpy(&v, emu_smem() + a, 16); return v; }
+inline void st_shared_f32(uint32_t a, float v) { std::memcpy(emu_smem() + a, &v, 4); }
+
+// ---- TMEM + tcgen05.mma -------------------------------------------------------------------------------
+inline float (*emu_tmem())[512] { static float t[128][512]; return t; }
+inline void tmem_alloc(uint32_t* holder, uint32_t) { *holder = 0; }
+inline void tmem_relinquish() {}
+inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+inline void tmem_ld_wait() {}
+inline void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  const uint32_t lane0 = taddr >> 16, col = taddr & 0xffffu;
+  for (int k = 0; k < 32; ++k) v[k] = emu_tmem()[lane0 + lane_id()][col + k];
+}
+
+inline uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+inline float emu_operand(uint64_t desc, int mn_major, int i, int k) {
+  const uint32_t start = static_cast<uint32_t>(desc & 0x3FFF) << 4;
+  const uint32_t lbo = static_cast<uint32_t>((desc >> 16) & 0x3FFF) << 4, sbo = static_cast<uint32_t>((desc >> 32) & 0x3FFF) << 4;
+  uint32_t a;
+  if (!mn_major) a = start + (i / 8) * sbo + (i % 8) * 128 + k * 2;                       // K-major: rows of 128 B, 8-row atoms
+  else a = start + (i / 64) * lbo + (k / 8) * sbo + (k % 8) * 128 + (i % 64) * 2;        // MN-major: 64-element chunks, k rows
+  uint16_t bits;
+  std::memcpy(&bits, emu_smem() + swz128(a), 2);
+  return emu::uint_as_float(static_cast<uint32_t>(bits) << 16);
+}
+// D[128 x N] (+)= A[128 x 16] B[N x 16]^T, bf16 operands from shared memory, fp32 accumulator in TMEM
+inline void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const int M = static_cast<int>((idesc >> 24) & 0x1f) << 4, N = static_cast<int>((idesc >> 17) & 0x3f) << 3;
+  const int a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
+  const uint32_t col0 = tmem_d & 0xffffu;
+  float a[128][16];
+  for (int i = 0; i < M; ++i)
+    for (int k = 0; k < 16; ++k) a[i][k] = emu_operand(desc_a, a_mn, i, k);
+  for (int j = 0; j < N; ++j) {
+    float b[16];
+    for (int k = 0; k < 16; ++k) b[k] = emu_operand(desc_b, b_mn, j, k);
+    for (int i = 0; i < M; ++i) {
+      float acc = accumulate ? emu_tmem()[i][col0 + j] : 0.f;
+      for (int k = 0; k < 16; ++k) acc = fmaf(a[i][k], b[k], acc);
+      emu_tmem()[i][col0 + j] = acc;
+    }
+  }
+}
+inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }     // the emulated MMAs are synchronous
+
+// ---- misc ---------------------------------------------------------------------------------------------------
+inline float ex2(float x) { return exp2f(x); }
+inline void named_bar_sync(int id, int nthreads) {
+  static std::mutex mu;
+  static std::condition_variable cv;
+  static int count[16] = {0};
+  static unsigned gen[16] = {0};
+  std::unique_lock<std::mutex> lk(mu);
+  const unsigned g = gen[id];
+  if (++count[id] == nthreads) { count[id] = 0; ++gen[id]; cv.notify_all(); }
+  else cv.wait(lk, [&] { return gen[id] != g; });
+}
+template <int N> inline void reg_alloc() {}
+template <int N> inline void reg_dealloc() {}
+inline uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  uint32_t r;
+  std::memcpy(&r, &t, 4);
+  return r;
+}
+
+}  // namespace op

@@ -291,3 +291,160 @@ def test_l2norm_scale_and_split(vec, dtype):
             h, m = (o[:, :d], o[:, 2 * d:]) if side == 0 else (o[:, :d], o[:, d:2 * d])
             assert np.allclose(h + m, xv, rtol=2.0 ** -15, atol=1e-30)       # two limbs reproduce fp32 to ~2^-16
             assert np.array_equal(o[:, d:2 * d] if side == 0 else o[:, 2 * d:], h)
+
+
+# ---------------------------------------------------------------------------------------------------
+# csrc/clip_kernels.cu: the tensor-core kernels under the functional TMA / mbarrier / tcgen05 / TMEM
+# stand-ins of tests/emu/ptx_emu.h.  FWD / DZ / MAX / GEMM were validated on hardware: they calibrate the
+# emulation.  RCMAX, RANK, SFWD, SDZ and DZ_L2 are the epilogue variants that have not run on a GPU yet.
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tc(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_bf16.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    out = str(tmp_path_factory.mktemp("emu") / "libclip_emu.so")
+    p = subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I" + CUDA_INC,
+                        "-I" + os.path.join(ROOT, "tests", "emu"), "-o", out, os.path.join(ROOT, "tests", "emu", "clip_kernels_emu.cpp")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lib = C.CDLL(out)
+    lib.emu_s_scratch_floats.restype = C.c_size_t
+    return lib
+
+
+def _unit(rng, n, d, scale=1.0):
+    x = torch.nn.functional.normalize(torch.from_numpy(rng.standard_normal((n, d))).float(), dim=-1) * scale
+    x = x.to(torch.bfloat16)
+    return x, x.double().numpy()
+
+
+SHAPES = [(300, 300, 72, 0), (256, 512, 128, 256), (130, 700, 64, 400)]       # (n, N, d, row offset): ragged tiles, K tails, panels
+
+
+@pytest.mark.parametrize("n,N,d,off", SHAPES)
+@pytest.mark.parametrize("sms", [3, 1])
+def test_emulated_forward_sums(tc, n, N, d, off, sms):
+    tc.emu_set_sms(sms)
+    rng = np.random.default_rng(n + N)
+    A, Av = _unit(rng, n, d)
+    B, Bv = _unit(rng, N, d, 1 / 0.07)
+    scale = torch.ones(1); stats = torch.zeros(4)
+    stats[0], stats[1] = float((Av ** 2).sum(-1).max()), float((Bv ** 2).sum(-1).max())
+    rowsum = torch.empty(n); colsum = torch.empty(N)
+    scratch = torch.zeros(tc.emu_s_scratch_floats(n, N))
+    tc.emu_fwd_sums(_p(A), _p(B), n, N, d, _p(scale), _p(stats), _p(rowsum), _p(colsum), _p(scratch))
+    E = np.exp2(LOG2E * (Av @ Bv.T))
+    assert np.allclose(rowsum.numpy(), E.sum(1), rtol=1e-5) and np.allclose(colsum.numpy(), E.sum(0), rtol=1e-5)
+
+
+def test_emulated_forward_uses_exact_maximum_when_the_norm_bound_is_loose(tc):
+    """Unnormalised features: the max pass (EPI_MAX) supplies G = max(0, x_max - 100)."""
+    tc.emu_set_sms(3)
+    rng = np.random.default_rng(9)
+    n, d = 256, 64
+    A, Av = _t(rng.standard_normal((n, d)), torch.bfloat16)
+    B, Bv = _t(rng.standard_normal((n, d)), torch.bfloat16)
+    scale = torch.tensor([8.0]); stats = torch.zeros(4)
+    stats[0], stats[1] = float((Av ** 2).sum(-1).max()), float((Bv ** 2).sum(-1).max())
+    rowsum = torch.empty(n); colsum = torch.empty(n)
+    scratch = torch.zeros(tc.emu_s_scratch_floats(n, n))
+    tc.emu_fwd_sums(_p(A), _p(B), n, n, d, _p(scale), _p(stats), _p(rowsum), _p(colsum), _p(scratch))
+    X = 8.0 * LOG2E * (Av @ Bv.T)
+    assert stats[3].item() == 1.0 and np.isclose(stats[2].item(), X.max(), rtol=1e-5)
+    G = max(0.0, X.max() - 100.0)
+    assert G > 0
+    assert np.allclose(rowsum.numpy(), np.exp2(X - G).sum(1), rtol=2e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize("rows,N,d,grow0", [(300, 300, 72, 0), (128, 512, 64, 256), (130, 700, 128, 400)])
+@pytest.mark.parametrize("variant", ["dz", "dz_l2", "siglip"])
+def test_emulated_panel_kernels(tc, rows, N, d, grow0, variant):
+    tc.emu_set_sms(3)
+    rng = np.random.default_rng(rows + N + d)
+    A, Av = _unit(rng, rows, d)
+    B, Bv = _unit(rng, N, d, 1 / 0.07)
+    scale = torch.ones(1); stats = torch.tensor([1.0, 205.0, 0.0, 0.0])
+    wr = torch.from_numpy((1e-3 * rng.random(rows)).astype(np.float32)); wc = torch.from_numpy((1e-3 * rng.random(N)).astype(np.float32))
+    dg = torch.from_numpy((0.1 * rng.random(rows)).astype(np.float32))
+    ldw = (N + 63) // 64 * 64
+    Wz = torch.full((rows, ldw), 7.0, dtype=torch.bfloat16)
+    Z = Av @ Bv.T
+    idx = np.arange(rows)
+    if variant == "siglip":
+        bias = torch.tensor([-3.0])
+        tc.emu_siglip_dz(_p(A), _p(B), rows, N, d, grow0, _p(scale), _p(bias), _p(wr), _p(dg), _p(Wz), ldw)
+        want = wr.double().numpy()[:, None] / (1 + np.exp(-(Z - 3.0)))
+    else:
+        tc.emu_dz_panel(_p(A), _p(B), rows, N, d, grow0, _p(scale), _p(stats), _p(wr), _p(wc), _p(dg), _p(Wz), ldw, int(variant == "dz_l2"))
+        want = np.exp2(LOG2E * Z) * (wr.double().numpy()[:, None] + wc.double().numpy()[None, :])
+    want[idx, grow0 + idx] -= dg.double().numpy()
+    got = Wz.double().numpy()
+    assert np.allclose(got[:, :N], want, rtol=2.0 ** -7, atol=1e-6)            # bf16 storage
+    assert np.all(got[:, N:] == 7.0)                                           # TMA stores clip the columns beyond N
+
+
+@pytest.mark.parametrize("n,N,d", [(300, 300, 72), (256, 512, 128)])
+def test_emulated_siglip_forward_and_rowcol_max(tc, n, N, d):
+    tc.emu_set_sms(3)
+    rng = np.random.default_rng(n * 3 + d)
+    A, Av = _unit(rng, n, d)
+    B, Bv = _unit(rng, N, d)
+    scale = torch.tensor([10.0]); bias = torch.tensor([-10.0])
+    rowsum = torch.empty(n)
+    scratch = torch.zeros(tc.emu_s_scratch_floats(n, N))
+    tc.emu_siglip_fwd(_p(A), _p(B), n, N, d, _p(scale), _p(bias), _p(rowsum), _p(scratch))
+    z = 10.0 * (Av @ Bv.T) - 10.0
+    sp = np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
+    assert np.allclose(rowsum.numpy() * np.log(2.0), sp.sum(1), rtol=2e-5)
+    # extreme logits stay finite (2^x alone would overflow)
+    big = torch.tensor([4000.0])
+    tc.emu_siglip_fwd(_p(A), _p(B), n, N, d, _p(big), None, _p(rowsum), _p(scratch))
+    zb = 4000.0 * (Av @ Bv.T)
+    assert np.all(np.isfinite(rowsum.numpy())) and np.allclose(rowsum.numpy() * np.log(2.0), (np.maximum(zb, 0) + np.log1p(np.exp(-np.abs(zb)))).sum(1), rtol=1e-4)
+    rowmax = torch.empty(n); colmax = torch.empty(N)
+    tc.emu_rowcol_max(_p(A), _p(B), n, N, d, _p(scale), _p(rowmax), _p(colmax), _p(scratch))
+    X = 10.0 * LOG2E * (Av @ Bv.T)
+    assert np.allclose(rowmax.numpy(), X.max(1), rtol=1e-5, atol=1e-5) and np.allclose(colmax.numpy(), X.max(0), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("N,d", [(300, 72), (512, 64)])
+def test_emulated_retrieval_ranks(tc, N, d):
+    tc.emu_set_sms(3)
+    rng = np.random.default_rng(N + d)
+    S, Sv = _unit(rng, N, d)
+    M = torch.nn.functional.normalize(S.float() + 0.8 * torch.from_numpy(rng.standard_normal((N, d))).float(), dim=-1).to(torch.bfloat16)
+    Mv = M.double().numpy()
+    Z = Sv @ Mv.T
+    label = torch.from_numpy(np.diag(Z).astype(np.float32))
+    r1 = torch.empty(N); r2 = torch.empty(N)
+    scratch = torch.zeros(tc.emu_s_scratch_floats(N, N))
+    tc.emu_retrieval_ranks(_p(S), _p(M), N, d, _p(label), _p(r1), _p(r2), _p(scratch))
+    Zf = (S.float() @ M.float().T).double().numpy()          # the kernel compares fp32-accumulated products with the fp32 label dots
+    off = ~np.eye(N, dtype=bool)
+    d32 = label.double().numpy()
+    want1 = ((Z > d32[:, None]) & off).sum(1); want2 = ((Z > d32[None, :]) & off).sum(0)
+    assert np.abs(r1.numpy() - want1).max() <= 1 and np.abs(r2.numpy() - want2).max() <= 1      # exact up to fp32-rounding ties
+    assert (r1.numpy() == want1).mean() > 0.99 and (r2.numpy() == want2).mean() > 0.99
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,Nc,K", [(300, 264, 200), (128, 256, 64)])
+def test_emulated_gemm_all_layouts_and_epilogues(tc, a_mn, b_mn, M, Nc, K):
+    tc.emu_set_sms(3)
+    rng = np.random.default_rng(M + Nc + K + 2 * a_mn + b_mn)
+    A, Av = _t(rng.standard_normal((K, M) if a_mn else (M, K)), torch.bfloat16)
+    B, Bv = _t(rng.standard_normal((K, Nc) if b_mn else (Nc, K)), torch.bfloat16)
+    ref = (Av.T if a_mn else Av) @ (Bv if b_mn else Bv.T)
+    acc_in = torch.from_numpy(rng.standard_normal((M, Nc)).astype(np.float32))
+    rs = torch.from_numpy(rng.random(M).astype(np.float32) + 0.5)
+    dot, dotv = _t(rng.standard_normal((M, Nc)), torch.bfloat16)
+    acc_out = torch.empty(M, Nc); out = torch.empty(M, Nc, dtype=torch.bfloat16)
+    ldd = (M + 127) // 128 * 128
+    slabs = 2 * ((Nc + 255) // 256)
+    rd = torch.zeros(slabs, ldd)
+    tc.emu_gemm(_p(A), A.stride(0), a_mn, _p(B), B.stride(0), b_mn, M, Nc, K, _p(acc_in), _p(acc_out), _p(out), Nc, _p(rs), _p(dot), Nc, _p(rd))
+    val = ref + acc_in.double().numpy()
+    assert np.allclose(acc_out.numpy(), val * rs.double().numpy()[:, None], rtol=1e-5, atol=1e-4)
+    assert np.allclose(out.double().numpy(), val * rs.double().numpy()[:, None], rtol=2.0 ** -7, atol=1e-2)
+    assert np.allclose(rd.double().numpy()[:, :M].sum(0), (val * dotv).sum(1), rtol=1e-4, atol=1e-3)      # row dots of the unscaled value

@@ -23,14 +23,34 @@ def available():
     return shutil.which("g++") is not None and os.path.exists(os.path.join(CUDA_INC, "cuda_bf16.h"))
 
 
+def prebuild():
+    """Compile all three emulation libraries (call once before spawning ranks)."""
+    _tc(); _vec(); _head()
+
+
+def _stamp():
+    """Cache key of a build: newest modification time of the kernel and emulation sources."""
+    dirs = [os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "oneprot_b200", "csrc"), os.path.join(ROOT, "include")]
+    return str(int(max(os.path.getmtime(os.path.join(d, f)) for d in dirs for f in os.listdir(d))))
+
+
 def _lib(name):
     if name not in _LIBS:
-        out = os.path.join(tempfile.mkdtemp(prefix="oneprot_emu_"), f"lib{name}.so")
+        cache = os.path.join(tempfile.gettempdir(), "oneprot_emu_cache_" + _stamp())
+        os.makedirs(cache, exist_ok=True)
+        out = os.path.join(cache, f"lib{name}.so")
+        if os.path.exists(out):                    # built by an earlier test / another rank
+            _LIBS[name] = C.CDLL(out)
+            if name == "clip_kernels_emu":
+                _LIBS[name].emu_s_scratch_floats.restype = C.c_size_t
+            return _LIBS[name]
+        tmp = out + f".{os.getpid()}.tmp"
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-w", "-I" + CUDA_INC, "-I" + os.path.join(ROOT, "tests", "emu"),
-               "-o", out, os.path.join(ROOT, "tests", "emu", name + ".cpp")]
+               "-o", tmp, os.path.join(ROOT, "tests", "emu", name + ".cpp")]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(p.stderr[-3000:])
+        os.replace(tmp, out)                       # atomic: concurrent ranks never load a half-written file
         lib = C.CDLL(out)
         if name == "clip_kernels_emu":
             lib.emu_s_scratch_floats.restype = C.c_size_t

@@ -149,13 +149,17 @@ def test_two_reference_path_equals_default_inside_the_window(fake):
 # ----------------------------------------------------------------------------------------------
 # world_size = 2, gloo
 # ----------------------------------------------------------------------------------------------
-def _worker(rank, world, port, results):
+def _worker(rank, world, port, results, provider="fake"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     from oneprot_b200 import clip_loss
-    clip_loss._KERNELS = fake_kernels
+    if provider == "emu":        # the library's own kernel source under the CPU emulation (tests/emu_kernels.py)
+        from tests import emu_kernels
+        clip_loss._KERNELS = emu_kernels
+    else:
+        clip_loss._KERNELS = fake_kernels
     g = load_golden("clip_dist_w2_n12_d32.npz")
     a = bf16_from_bits(g[f"r{rank}_A_bf16"])
     b = bf16_from_bits(g[f"r{rank}_B_bf16"])
@@ -187,11 +191,19 @@ def _worker(rank, world, port, results):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_conventions_vs_reference_golden():
+@pytest.mark.parametrize("provider,port", [("fake", 29733), ("emu", 29735)])
+def test_two_rank_gloo_conventions_vs_reference_golden(provider, port):
+    """provider "fake": float64 emulation of the kernel contracts; "emu": the real kernel source run by the
+    CPU emulation - host sharding logic AND kernels (row offsets, both modes, the two-reference path)."""
     world = 2
+    if provider == "emu":
+        from tests import emu_kernels
+        if not emu_kernels.available():
+            pytest.skip("g++ or the CUDA headers are not available")
+        emu_kernels.prebuild()
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, 29733, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, results, provider), nprocs=world, join=True)
     g = load_golden("clip_dist_w2_n12_d32.npz")
     for r in range(world):
         rec = results[r]

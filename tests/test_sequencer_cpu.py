@@ -307,3 +307,62 @@ def test_sequencer_argument_validation():
     assert lib.oneprot_seq_bwd_main(C.byref(q)) == 1
     assert lib.oneprot_seq_fwd_ws_bytes(0, 0) == 0
     assert lib.oneprot_seq_fwd_ws_bytes(4096, 32768) >= lib.oneprot_clip_fwd_scratch_bytes(4096, 32768) + 3 * 32768 * 4
+
+
+def _args(line):
+    return {k: v for k, v in (tok.split("=", 1) for tok in line.split()[1:] if "=" in tok)}
+
+
+def _addr(v):
+    return 0 if v == "(nil)" else int(v, 16)
+
+
+@pytest.mark.parametrize("n,d,panel_rows", [(512, 64, None), (1000, 72, 384), (640, 128, 256)])
+def test_sequencer_workspace_regions_do_not_overlap(streams, n, d, panel_rows):
+    """The launch-trace equality above cannot see whether two slices of the C side's single workspace
+    overlap; here the extents of every slice are rebuilt from the traced addresses and checked."""
+    from oneprot_b200 import _lib
+    lib = _lib.load()
+    A, B, scale = _pair(n, d)
+    N = n
+    ldw = (N + 63) // 64 * 64
+    pb = cl.DEFAULT_PANEL_BYTES if panel_rows is None else 2 * ldw * panel_rows
+    lines, _ = _run(streams, A, B, scale, _cfg(1, 0, False, False, pb, True), comm_mod.LocalComm(K))
+    cut = lines.index("---- backward")
+    fwd, bwd = lines[:cut], lines[cut + 1:]
+    # ---- forward: [finalize scratch 512 | sums 3N floats (padded) | forward scratch]
+    ms = [_args(ln) for ln in fwd if ln.startswith("memset")]
+    fs = _args(next(ln for ln in fwd if ln.startswith("fwd_sums")))
+    fin = _args(next(ln for ln in fwd if ln.startswith("loss_finalize")))
+    ws0 = _addr(ms[1]["p"])                                       # second memset = finalize scratch = workspace base
+    regions = [("fin", _addr(fin["scratch"]), 512), ("sums", _addr(fs["colsum"]), 3 * N * 4),
+               ("fscratch", _addr(fs["scratch"]), int(lib.oneprot_clip_fwd_scratch_bytes(n, N)))]
+    assert _addr(fs["rowsum"]) == _addr(fs["colsum"]) + 4 * N and _addr(fin["diag"]) == _addr(fs["colsum"]) + 8 * N
+    end = ws0 + int(lib.oneprot_seq_fwd_ws_bytes(n, N))
+    regions.sort(key=lambda r: r[1])
+    assert regions[0][1] >= ws0
+    for (na, a0, sz), (nb, b0, _) in zip(regions, regions[1:]):
+        assert a0 + sz <= b0, (na, nb)
+    assert regions[-1][1] + regions[-1][2] <= end
+    saved = _addr(fin["loss"])
+    assert _addr(fin["stats"]) == saved + 16 and _addr(fin["flag"]) == saved + 32
+    assert _addr(fin["inv_rs"]) == saved + 64 and _addr(fin["inv_cs"]) == saved + 64 + 4 * N
+    # ---- backward: [g placeholder 256 | g gathered 256 | wr dg sA wc sB | fp32 dB accumulator | Wz panel]
+    bw = _args(next(ln for ln in bwd if ln.startswith("bwd_weights")))
+    dz = [_args(ln) for ln in bwd if ln.startswith("dz_panel")]
+    gm = [_args(ln) for ln in bwd if ln.startswith("gemm")]
+    n_panels = len(dz)
+    rows_cap = max(int(a["rows"]) for a in dz)
+    regs = [("wr", _addr(bw["wr"]), 4 * n), ("dg", _addr(bw["dg"]), 4 * n), ("sA", _addr(bw["sA"]), 4 * n),
+            ("wc", _addr(bw["wc"]), 4 * N), ("sB", _addr(bw["sB"]), 4 * N), ("Wz", _addr(dz[0]["Wz"]), rows_cap * ldw * 2)]
+    accs = {_addr(a["acc_out"]) for a in gm if _addr(a["acc_out"])}
+    assert len(accs) == (1 if n_panels > 1 else 0)
+    if accs:
+        regs.append(("acc", accs.pop(), N * d * 4))
+    ws_b = min(r[1] for r in regs) - 512
+    endb = ws_b + int(lib.oneprot_seq_bwd_ws_bytes(n, N, d, 1, 1, pb))
+    regs.sort(key=lambda r: r[1])
+    for (na, a0, sz), (nb, b0, _) in zip(regs, regs[1:]):
+        assert a0 + sz <= b0, (na, nb)
+    assert regs[-1][1] + regs[-1][2] <= endb
+    assert all(_addr(a["Wz"]) == _addr(dz[0]["Wz"]) for a in dz) and all(int(a["ldw"]) == ldw for a in dz)

@@ -58,9 +58,15 @@ class _Stream:
         pass
 
 
-def install():
+def install(provider=None):
+    """provider "fake" (default): float64 emulation of the kernel contracts; "emu" (ONEPROT_CPU_SHIM=emu):
+    the library's own kernel source under the CPU emulation of tests/emu - slow, but the real kernels."""
+    import os
     from oneprot_b200 import clip_loss, epilogue, heads, retrieval
-    from tests import fake_kernels
+    if (provider or os.environ.get("ONEPROT_CPU_SHIM")) == "emu":
+        from tests import emu_kernels as fake_kernels
+    else:
+        from tests import fake_kernels
     for name in ("empty", "zeros", "ones", "full", "randn", "rand", "randint", "tensor", "arange", "eye", "empty_like", "zeros_like"):
         setattr(torch, name, _wrap_factory(getattr(torch, name)))
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()        # a new tensor, like a real host-to-device copy

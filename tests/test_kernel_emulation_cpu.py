@@ -358,9 +358,9 @@ def test_emulated_forward_uses_exact_maximum_when_the_norm_bound_is_loose(tc):
 
 
 @pytest.mark.parametrize("rows,N,d,grow0", [(300, 300, 72, 0), (128, 512, 64, 256), (130, 700, 128, 400)])
-@pytest.mark.parametrize("variant", ["dz", "dz_l2", "siglip"])
-def test_emulated_panel_kernels(tc, rows, N, d, grow0, variant):
-    tc.emu_set_sms(3)
+@pytest.mark.parametrize("variant,sms", [("dz", 3), ("dz", 1), ("dz_l2", 2), ("siglip", 3), ("siglip", 5)])
+def test_emulated_panel_kernels(tc, rows, N, d, grow0, variant, sms):
+    tc.emu_set_sms(sms)
     rng = np.random.default_rng(rows + N + d)
     A, Av = _unit(rng, rows, d)
     B, Bv = _unit(rng, N, d, 1 / 0.07)
@@ -431,7 +431,7 @@ def test_emulated_retrieval_ranks(tc, N, d):
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,Nc,K", [(300, 264, 200), (128, 256, 64)])
 def test_emulated_gemm_all_layouts_and_epilogues(tc, a_mn, b_mn, M, Nc, K):
-    tc.emu_set_sms(3)
+    tc.emu_set_sms(1 + (M + a_mn + 2 * b_mn) % 4)          # 1..4 persistent CTAs
     rng = np.random.default_rng(M + Nc + K + 2 * a_mn + b_mn)
     A, Av = _t(rng.standard_normal((K, M) if a_mn else (M, K)), torch.bfloat16)
     B, Bv = _t(rng.standard_normal((K, Nc) if b_mn else (Nc, K)), torch.bfloat16)

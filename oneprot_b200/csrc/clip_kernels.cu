@@ -17,13 +17,15 @@
 // plus the HBM-bound vector kernels and the multimem (NVLS) exchange kernels at the end.
 // ONEPROT_KERNEL_EMULATION (tests/emu): the kernel bodies of this file are also compiled for the CPU, with
 // ptx_emu.h supplying functional stand-ins for the TMA / mbarrier / tcgen05 / TMEM primitives of ptx.cuh.
+// With ONEPROT_HOST_EMULATION on top, the C ABI functions at the end are compiled for the CPU as well
+// (tests/emu/translate.py rewrites their <<<...>>> launches, host_emu.h stubs the CUDA runtime calls).
 #ifndef ONEPROT_KERNEL_EMULATION
 #include "ptx.cuh"
-#include "host_trace.h"
 #define OP_DYNAMIC_SMEM(name) extern __shared__ uint8_t name[]
 #else
 #include "ptx_emu.h"
 #endif
+#include "host_trace.h"
 #include "../../include/oneprot_clip.h"
 
 #include <cuda_bf16.h>
@@ -1065,7 +1067,7 @@ __global__ void mc_reduce_bf16_kernel(const uint4* src_mc, uint4* __restrict__ d
 #endif  // ONEPROT_KERNEL_EMULATION
 }  // namespace op
 
-#ifndef ONEPROT_KERNEL_EMULATION
+#if !defined(ONEPROT_KERNEL_EMULATION) || defined(ONEPROT_HOST_EMULATION)
 // ==========================================================================================
 // Host side: C ABI
 // ==========================================================================================
@@ -1565,6 +1567,7 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
   if (b_mn) rc = make_map(&mapB, B, Nc, K, ldb, 64); else rc = make_map(&mapB, B, K, Nc, ldb, op::BN);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifndef ONEPROT_KERNEL_EMULATION   // CTA pairs are not emulated
   static const bool use_pairs = getenv("ONEPROT_CG2") != nullptr;
   if (use_pairs && !dot_mat && (num_sms() % 2 == 0)) {
     // CTA-pair variant: per-CTA boxes are 128 rows for both operands
@@ -1588,6 +1591,7 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
     OP_CUDA(cudaGetLastError());
     return ONEPROT_OK;
   }
+#endif
   const int grid = std::min(num_sms(), p.nMb * p.nNb);
 #define LAUNCH_GEMM(AM, BMJ)                                                                       \
   do {                                                                                             \
@@ -1728,7 +1732,11 @@ int oneprot_mc_store(const void* src, void* dst_mc, size_t bytes, void* stream) 
   if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const size_t n16 = bytes / 16;
   const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+#ifndef ONEPROT_KERNEL_EMULATION   // multimem exchanges are not emulated
   op::mc_store_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst_mc), n16);
+#else
+  return fail(ONEPROT_ERR_DEVICE, "multimem exchanges are not available under the CPU emulation");
+#endif
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -1740,7 +1748,11 @@ int oneprot_mc_allreduce_f32(const float* src_mc, float* dst, int count, int op,
     return fail(ONEPROT_ERR_ARG, "mc_allreduce: count must be a multiple of 4, pointers 16-byte aligned");
   if (optrace::recording()) optrace::add("mc_allreduce_f32 src_mc=%p dst=%p count=%d op=%d st=%p", (const void*)src_mc, (void*)dst, count, op, stream);
   if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
+#ifndef ONEPROT_KERNEL_EMULATION   // multimem exchanges are not emulated
   op::mc_allreduce_kernel<<<cdiv(count / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src_mc, dst, count, op);
+#else
+  return fail(ONEPROT_ERR_DEVICE, "multimem exchanges are not available under the CPU emulation");
+#endif
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -1753,7 +1765,11 @@ int oneprot_mc_reduce_bf16(const void* src_mc, void* dst, size_t bytes, void* st
   if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
   const size_t n16 = bytes / 16;
   const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
+#ifndef ONEPROT_KERNEL_EMULATION   // multimem exchanges are not emulated
   op::mc_reduce_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src_mc), static_cast<uint4*>(dst), n16);
+#else
+  return fail(ONEPROT_ERR_DEVICE, "multimem exchanges are not available under the CPU emulation");
+#endif
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

@@ -6,7 +6,7 @@
 // All kernels: 16-byte vector loads (8 bf16 or 2 x 4 fp32 per lane), fp32 arithmetic, warp-shuffle
 // reductions, one warp per row where a row reduction is needed; column reductions (d gamma, d beta)
 // go through per-chunk partial slots that are summed in a fixed order (deterministic).
-#ifndef ONEPROT_KERNEL_EMULATION   // tests/emu: the kernel bodies below are also compiled for the CPU (SIMT emulation)
+#if !defined(ONEPROT_KERNEL_EMULATION) || defined(ONEPROT_HOST_EMULATION)   // tests/emu: the kernel bodies below are also compiled for the CPU
 #include "host_trace.h"
 #include "../../include/oneprot_clip.h"
 
@@ -471,7 +471,7 @@ __global__ void attnpool_bwd_x_kernel(const void* __restrict__ g, const float* _
 
 }  // namespace oph
 
-#ifndef ONEPROT_KERNEL_EMULATION
+#if !defined(ONEPROT_KERNEL_EMULATION) || defined(ONEPROT_HOST_EMULATION)
 namespace {
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

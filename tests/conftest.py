@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    if os.environ.get("ONEPROT_CPU_SHIM") in ("1", "emu"):      # tests/cpu_shim.py: GPU test files on CPU stand-ins (test hygiene only)
+    if os.environ.get("ONEPROT_CPU_SHIM") in ("1", "emu", "lib"):      # tests/cpu_shim.py: GPU test files on CPU stand-ins (test hygiene only)
         from tests import cpu_shim
         cpu_shim.install()
         return

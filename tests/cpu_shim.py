@@ -62,11 +62,28 @@ def install(provider=None):
     """provider "fake" (default): float64 emulation of the kernel contracts; "emu" (ONEPROT_CPU_SHIM=emu):
     the library's own kernel source under the CPU emulation of tests/emu - slow, but the real kernels."""
     import os
+    provider = provider or os.environ.get("ONEPROT_CPU_SHIM")
+    if provider == "lib":
+        # the WHOLE library compiled for the CPU (tests/emu/build_full_lib.py): the product's own kernels.py
+        # wrappers, ctypes signatures, C host functions (incl. the step sequencer) and kernel source all run
+        from tests.emu import build_full_lib
+        os.environ["ONEPROT_LIB"] = build_full_lib.build()
+        from oneprot_b200 import _lib, kernels
+        _lib.LIB_PATH = os.environ["ONEPROT_LIB"]
+        kernels._DRY = lambda: 0            # accept CPU tensors; "current stream" handle 0
+        _install_torch_stubs()
+        return
     from oneprot_b200 import clip_loss, epilogue, heads, retrieval
-    if (provider or os.environ.get("ONEPROT_CPU_SHIM")) == "emu":
+    if provider == "emu":
         from tests import emu_kernels as fake_kernels
     else:
         from tests import fake_kernels
+    _install_torch_stubs()
+    for mod in (clip_loss, epilogue, heads, retrieval):
+        mod._KERNELS = fake_kernels
+
+
+def _install_torch_stubs():
     for name in ("empty", "zeros", "ones", "full", "randn", "rand", "randint", "tensor", "arange", "eye", "empty_like", "zeros_like"):
         setattr(torch, name, _wrap_factory(getattr(torch, name)))
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()        # a new tensor, like a real host-to-device copy
@@ -91,5 +108,3 @@ def install(provider=None):
     torch.cuda.max_memory_allocated = lambda *a, **k: 0
     torch.cuda.reset_peak_memory_stats = lambda *a, **k: None
     torch.cuda.empty_cache = lambda: None
-    for mod in (clip_loss, epilogue, heads, retrieval):
-        mod._KERNELS = fake_kernels

@@ -105,7 +105,7 @@ int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int
 /* Loss value + softmax normalisers from complete sums (all length N, global index order):
  *   loss_out[0] = this rank's return value (MODE_GLOBAL: mean over all N; MODE_LOCAL: mean over
  *   rows/cols [row_offset, row_offset+n)), fp32;  inv_rowsum/inv_colsum[k] = 1/sum;
- *   flag[0] |= 1 if any sum left the validated fp32 window (result then not trustworthy).
+ *   flag[0] |= 1 if any sum left the validated fp32 window; loss_out[0] is then NaN (not trustworthy).
  * scratch: ONEPROT_FINALIZE_SCRATCH_BYTES bytes, 8-byte aligned, zero-initialised ONCE by the
  * caller (the kernel leaves it ready for the next call).
  * Replaces the nll half of F.cross_entropy and the /2 (loss.py:109-112). */

@@ -110,6 +110,7 @@ inline uint32_t float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); ret
 #define __shfl_xor_sync(mask, v, m) emu::shfl_xor((v), (m))
 #define __uint_as_float(u) emu::uint_as_float(u)
 #define __float_as_uint(f) emu::float_as_uint(f)
+#define __int_as_float(i) emu::uint_as_float(static_cast<uint32_t>(i))
 #define __expf(x) expf(x)
 #define __log2f(x) log2f(x)
 #define rsqrtf(x) (1.0f / sqrtf(x))

@@ -85,6 +85,7 @@ def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_d
         or (rowsum_all < 1e-27).any() or (colsum_all < 1e-27).any()
     if bool(bad):
         flag[0] = int(flag[0]) | 1
+        loss_out[0] = float("nan")          # outside the validated window the value is returned as NaN
 
 
 def rowcol_max(A, B_all, scale_dev, rowmax, colmax, scratch=None):

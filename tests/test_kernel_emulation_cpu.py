@@ -237,7 +237,7 @@ def test_loss_finalize_and_bwd_weights(vec, mode, with_refs):
     colsum[5] = 0.0
     vec.emu_loss_finalize(_p(rowsum), _p(colsum), _p(diag), N, n, off, mode, _p(scale), _p(stats), _p(loss), _p(inv_rs), _p(inv_cs),
                           _p(flag), _p(scratch), C.c_void_p(counter.data_ptr()), _p(rr), _p(cr))
-    assert flag.item() == 1                              # a flushed sum raises the hazard flag
+    assert flag.item() == 1 and np.isnan(loss.item())    # a flushed sum raises the hazard flag and the value becomes NaN
     # backward weights of both conventions
     world, rank = 2, 1
     gvec = torch.tensor([1.0, 1.5]); wr = torch.empty(n); wc = torch.empty(N); dg = torch.empty(n); sa = torch.empty(n); sb = torch.empty(N)

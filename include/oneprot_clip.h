@@ -151,7 +151,9 @@ int oneprot_retrieval_ranks(const void* S, const void* M, int N, int d, const fl
  *                            as the ClipLoss forward; scratch of oneprot_clip_fwd_scratch_bytes(n, N))
  *   oneprot_siglip_finalize  loss_out[0] = (ln2 sum_i rowsum[i] - sum_i (logit_scale diag[i] + bias)) / n
  *   oneprot_siglip_dz_panel  Wz_ij = wr[i] sigma(z_ij) - [grow0 + i == j] dg[i]  (bf16 panel, as
- *                            oneprot_clip_dz_panel; dL/dz_ij = (g / n) (sigma(z_ij) - [i == j]))
+ *                            oneprot_clip_dz_panel; dL/dz_ij = (g / n) (sigma(z_ij) - [i == j])).
+ *                            sig_rowsum (optional, with scratch of oneprot_siglip_dz_scratch_bytes):
+ *                            sig_rowsum[i] = sum_j sigma(z_ij), for d logit_bias = (g / n) (sum sigma - n)
  * The ring of neighbour exchanges of the reference (loss.py:258-309) becomes the all-gather of the
  * second operand + reduce-scatter of its partial gradient that the ClipLoss path already uses.
  * bias_dev may be NULL (no logit_bias). */
@@ -159,8 +161,10 @@ int oneprot_siglip_fwd(const void* A, const void* B_all, int n, int N, int d, co
                        float* rowsum, void* scratch, size_t scratch_bytes, void* stream);
 int oneprot_siglip_finalize(const float* rowsum, const float* diag, int n, const float* scale_dev, const float* bias_dev,
                             float* loss_out, void* stream);
+size_t oneprot_siglip_dz_scratch_bytes(int rows, int N);
 int oneprot_siglip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0, const float* scale_dev,
-                            const float* bias_dev, const float* wr, const float* dg, void* Wz, int ldw, void* stream);
+                            const float* bias_dev, const float* wr, const float* dg, void* Wz, int ldw, float* sig_rowsum,
+                            void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- backward ----------------------------------------------------------------------------- */
 

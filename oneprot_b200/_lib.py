@@ -80,7 +80,8 @@ SIGNATURES = {
     "oneprot_split_fp32": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
     "oneprot_siglip_fwd": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
     "oneprot_siglip_finalize": (_i, [_fp, _fp, _i, _fp, _fp, _fp, _vp]),
-    "oneprot_siglip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
+    "oneprot_siglip_dz_scratch_bytes": (_sz, [_i, _i]),
+    "oneprot_siglip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _i, _fp, _vp, _sz, _vp]),
     # projection-head row kernels (csrc/head_kernels.cu)
     "oneprot_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _f, _vp]),
     "oneprot_layernorm_bwd_scratch_bytes": (_sz, [_i, _i]),

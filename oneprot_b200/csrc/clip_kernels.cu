@@ -579,7 +579,12 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               if (EPI == EPI_SDZ) {
                 // sigma(z) = 1 / (1 + 2^-x): 0 for x -> -inf (2^-x = inf), 1 for x -> +inf
 #pragma unroll
-                for (int u = 0; u < 4; ++u) dz[u] = __fdividef(wr_i, 1.f + ex2(-fmaf(v[k4 * 4 + u], c, negG)));
+                for (int u = 0; u < 4; ++u) {
+                  const float sg = __fdividef(1.f, 1.f + ex2(-fmaf(v[k4 * 4 + u], c, negG)));
+                  dz[u] = wr_i * sg;
+                  // optional row sums of sigma (d logit_bias = (g / n) (sum sigma - n)): only valid entries count
+                  if (p.rowpart) rsum += (rowok && (j0 + cc * 32 + k4 * 4 + u < p.N)) ? sg : 0.f;
+                }
               } else {
                 const float4 w4 = ld_shared_f4(colvec_s + (h * 128 + cc * 32 + k4 * 4) * 4);
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -616,7 +621,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
           }
         }
-        if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD) {
+        if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD || (EPI == EPI_SDZ && p.rowpart)) {
           p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1501,21 +1506,32 @@ int oneprot_siglip_finalize(const float* rowsum, const float* diag, int n, const
   return ONEPROT_OK;
 }
 
+size_t oneprot_siglip_dz_scratch_bytes(int rows, int N) {
+  op::SParams p{};
+  s_schedule(rows, N, 1, p);
+  return sizeof(float) * 2 * static_cast<size_t>(p.nJ) * p.nI * op::BM;
+}
+
 int oneprot_siglip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0, const float* scale_dev,
-                            const float* bias_dev, const float* wr, const float* dg, void* Wz, int ldw, void* stream) {
+                            const float* bias_dev, const float* wr, const float* dg, void* Wz, int ldw, float* sig_rowsum,
+                            void* scratch, size_t scratch_bytes, void* stream) {
   if (!A_rows || !B_all || !scale_dev || !wr || !dg || !Wz) return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: null pointer");
+  if (sig_rowsum && (!scratch || scratch_bytes < oneprot_siglip_dz_scratch_bytes(rows, N)))
+    return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: sig_rowsum needs scratch of oneprot_siglip_dz_scratch_bytes(rows, N)");
   if (rows <= 0 || N <= 0 || d <= 0 || d % 8 || ldw < N || ldw % 8) return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: bad sizes");
   if (reinterpret_cast<uintptr_t>(Wz) & 15) return fail(ONEPROT_ERR_ARG, "siglip_dz_panel: Wz must be 16-byte aligned");
   if (optrace::recording())
-    optrace::add("siglip_dz_panel A=%p B=%p rows=%d N=%d d=%d grow0=%d scale=%p bias=%p wr=%p dg=%p Wz=%p ldw=%d st=%p", A_rows, B_all, rows,
-                 N, d, grow0, (const void*)scale_dev, (const void*)bias_dev, (const void*)wr, (const void*)dg, Wz, ldw, stream);
-  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
+    optrace::add("siglip_dz_panel A=%p B=%p rows=%d N=%d d=%d grow0=%d scale=%p bias=%p wr=%p dg=%p Wz=%p ldw=%d sig_rowsum=%p scratch=%p st=%p",
+                 A_rows, B_all, rows, N, d, grow0, (const void*)scale_dev, (const void*)bias_dev, (const void*)wr, (const void*)dg, Wz, ldw,
+                 (void*)sig_rowsum, scratch, stream);
+  if (optrace::dry()) { g_launches += sig_rowsum ? 2 : 1; return ONEPROT_OK; }
   op::SParams p{};
   s_schedule(rows, N, 1, p);
   p.rows = rows; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = grow0;
   p.scale = scale_dev; p.wc = bias_dev;
   p.wr = wr; p.dg = dg;
   p.Wz = static_cast<__nv_bfloat16*>(Wz); p.ldw = ldw;
+  if (sig_rowsum) { p.rowpart = static_cast<float*>(scratch); p.ldr = p.nI * op::BM; }
   CUtensorMap mapA, mapB, mapW;
   int rc;
   if ((rc = make_map(&mapA, A_rows, d, rows, d, op::BM))) return rc;
@@ -1526,6 +1542,10 @@ int oneprot_siglip_dz_panel(const void* A_rows, const void* B_all, int rows, int
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
   op::clip_s_kernel<op::EPI_SDZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
   ++g_launches;
+  if (sig_rowsum) {
+    op::reduce_slots_kernel<<<cdiv(rows, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(p.rowpart, 2 * p.nJ, p.ldr, rows, sig_rowsum);
+    ++g_launches;
+  }
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
 }

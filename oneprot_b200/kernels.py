@@ -243,16 +243,22 @@ def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
                                               _stream()), "oneprot_siglip_finalize")
 
 
-def siglip_dz_panel(A_rows, B_all, grow0: int, scale_dev, bias_dev, wr, dg, Wz):
-    """Wz[i, j] = wr[i] sigma(z_ij) - [grow0 + i == j] dg[i]  (bf16 panel, rows x ldw)."""
-    _need_cuda(A_rows, B_all, scale_dev, bias_dev, wr, dg, Wz)
+def siglip_dz_panel(A_rows, B_all, grow0: int, scale_dev, bias_dev, wr, dg, Wz, sig_rowsum=None):
+    """Wz[i, j] = wr[i] sigma(z_ij) - [grow0 + i == j] dg[i]  (bf16 panel, rows x ldw);
+    sig_rowsum (optional, fp32[rows]): sum_j sigma(z_ij)."""
+    _need_cuda(A_rows, B_all, scale_dev, bias_dev, wr, dg, Wz, sig_rowsum)
     _need(A_rows, torch.bfloat16, "A_rows"); _need(B_all, torch.bfloat16, "B_all"); _need(Wz, torch.bfloat16, "Wz")
     rows, d = A_rows.shape
     N = B_all.shape[0]
     if Wz.shape[0] < rows:
         raise ValueError("Wz panel has fewer rows than A_rows")
+    scratch, nbytes = None, 0
+    if sig_rowsum is not None:
+        nbytes = int(_lib.load().oneprot_siglip_dz_scratch_bytes(rows, N))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=A_rows.device)
     check(_lib.load().oneprot_siglip_dz_panel(ptr(A_rows), ptr(B_all), rows, N, d, grow0, ptr(scale_dev), ptr(bias_dev), ptr(wr),
-                                              ptr(dg), ptr(Wz), Wz.stride(0), _stream()), "oneprot_siglip_dz_panel")
+                                              ptr(dg), ptr(Wz), Wz.stride(0), ptr(sig_rowsum), ptr(scratch), nbytes, _stream()),
+          "oneprot_siglip_dz_panel")
 
 
 def gemm_rowdot_scratch_floats(M: int, Nc: int) -> int:

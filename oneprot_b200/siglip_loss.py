@@ -16,9 +16,11 @@ operand; the backward recomputes the panel into the bounded bf16 dL/dZ workspace
 dB = Wz^T A is reduce-scattered - which is what the autograd of the ring (loss.py:169-201) adds up.
 ``bidir`` only changes the reference's hop schedule, not the result; it is accepted and ignored.
 
-Scope of this first version: ``logit_scale`` / ``logit_bias`` as Python floats or tensors WITHOUT
-gradient (OneProt calls the loss with the defaults, oneprot_module.py:100); asking for their gradient
-raises.  Exchanges go through torch.distributed (all-gather / reduce-scatter).  No eager fallback.
+``logit_scale`` / ``logit_bias`` may be Python floats or 0-dim tensors; tensors that require grad get their
+gradient like in the reference (d scale = (1/scale) sum_i <a_i, dA_i>, the row-dot of the gradient that is
+computed anyway; d bias = (g/n) (sum_ij sigma(z_ij) - n) from row sums the panel kernel adds up on the
+side).  As in the reference each rank's scalar gradients are those of ITS loss (DDP all-reduces
+parameters later).  Exchanges go through torch.distributed (all-gather / reduce-scatter).  No eager fallback.
 """
 from __future__ import annotations
 
@@ -40,24 +42,29 @@ def _K():
     return _cl._KERNELS          # the kernel provider of the ClipLoss path (tests swap it there)
 
 
-def _scalar_dev(v, device) -> Optional[torch.Tensor]:
+def _scalar_in(v, device) -> Optional[torch.Tensor]:
+    """float -> cached 1-element device tensor (no grad); tensor -> itself (autograd input)."""
     if v is None:
         return None
     if torch.is_tensor(v):
         if v.numel() != 1:
             raise ValueError("logit_scale / logit_bias must be scalars")
-        if v.requires_grad and torch.is_grad_enabled():
-            raise NotImplementedError("SigLipLoss on B200: gradients w.r.t. logit_scale / logit_bias are not built yet")
-        return v.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+        return v
     return _cl._float_scale_on(device, float(v))
+
+
+def _dev1(t, device):
+    return None if t is None else t.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
 
 
 class _SigLipFunction(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, A, B, scale_dev, bias_dev, cfg):
+    def forward(ctx, A, B, scale_t, bias_t, cfg):
         with _K().stream_scope():
             K = _K()
+            scale_dev, bias_dev = _dev1(scale_t, A.device), _dev1(bias_t, A.device)
+            ctx.scalar_meta = [(t.dtype, t.device, t.shape) if t is not None else None for t in (scale_t, bias_t)]
             W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
             ops = _cl._Operands(A, B)
             n, off = ops.n, rank * ops.n
@@ -86,11 +93,13 @@ class _SigLipFunction(torch.autograd.Function):
             N, off = W * n, rank * n
             dev = ops.A.device
             need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            need_s = ctx.needs_input_grad[2]
+            need_bias = ctx.bias_dev is not None and ctx.needs_input_grad[3]
             g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
                    else g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1))
             # dL/dz_ij = (g / n) (sigma(z_ij) - [i == j]); the panel carries the logit_scale of d z / d <a, b> as well
             coef = (ctx.scale_dev * g32 / n).expand(n).contiguous()
-            want_a, want_b = bool(need_a), bool(need_b or W > 1)       # with W > 1 every rank enters the reduce-scatter
+            want_a, want_b = bool(need_a or need_s), bool(need_b or W > 1)   # with W > 1 every rank enters the reduce-scatter
             grad_dtype = torch.float32 if ops.split else torch.bfloat16
             ldw = (N + 63) // 64 * 64
             rows_cap = max(128, (cfg["panel_bytes"] // (2 * ldw)) // 128 * 128)
@@ -110,9 +119,11 @@ class _SigLipFunction(torch.autograd.Function):
             dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
             chain_b = _cl._GemmChain(N, d, dBp, None, len(panels) * n_bp) if want_b else None
             b_pieces = ops.b_pieces(B_all)
+            sig = torch.empty(n, dtype=torch.float32, device=dev) if need_bias else None     # row sums of sigma(z)
             for r0, rows in panels:
                 A_rows = ops.A[r0:r0 + rows]
-                K.siglip_dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.bias_dev, coef[r0:r0 + rows], coef[r0:r0 + rows], Wz)
+                K.siglip_dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.bias_dev, coef[r0:r0 + rows], coef[r0:r0 + rows], Wz,
+                                  sig_rowsum=None if sig is None else sig[r0:r0 + rows])
                 Wp = Wz[:rows]
                 if want_b:
                     for Ap in ops.a_pieces(A_rows):
@@ -123,7 +134,16 @@ class _SigLipFunction(torch.autograd.Function):
                         chain_a.add(Wp, False, Bp, True, N)
             if want_b and W > 1:
                 dBp = _reduce_scatter_rows(dBp, rank, W, group)
-            return _cl._finish_grad(dA, ops, need_a), _cl._finish_grad(dBp, ops, need_b), None, None, None
+            grad_s = grad_bias = None
+            if need_s:      # d loss / d scale = sum_ij dL/dz_ij <a_i, b_j> = (1 / scale) sum_i <a_i, dA_i>
+                sdt, sdev, sshape = ctx.scalar_meta[0]
+                grad_s = (_cl._rowdot_sum(ops.a_head(ops.A), dA) / ctx.scale_dev).reshape(sshape).to(device=sdev, dtype=sdt)
+            if need_bias:   # d loss / d bias = sum_ij dL/dz_ij = (g / n) (sum_ij sigma(z_ij) - n)
+                bdt, bdev, bshape = ctx.scalar_meta[1]
+                tot = torch.empty(1, dtype=torch.float32, device=dev)
+                K.sum_f32(sig, tot)
+                grad_bias = ((tot - n) * g32 / n).reshape(bshape).to(device=bdev, dtype=bdt)
+            return _cl._finish_grad(dA, ops, need_a), _cl._finish_grad(dBp, ops, need_b), grad_s, grad_bias, None
 
 
 class SigLipLoss(nn.Module):
@@ -177,6 +197,6 @@ class SigLipLoss(nn.Module):
                 raise RuntimeError("SigLipLoss world_size does not match the process group")
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, loss_dtype=self.loss_dtype,
                    panel_bytes=self.panel_bytes)
-        loss, loss32 = _SigLipFunction.apply(A, B, _scalar_dev(logit_scale, A.device), _scalar_dev(logit_bias, A.device), cfg)
+        loss, loss32 = _SigLipFunction.apply(A, B, _scalar_in(logit_scale, A.device), _scalar_in(logit_bias, A.device), cfg)
         self.last_loss_fp32 = loss32
         return {"contrastive_loss": loss} if output_dict else loss

@@ -257,6 +257,8 @@ class SigLipResult:
     loss: float          # value returned on this rank (loss.py:256-311)
     dA: np.ndarray       # gradient w.r.t. this rank's first positional feature tensor
     dB: np.ndarray       # gradient w.r.t. this rank's second positional feature tensor (ring backward: all ranks' losses)
+    dscale: float = 0.0  # gradient of THIS rank's loss w.r.t. logit_scale (times its upstream gradient)
+    dbias: float = 0.0   # ... w.r.t. logit_bias
 
 
 def siglip_closed_form(A_all: np.ndarray, B_all: np.ndarray, scale: float, bias: float = 0.0, *, rank: int = 0,
@@ -278,4 +280,5 @@ def siglip_closed_form(A_all: np.ndarray, B_all: np.ndarray, scale: float, bias:
     rows = slice(rank * n, (rank + 1) * n)
     dZ = (1.0 / (1.0 + np.exp(-Z)) - np.eye(N)) / n                         # d loss_r / d z_ij for i in rank r
     dZ = dZ * np.repeat(g, n)[:, None]
-    return SigLipResult(loss=float(lossmat[rows].sum() / n), dA=scale * (dZ[rows] @ B_all), dB=scale * (dZ[:, rows].T @ A_all))
+    return SigLipResult(loss=float(lossmat[rows].sum() / n), dA=scale * (dZ[rows] @ B_all), dB=scale * (dZ[:, rows].T @ A_all),
+                        dscale=float((dZ[rows] * (A_all[rows] @ B_all.T)).sum()), dbias=float(dZ[rows].sum()))

@@ -155,10 +155,13 @@ def _siglip_worker(rank, world, port, n, d, bidir, results):
     a, b = synthetic_pair(n, d, seed=777, pair_id=0, rank=rank, correlated=True, temperature_into_b=False, dtype="bf16")
     A = a.double().requires_grad_(True)
     B = b.double().requires_grad_(True)
-    loss = SigLipLoss(rank=rank, world_size=world, bidir=bidir)(A, B, 10.0, -10.0)
+    st = torch.tensor(10.0, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(-10.0, dtype=torch.float64, requires_grad=True)
+    loss = SigLipLoss(rank=rank, world_size=world, bidir=bidir)(A, B, st, bt)
     (loss * (1.0 + 0.5 * rank)).backward()
     results[rank] = {"A_bf16": bf16_bits(a), "B_bf16": bf16_bits(b), "loss": np.float64(loss.item()),
-                     "dA": A.grad.numpy().copy(), "dB": B.grad.numpy().copy()}
+                     "dA": A.grad.numpy().copy(), "dB": B.grad.numpy().copy(),
+                     "dscale": np.float64(st.grad.item()), "dbias": np.float64(bt.grad.item())}
     dist.barrier()
     dist.destroy_process_group()
 
@@ -175,8 +178,12 @@ def siglip_cases():
         a, b = synthetic_pair(n, d, seed=2468, pair_id=0, rank=0, correlated=True, temperature_into_b=(tag == "train"), dtype="bf16")
         A = a.double().requires_grad_(True)
         B = b.double().requires_grad_(True)
-        loss = SigLipLoss(world_size=1)(A, B, scale, bias)
+        st = torch.tensor(float(scale), dtype=torch.float64, requires_grad=True)
+        bt = None if bias is None else torch.tensor(float(bias), dtype=torch.float64, requires_grad=True)
+        loss = SigLipLoss(world_size=1)(A, B, st, bt)
         loss.backward()
+        rec[f"{tag}_dscale"] = np.float64(st.grad.item())
+        rec[f"{tag}_dbias"] = np.float64(0.0 if bt is None else bt.grad.item())
         rec.update({f"{tag}_A_bf16": bf16_bits(a), f"{tag}_B_bf16": bf16_bits(b), f"{tag}_scale": np.float64(scale),
                     f"{tag}_bias": np.float64(0.0 if bias is None else bias), f"{tag}_has_bias": np.bool_(bias is not None),
                     f"{tag}_loss": np.float64(loss.item()), f"{tag}_dA": A.grad.numpy().copy(), f"{tag}_dB": B.grad.numpy().copy()})

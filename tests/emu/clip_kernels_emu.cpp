@@ -122,9 +122,10 @@ void emu_siglip_fwd(const void* A, const void* B, int n, int N, int d, const flo
 }
 
 void emu_siglip_dz(const void* A_rows, const void* B, int rows, int N, int d, int grow0, const float* scale, const float* bias,
-                   const float* wr, const float* dg, void* Wz, int ldw) {
+                   const float* wr, const float* dg, void* Wz, int ldw, float* sig_rowsum, float* scratch) {
   op::SParams p{};
-  s_common(p, rows, N, d, 1, nullptr);
+  s_common(p, rows, N, d, 1, sig_rowsum ? scratch : nullptr);
+  if (!sig_rowsum) p.rowpart = nullptr;
   p.grow0 = grow0; p.scale = scale; p.wc = bias; p.wr = wr; p.dg = dg;
   p.Wz = static_cast<__nv_bfloat16*>(Wz); p.ldw = ldw;
   CUtensorMap mA, mB, mW;
@@ -132,6 +133,7 @@ void emu_siglip_dz(const void* A_rows, const void* B, int rows, int N, int d, in
   make_map(&mB, B, d, N, d, op::BN);
   make_map(&mW, Wz, N, rows, ldw, op::BM);
   run_s<op::EPI_SDZ>(mA, mB, mW, p);
+  if (sig_rowsum) reduce(p.rowpart, 2 * p.nJ, p.ldr, rows, sig_rowsum, false);
 }
 
 // oneprot_gemm_bf16_ex

@@ -212,10 +212,12 @@ def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
     _vec().emu_siglip_finalize(_p(rowsum), _p(diag), rowsum.numel(), _p(scale_dev), _p(bias_dev), _p(loss_out))
 
 
-def siglip_dz_panel(A_rows, B_all, grow0, scale_dev, bias_dev, wr, dg, Wz):
+def siglip_dz_panel(A_rows, B_all, grow0, scale_dev, bias_dev, wr, dg, Wz, sig_rowsum=None):
     CALLS.append("siglip_dz_panel")
     rows, d = A_rows.shape
-    _tc().emu_siglip_dz(_p(A_rows), _p(B_all), rows, B_all.shape[0], d, grow0, _p(scale_dev), _p(bias_dev), _p(wr), _p(dg), _p(Wz), Wz.stride(0))
+    s = _scratch(rows, B_all.shape[0])
+    _tc().emu_siglip_dz(_p(A_rows), _p(B_all), rows, B_all.shape[0], d, grow0, _p(scale_dev), _p(bias_dev), _p(wr), _p(dg), _p(Wz), Wz.stride(0),
+                        _p(sig_rowsum), _p(s))
 
 
 # ---- epilogue + heads ------------------------------------------------------------------------------

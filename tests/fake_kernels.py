@@ -351,11 +351,13 @@ def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
     loss_out[0] = float((math.log(2.0) * rowsum.double().sum() - (float(scale_dev[0]) * diag.double() + b).sum()) / n)
 
 
-def siglip_dz_panel(A_rows, B_all, grow0, scale_dev, bias_dev, wr, dg, Wz):
+def siglip_dz_panel(A_rows, B_all, grow0, scale_dev, bias_dev, wr, dg, Wz, sig_rowsum=None):
     CALLS.append("siglip_dz_panel")
     b = 0.0 if bias_dev is None else float(bias_dev[0])
     rows, N = A_rows.shape[0], B_all.shape[0]
     z = float(scale_dev[0]) * (A_rows.double() @ B_all.double().T) + b
+    if sig_rowsum is not None:
+        sig_rowsum.copy_(torch.sigmoid(z).sum(1).float())
     Wd = torch.sigmoid(z) * wr.double()[:, None]
     idx = torch.arange(rows)
     Wd[idx, grow0 + idx] -= dg.double()

@@ -26,9 +26,14 @@ def test_siglip_golden_single_gpu(tag, dtype):
     B = b.to(dtype).cuda().requires_grad_(True)
     bias = float(g[f"{tag}_bias"]) if bool(g[f"{tag}_has_bias"]) else None
     m = SigLipLoss()
-    loss = m(A, B, float(g[f"{tag}_scale"]), bias)
+    st = torch.tensor(float(g[f"{tag}_scale"]), device="cuda", requires_grad=True)
+    bt = None if bias is None else torch.tensor(bias, device="cuda", requires_grad=True)
+    loss = m(A, B, st, bt)
     assert loss.dtype == dtype
     loss.backward()
+    assert abs(st.grad.item() - float(g[f"{tag}_dscale"])) < 2e-2 * abs(float(g[f"{tag}_dscale"])) + 1e-6
+    if bt is not None:
+        assert abs(bt.grad.item() - float(g[f"{tag}_dbias"])) < 2e-3 * abs(float(g[f"{tag}_dbias"])) + 1e-6
     assert rel_err(m.last_loss_fp32.item(), g[f"{tag}_loss"]) < (1e-3 if dtype == torch.bfloat16 else 1e-5)
     for got, want in ((A.grad, g[f"{tag}_dA"]), (B.grad, g[f"{tag}_dB"])):
         assert cosine(got.double().cpu().numpy(), want) >= 0.9999

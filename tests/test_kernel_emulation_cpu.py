@@ -373,7 +373,9 @@ def test_emulated_panel_kernels(tc, rows, N, d, grow0, variant, sms):
     idx = np.arange(rows)
     if variant == "siglip":
         bias = torch.tensor([-3.0])
-        tc.emu_siglip_dz(_p(A), _p(B), rows, N, d, grow0, _p(scale), _p(bias), _p(wr), _p(dg), _p(Wz), ldw)
+        sig = torch.empty(rows); scr = torch.zeros(tc.emu_s_scratch_floats(rows, N))
+        tc.emu_siglip_dz(_p(A), _p(B), rows, N, d, grow0, _p(scale), _p(bias), _p(wr), _p(dg), _p(Wz), ldw, _p(sig), _p(scr))
+        assert np.allclose(sig.numpy(), (1 / (1 + np.exp(-(Z - 3.0)))).sum(1), rtol=1e-5)        # row sums of sigma (d logit_bias)
         want = wr.double().numpy()[:, None] / (1 + np.exp(-(Z - 3.0)))
     else:
         tc.emu_dz_panel(_p(A), _p(B), rows, N, d, grow0, _p(scale), _p(stats), _p(wr), _p(wc), _p(dg), _p(Wz), ldw, int(variant == "dz_l2"))

@@ -4,7 +4,10 @@ exists.  Test infrastructure (started by tests/test_bench_cpu.py in a subprocess
 events / pinned memory are stubs, the kernels are the float64 emulation of tests/fake_kernels.py and
 the problem is tiny (ONEPROT_BENCH_N / _D).  The numbers it prints mean nothing.
 
-    python tests/bench_cpu_harness.py [pipelined|fallback]
+    python tests/bench_cpu_harness.py [pipelined|fallback|lib-pipelined|lib-fallback]
+
+The lib-* modes replace the float64 stand-ins by the library itself compiled for the CPU (tests/emu), so
+bench.py's calls go through the real kernels.py wrappers, ctypes signatures and C entry points.
 """
 import contextlib
 import os
@@ -78,9 +81,17 @@ torch.device = _Dev()
 
 from oneprot_b200 import clip_loss, kernels  # noqa: E402
 
-clip_loss._KERNELS = fake_kernels
-for name in ("rowstats", "fwd_sums", "dz_panel", "gemm_bf16", "loss_finalize", "bwd_weights"):
-    setattr(kernels, name, getattr(fake_kernels, name))
+if mode.startswith("lib"):
+    # the product's own wrappers and C host code over the library compiled for the CPU (tests/emu/build_full_lib.py)
+    from tests.emu import build_full_lib
+    from oneprot_b200 import _lib
+    os.environ["ONEPROT_LIB"] = _lib.LIB_PATH = build_full_lib.build()
+    kernels._DRY = lambda: 0
+    mode = mode[len("lib-"):] or "fallback"
+else:
+    clip_loss._KERNELS = fake_kernels
+    for name in ("rowstats", "fwd_sums", "dz_panel", "gemm_bf16", "loss_finalize", "bwd_weights"):
+        setattr(kernels, name, getattr(fake_kernels, name))
 
 if mode == "pipelined":
     # let the prefetcher believe it stages into CUDA memory

@@ -41,6 +41,20 @@ def test_gpu_arm_control_flow_prints_one_line(mode):
         assert e["mode"].startswith("serial") and "pipelined leg failed" in e["mode"]
 
 
+def test_gpu_arm_over_the_emulated_library():
+    """bench.py through the product's own wrappers / C entry points (library compiled for the CPU): the launch count the
+    line claims is the library's own counter, 10 kernels per step."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_cpu_harness.py"), "lib-pipelined"], capture_output=True,
+                       text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = _json_lines(p.stdout)
+    assert len(lines) == 1, p.stdout
+    ln = lines[0]
+    assert KEYS <= set(ln) and ln["gpu_launches"] == 30 and ln["e2e"]["mode"].startswith("pipelined")
+    assert len(ln["roofline"]["kernels"]) == 4 and abs(ln["roofline"]["step"]["executed_over_algorithmic"] - 4 / 3) < 1e-9
+    assert 3.0 < ln["config"]["loss"] < 6.0
+
+
 def test_two_rank_control_flow_over_gloo():
     """The driver's multi-GPU launch line with 2 ranks: rank 0 prints the one line, both exit 0."""
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",

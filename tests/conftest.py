@@ -26,6 +26,15 @@ def pytest_collection_modifyitems(config, items):
     except Exception:  # pragma: no cover
         has_gpu = False
     if has_gpu:
+        # a device-side hang must end the test process instead of wedging the box: the kernels trap after
+        # ONEPROT_WAIT_TRAP_CYCLES on their own, this bounds everything else (collectives, host waits)
+        try:
+            import pytest_timeout  # noqa: F401
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(900, method="thread"))
+        except ImportError:
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -195,6 +195,18 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
                           const float* scale_dev, const float* stats, const float* wr, const float* wc,
                           const float* dg, void* Wz, int ldw, void* stream);
 
+/* Stored-exponentials variant of the pair above (opt-in; trades n x lde x 2 bytes of HBM for the second
+ * pass over the logits): oneprot_clip_fwd_sums_keep is oneprot_clip_fwd_sums_ag (ag may be NULL) that also
+ * writes E[i][j] = 2^(x_ij - G) as bf16 (n rows, row pitch lde >= N, multiple of 8, 16-byte aligned; E == NULL:
+ * plain forward); oneprot_clip_dz_from_exp then turns rows [r0, r0 + rows) of E into the dL/dZ panel IN PLACE,
+ * Wz_ij = E_ij (wr[i] + wc[j]) - [grow0 + i == j] dg[i] (E points at row r0, wr / dg at element r0) - the
+ * same panel oneprot_clip_dz_panel writes, up to one more bf16 rounding of e_ij.  HBM-bound, no tensor cores. */
+int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
+                               float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
+                               size_t scratch_bytes, void* E, int lde, void* stream);
+int oneprot_clip_dz_from_exp(void* E, int rows, int N, int lde, int grow0, const float* wr, const float* wc,
+                             const float* dg, void* stream);
+
 /* C[M x Nc] = op(A) * op(B) with bf16 operands, fp32 accumulation in TMEM.
  *   a_mn = 0: A is M x K row-major (lda >= K);  a_mn = 1: A is K x M row-major (lda >= M)
  *   b_mn = 0: B is Nc x K row-major (ldb >= K); b_mn = 1: B is K x Nc row-major (ldb >= Nc)

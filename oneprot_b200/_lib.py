@@ -63,6 +63,8 @@ SIGNATURES = {
     "oneprot_retrieval_ranks": (_i, [_vp, _vp, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
     "oneprot_clip_bwd_weights": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _vp]),
     "oneprot_clip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _vp, _i, _vp]),
+    "oneprot_clip_fwd_sums_keep": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, C.POINTER(AgDesc), _fp, _fp, _vp, _sz, _vp, _i, _vp]),
+    "oneprot_clip_dz_from_exp": (_i, [_vp, _i, _i, _i, _i, _fp, _fp, _fp, _vp]),
     "oneprot_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_rowdot_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_gemm_bf16_ex": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _fp, _vp, _i, _fp, _vp]),

@@ -47,6 +47,9 @@ _KERNELS = _cuda_kernels
 # bound of the bf16 dL/dZ panel workspace: 1.25 GiB lets N = 32768 run as two wave-aligned panels
 DEFAULT_PANEL_BYTES = int(__import__("os").environ.get("ONEPROT_PANEL_BYTES", 5 << 28))
 
+# bound of the stored-exponentials panel (keep_exp=True): n x N bf16 per rank, 2 GiB at N = 32768 on one GPU
+DEFAULT_KEEP_BYTES = int(__import__("os").environ.get("ONEPROT_KEEP_BYTES", 8 << 30))
+
 _SCALE_CACHE = {}               # (device, python float) -> 1-element fp32 device tensor
 
 
@@ -275,7 +278,20 @@ class _ClipLossFunction(torch.autograd.Function):
         scale_dev = scale_t.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         loss_dtype = cfg["loss_dtype"] or ops.in_dtype
 
-        if K is _cuda_kernels and _seq.enabled(cfg) and _seq.eligible(cfg, ops, comm, scale_t.requires_grad):
+        # Stored-exponentials backward (opt-in): the forward keeps e_ij as a bf16 n x N panel and the backward
+        # rescales it in place instead of recomputing the logits (3 GEMM units per step instead of 4).  Needs the
+        # one-pass gradient conventions, bf16 operands, the single-reference path and the panel to fit keep_bytes.
+        local_mode = W > 1 and cfg["local_loss"]
+        ldw = (N + 63) // 64 * 64
+        keep = None
+        if (cfg.get("keep_exp") and not ops.split and cfg.get("robust", "off") == "off"
+                and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or scale_t.requires_grad)
+                and not (local_mode and (not cfg["gather_with_grad"] or scale_t.requires_grad))
+                and 2 * ldw * ((n + 127) // 128 * 128) <= cfg.get("keep_bytes", DEFAULT_KEEP_BYTES)):
+            keep = torch.empty((n + 127) // 128 * 128, ldw, dtype=torch.bfloat16, device=dev)
+
+        if (K is _cuda_kernels and keep is None and _seq.enabled(cfg)
+                and _seq.eligible(cfg, ops, comm, scale_t.requires_grad)):
             # host-side step sequencer: the launches below, issued from one C call per phase
             loss32, flag = _seq.forward(ctx, ops, scale_dev, cfg, comm, K)
             ctx.cfg, ctx.ops, ctx.comm = cfg, ops, comm
@@ -290,10 +306,12 @@ class _ClipLossFunction(torch.autograd.Function):
         K.rowstats(ops.A, st["stats_rows"], st["stats_off"], sums[2 * N + off:2 * N + off + n], st["stats"])
         stats = comm.global_stats(st)                  # one reference G on every rank
         if st.get("ag") is not None:     # all-gather fused into the forward kernel (NVLS provider)
-            K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N], ag=st["ag"])
+            K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N], ag=st["ag"],
+                       **({"keep": keep} if keep is not None else {}))
             stats = st["stats_glob"]     # global maxima, written by the kernel
         else:
-            K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N])
+            K.fwd_sums(ops.A, B_all, scale_dev, stats, sums[N + off:N + off + n], sums[0:N],
+                       **({"keep": keep} if keep is not None else {}))
         sums = comm.complete_sums(st)
         colsum, rowsum_all, diag_all = sums[0:N], sums[N:2 * N], sums[2 * N:3 * N]
 
@@ -304,6 +322,7 @@ class _ClipLossFunction(torch.autograd.Function):
         K.loss_finalize(rowsum_all, colsum, diag_all, n, off, mode, scale_dev, stats, loss32, inv_rs, inv_cs, flag)
 
         ctx.dz_ops = None
+        ctx.E = keep                    # consumed (overwritten) by the first backward
         robust = cfg.get("robust", "off")
         if robust == "always" or (robust == "auto" and int(flag.item()) != 0):     # "auto" pays one host sync
             # Two-reference path: per-row and per-column references, one pass per softmax direction
@@ -387,7 +406,15 @@ class _ClipLossFunction(torch.autograd.Function):
             else:
                 rows_cap = min(rows_cap, -(-target // 128) * 128)
         panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
-        Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
+        E = getattr(ctx, "E", None)
+        if E is not None and len(passes) == 1:
+            # stored exponentials: the whole n x N panel exists already; one in-place rescale replaces the dL/dZ
+            # recompute.  A second backward over the same graph (retain_graph) finds E consumed and recomputes.
+            ctx.E = None
+            panels, Wz = [(0, n)], E
+        else:
+            E = None
+            Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
 
         vec = torch.empty(3 * n + 2 * N, dtype=torch.float32, device=dev)
         wr, dg, sA = vec[0:n], vec[n:2 * n], vec[2 * n:3 * n]
@@ -416,7 +443,9 @@ class _ClipLossFunction(torch.autograd.Function):
             ev_rs, dB_async = None, None
             for qi, (r0, rows) in enumerate(panels):
                 A_rows = ops.A[r0:r0 + rows]
-                if ctx.dz_ops is not None:       # two-reference path: augmented operands of this direction
+                if E is not None:
+                    K.dz_from_exp(E, n, N, off, wr, wc, dg)
+                elif ctx.dz_ops is not None:     # two-reference path: augmented operands of this direction
                     A_aug, B_aug = ctx.dz_ops[part]
                     K.dz_panel(A_aug[r0:r0 + rows], B_aug, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc,
                                dg[r0:r0 + rows], Wz)
@@ -528,6 +557,9 @@ class ClipLoss(nn.Module):
                    ONEPROT_SEQ=1) instead of kernel by kernel from Python.
       graph        replay the forward / backward launch sequences as CUDA graphs (world_size == 1);
                    removes the ~0.4 ms of host enqueue per step that dominates at OneProt's batch sizes.
+      keep_exp     stored-exponentials backward (opt-in, also ONEPROT_KEEP_EXP=1): the forward keeps the n x N
+                   exponentials as a bf16 panel (<= keep_bytes, default 8 GiB) and the backward rescales it in
+                   place instead of recomputing the logits - 3 GEMM units per step instead of 4.
       robust       "off": one common reference, validated window, device flag;
                    "always": per-row / per-column references for arbitrary inputs (2.25x the work);
                    "auto": run the normal path, read the device flag (one host sync per forward)
@@ -541,7 +573,8 @@ class ClipLoss(nn.Module):
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
                  panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
-                 robust: Optional[str] = None, graph: bool = False):
+                 robust: Optional[str] = None, graph: bool = False, keep_exp: Optional[bool] = None,
+                 keep_bytes: int = DEFAULT_KEEP_BYTES):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -559,6 +592,8 @@ class ClipLoss(nn.Module):
         if graph and (world_size != 1 or robust == "auto"):
             raise ValueError("graph=True needs world_size == 1 and a robust mode that is decided on the host side up front")
         self.graph = bool(graph)
+        self.keep_exp = (__import__("os").environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
+        self.keep_bytes = int(keep_bytes)
         self._graphs = {}            # (shape, dtype, gradient pattern, scale kind) -> GraphedStep
         # cache state (same attributes as the reference, loss.py:68-70)
         self.prev_num_logits = 0
@@ -630,7 +665,8 @@ class ClipLoss(nn.Module):
             scale_t = _float_scale_on(A.device, logit_scale)   # cached: no host-to-device copy per call
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
-                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer)
+                   panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer, keep_exp=self.keep_exp,
+                   keep_bytes=self.keep_bytes)
         if self.robust is None:     # training: never sync; evaluation: fall back to the two-reference path when flagged
             cfg["robust"] = "off" if (torch.is_grad_enabled() or self.graph) else "auto"
         else:

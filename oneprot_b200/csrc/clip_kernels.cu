@@ -287,14 +287,18 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
 
 enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4,    // RCMAX: row/col maxima; RANK: retrieval ranks
        EPI_SFWD = 5, EPI_SDZ = 6,     // SigLIP: row sums of softplus(z) / dL/dZ panel sigma(z) wr_i - [i == j] dg_i
-       EPI_DZ_L2 = 7 };               // EPI_DZ with L2 hints: panel stores evict-first, operand loads evict-last (A/B experiment)
+       EPI_DZ_L2 = 7,                 // EPI_DZ with L2 hints: panel stores evict-first, operand loads evict-last (A/B experiment)
+       EPI_FWD_E = 8 };               // EPI_FWD that also keeps the exponentials e_ij as a bf16 panel: the backward then
+                                      // rescales them in place (dz_from_exp_kernel) instead of recomputing the logits
 
 template <int EPI>
 struct SCfg {
   static constexpr int NS = 4;                                             // operand ring depth
   static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ || EPI == EPI_DZ_L2);   // writes a bf16 dL/dZ panel by TMA stores
   static constexpr bool L2_HINTS = (EPI == EPI_DZ_L2);
-  static constexpr int STAGING = PANEL ? STORE_STAGING_BYTES : 0;             // FWD / MAX / RCMAX / RANK / SFWD need none
+  static constexpr bool SUMS = (EPI == EPI_FWD || EPI == EPI_FWD_E);          // row / column exp-sums (+ the fused all-gather)
+  static constexpr bool KEEP_E = (EPI == EPI_FWD_E);
+  static constexpr int STAGING = (PANEL || KEEP_E) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX / RANK / SFWD need none
   static constexpr int SMEM = smem_bytes(NS, STAGING);
 };
 
@@ -323,7 +327,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
-        if (EPI == EPI_FWD && p.ag_src) {
+        if (SCfg<EPI>::SUMS && p.ag_src) {
           // columns [256 jb, 256 jb + 256) belong to one chunk of one rank: wait until it has landed
           const int col0 = jb * BN;
           const int r = col0 / p.ag_rows;
@@ -377,7 +381,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   } else if (warp < EPI_WARP0) {
     reg_dealloc<56>();
 #ifndef ONEPROT_KERNEL_EMULATION
-    if (EPI == EPI_FWD && warp == 3 && p.ag_src) {
+    if (SCfg<EPI>::SUMS && warp == 3 && p.ag_src) {
       // ---------------------------------------------- all-gather push (spare warp)
       const int lane = lane_id();
       const int fl = p.ag_rank * (p.ag_chunks + 1);
@@ -420,6 +424,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int r = q * 32 + lane; // row inside the tile
     float c, negG;
     constexpr bool PANEL = SCfg<EPI>::PANEL;
+    constexpr bool SUMS = SCfg<EPI>::SUMS, KEEP_E = SCfg<EPI>::KEEP_E;
     if (EPI == EPI_MAX || EPI == EPI_RCMAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
     else if (EPI == EPI_RANK) { c = 1.f; negG = 0.f; }
     else if (EPI == EPI_SFWD || EPI == EPI_SDZ) {
@@ -432,7 +437,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     float xmax = 0.f;               // EPI_MAX: running max(0, x) of this thread
 
-    float colacc[(EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) ? 128 : 1];
+    float colacc[(SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK) ? 128 : 1];
     // DZ: bf16 staging of 64 columns of this warp group's half tile = one SWIZZLE_128B box {64 cols, 128 rows}
     const uint32_t colvec_s = smem_u32(&s.tail->colvec[0]);
     const uint32_t stage_s = smem_u32(s.staging) + h * 16384;
@@ -442,7 +447,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
       const int j0 = jb * BN + h * 128;   // first column this thread sees
-      if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) {
+      if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK) {
 #pragma unroll
         for (int k = 0; k < 128; ++k) colacc[k] = (EPI == EPI_RCMAX) ? -INFINITY : 0.f;
       }
@@ -549,13 +554,14 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
             continue;
           }
-          if (EPI == EPI_FWD) {
+          if (SUMS) {
             if (!edge) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) {
                 const float e = ex2(fmaf(v[k], c, negG));
                 rsum += e;
                 colacc[cc * 32 + k] += e;
+                if (KEEP_E) v[k] = e;
               }
             } else {
 #pragma unroll
@@ -564,6 +570,30 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 const float e = ok ? ex2(fmaf(v[k], c, negG)) : 0.f;
                 rsum += e;
                 colacc[cc * 32 + k] += e;
+                if (KEEP_E) v[k] = e;
+              }
+            }
+            if (KEEP_E) {
+              // the exponentials of this 32-column slice -> bf16 -> the staging box of this warp group -> TMA store
+              // (same box protocol as the dL/dZ panel below)
+              if ((cc & 1) == 0) {
+                if (store_issuer) bulk_wait_read<0>();
+                named_bar_sync(2 + h, 128);
+              }
+              const uint32_t line = stage_s + r * 128;
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                const uint32_t slot = static_cast<uint32_t>(((cc & 1) * 4 + v4) ^ (r & 7));
+                st_shared_v4(line + slot * 16, pack_bf16x2(v[v4 * 8], v[v4 * 8 + 1]), pack_bf16x2(v[v4 * 8 + 2], v[v4 * 8 + 3]),
+                             pack_bf16x2(v[v4 * 8 + 4], v[v4 * 8 + 5]), pack_bf16x2(v[v4 * 8 + 6], v[v4 * 8 + 7]));
+              }
+              if (cc & 1) {
+                fence_proxy_async();
+                named_bar_sync(2 + h, 128);
+                if (store_issuer) {
+                  tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
+                  bulk_commit();
+                }
               }
             }
           } else {
@@ -621,12 +651,12 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
           }
         }
-        if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD || (EPI == EPI_SDZ && p.rowpart)) {
+        if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD || (EPI == EPI_SDZ && p.rowpart)) {
           p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (EPI == EPI_FWD || EPI == EPI_RCMAX || EPI == EPI_RANK) {
+      if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK) {
         // flush column sums (maxima, counts) of this item: reduce over the 32 rows of the warp, one slot per (chunk, quadrant)
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -638,7 +668,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
       }
     }
-    if (PANEL && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
+    if ((PANEL || KEEP_E) && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
     if (EPI == EPI_MAX) {
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
@@ -1237,6 +1267,14 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
 int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
                              float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
                              size_t scratch_bytes, void* stream) {
+  return oneprot_clip_fwd_sums_keep(A, B_all, n, N, d, scale_dev, stats, ag, rowsum, colsum, scratch, scratch_bytes, nullptr, 0, stream);
+}
+
+int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev,
+                               float* stats, const oneprot_ag_t* ag, float* rowsum, float* colsum, void* scratch,
+                               size_t scratch_bytes, void* E, int lde, void* stream) {
+  if (E && (lde < N || lde % 8 || (reinterpret_cast<uintptr_t>(E) & 15)))
+    return fail(ONEPROT_ERR_ARG, "fwd_sums_keep: E must be 16-byte aligned with a row pitch lde >= N that is a multiple of 8");
   if (!A || !B_all || !scale_dev || !stats || !rowsum || !colsum || !scratch) return fail(ONEPROT_ERR_ARG, "fwd_sums: null pointer");
   if (n <= 0 || N <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "fwd_sums: need n, N > 0 and d a positive multiple of 8");
   if (scratch_bytes < oneprot_clip_fwd_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "fwd_sums: scratch too small");
@@ -1275,11 +1313,13 @@ int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int
                    ag->src, ag->dst_mc, (void*)ag->counters, (void*)ag->flags_mc, (const void*)ag->flags, (void*)ag->stats_mc,
                    (const void*)ag->stats_all, (void*)ag->stats_out, ag->epoch, ag->rank, ag->world, ag->chunks, ag->rows_per_rank);
   }
+  if (E && optrace::recording()) optrace::add("  keep E=%p lde=%d", E, lde);
   if (optrace::dry()) { g_launches += (!ag && n == N) ? 4 : 3; return ONEPROT_OK; }
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapE;
   int rc;
   if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
   if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  if (E && (rc = make_map(&mapE, E, N, n, lde, op::BM))) return rc;    // store side, like the dL/dZ panel: boxes {64 cols, 128 rows}
   constexpr int smem = op::SCfg<op::EPI_FWD>::SMEM;
   if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD>, smem))) return rc;
   // fused gather: every CTA of the grid pushes a slice, so the grid must be fully co-resident (it is: <= #SMs)
@@ -1294,7 +1334,13 @@ int oneprot_clip_fwd_sums_ag(const void* A, const void* B_all, int n, int N, int
     ++g_launches;
     OP_CUDA(cudaGetLastError());
   }
-  op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+  if (E) {
+    constexpr int smem_e = op::SCfg<op::EPI_FWD_E>::SMEM;
+    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E>, smem_e))) return rc;
+    op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
+  } else {
+    op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+  }
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   op::reduce_slots_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
@@ -1458,6 +1504,21 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
     if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
     op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
   }
+  ++g_launches;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_clip_dz_from_exp(void* E, int rows, int N, int lde, int grow0, const float* wr, const float* wc, const float* dg,
+                             void* stream) {
+  if (!E || !wr || !wc || !dg) return fail(ONEPROT_ERR_ARG, "dz_from_exp: null pointer");
+  if (rows <= 0 || N <= 0 || lde < N || lde % 8 || (reinterpret_cast<uintptr_t>(E) & 15)) return fail(ONEPROT_ERR_ARG, "dz_from_exp: bad sizes");
+  if (optrace::recording())
+    optrace::add("dz_from_exp E=%p rows=%d N=%d lde=%d grow0=%d wr=%p wc=%p dg=%p st=%p", E, rows, N, lde, grow0, (const void*)wr,
+                 (const void*)wc, (const void*)dg, stream);
+  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
+  const dim3 grid(cdiv(N, 256 * 8), cdiv(rows, op::DZE_ROWS));
+  op::dz_from_exp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__nv_bfloat16*>(E), rows, N, lde, grow0, wr, wc, dg);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

@@ -131,6 +131,40 @@ __global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, i
   }
 }
 
+// dL/dZ from stored exponentials, in place: W_ij = E_ij (wr_i + wc_j) - [grow0 + i == j] dg_i, bf16 in, bf16 out.
+// The forward kept e_ij = 2^(x_ij - G) (clip_s_kernel<FWD_E>), so the backward needs no second pass over the
+// logits: 2 bytes read + 2 written per logit, HBM-bound.  Block = 256 threads x 8 columns, DZE_ROWS rows; the
+// column weights of a thread stay in registers over its rows.
+constexpr int DZE_ROWS = 32;
+__global__ void __launch_bounds__(256) dz_from_exp_kernel(__nv_bfloat16* __restrict__ E, int rows, int N, int ld, int grow0,
+                                                          const float* __restrict__ wr, const float* __restrict__ wc,
+                                                          const float* __restrict__ dg) {
+  const int c0 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c0 >= N) return;
+  const int nv = min(8, N - c0);
+  float w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = (k < nv) ? __ldg(wc + c0 + k) : 0.f;
+  const int r0 = blockIdx.y * DZE_ROWS, r1 = min(rows, r0 + DZE_ROWS);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    __nv_bfloat16* p = E + static_cast<size_t>(r) * ld + c0;
+    const float wri = __ldg(wr + r);
+    const int dcol = grow0 + r - c0;            // position of the diagonal among this thread's 8 columns, if any
+    const float dgi = (dcol >= 0 && dcol < 8) ? __ldg(dg + r) : 0.f;
+    if (nv == 8) {
+      float f[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(p), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = f[k] * (wri + w[k]) - (k == dcol ? dgi : 0.f);
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    } else {                                    // ragged right edge (N not a multiple of 8)
+      for (int k = 0; k < nv; ++k)
+        p[k] = __float2bfloat16_rn(__bfloat162float(p[k]) * (wri + w[k]) - (k == dcol ? dgi : 0.f));
+    }
+  }
+}
+
 // loss value, reciprocal sums, hazard flag.  FIN_BLOCKS blocks each reduce a fixed slice in double
 // precision; the last block to finish adds the per-block partials in index order (deterministic).
 constexpr int FIN_BLOCKS = 32;

@@ -132,9 +132,11 @@ def fwd_scratch_bytes(n: int, N: int) -> int:
     return int(_lib.load().oneprot_clip_fwd_scratch_bytes(n, N))
 
 
-def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None, keep=None):
     """rowsum[i] = sum_j e_ij, colsum[j] = sum_i e_ij for the n x N logit panel (never stored).
-    ag: optional dict describing the fused all-gather (see oneprot_ag_t)."""
+    ag: optional dict describing the fused all-gather (see oneprot_ag_t).
+    keep: optional bf16 tensor (>= n rows, row pitch >= N, multiple of 8) that receives the exponentials
+    e_ij for dz_from_exp (stored-exponentials backward)."""
     _need_cuda(A, B_all, scale_dev, stats, rowsum, colsum)
     _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
     n, d = A.shape
@@ -147,6 +149,17 @@ def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
         desc = _lib.AgDesc(ag["src"], ag["dst_mc"], ag["counters"], ag["flags_mc"], ag["flags"], ag["stats_mc"],
                            ag["stats_all"], ag["stats_out"], ag["epoch"], ag["rank"], ag["world"], ag["chunks"],
                            ag["rows_per_rank"])
+    if keep is not None:
+        _need_cuda(keep)
+        _need(keep, torch.bfloat16, "keep")
+        if keep.dim() != 2 or keep.shape[0] < n or keep.stride(1) != 1:
+            raise ValueError("keep must be a row-major 2-D tensor with at least n rows")
+        check(_lib.load().oneprot_clip_fwd_sums_keep(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(stats),
+                                                     C.byref(desc) if desc is not None else None, ptr(rowsum), ptr(colsum),
+                                                     ptr(scratch), scratch.numel() * scratch.element_size(), ptr(keep),
+                                                     keep.stride(0), _stream()),
+              "oneprot_clip_fwd_sums_keep")
+        return scratch
     check(_lib.load().oneprot_clip_fwd_sums_ag(ptr(A), ptr(B_all), n, N, d, ptr(scale_dev), ptr(stats),
                                                C.byref(desc) if desc is not None else None, ptr(rowsum), ptr(colsum),
                                                ptr(scratch), scratch.numel() * scratch.element_size(), _stream()),
@@ -221,6 +234,17 @@ def dz_panel(A_rows, B_all, grow0: int, scale_dev, stats, wr, wc, dg, Wz):
     check(_lib.load().oneprot_clip_dz_panel(ptr(A_rows), ptr(B_all), rows, N, d, grow0, ptr(scale_dev), ptr(stats),
                                             ptr(wr), ptr(wc), ptr(dg), ptr(Wz), Wz.stride(0), _stream()),
           "oneprot_clip_dz_panel")
+
+
+def dz_from_exp(E, rows: int, N: int, grow0: int, wr, wc, dg):
+    """In place on the stored exponentials: E[i, j] <- E[i, j] (wr[i] + wc[j]) - [grow0+i == j] dg[i] for
+    i < rows, j < N - the dL/dZ panel of dz_panel without a second pass over the logits."""
+    _need_cuda(E, wr, wc, dg)
+    _need(E, torch.bfloat16, "E")
+    if E.dim() != 2 or E.shape[0] < rows or E.stride(1) != 1:
+        raise ValueError("E must be a row-major 2-D tensor with at least `rows` rows")
+    check(_lib.load().oneprot_clip_dz_from_exp(ptr(E), rows, N, E.stride(0), grow0, ptr(wr), ptr(wc), ptr(dg), _stream()),
+          "oneprot_clip_dz_from_exp")
 
 
 def siglip_fwd(A, B_all, scale_dev, bias_dev, rowsum, scratch=None):

@@ -60,15 +60,20 @@ size_t emu_s_scratch_floats(int n, int N) {
 
 // oneprot_clip_fwd_sums: [max pass when the whole matrix is here] + forward + the two slot reductions
 void emu_fwd_sums(const void* A, const void* B, int n, int N, int d, const float* scale, float* stats, float* rowsum, float* colsum,
-                  float* scratch) {
+                  float* scratch, void* E, int lde) {
   op::SParams p{};
   s_common(p, n, N, d, 2, scratch);
   p.scale = scale; p.stats = stats;
-  CUtensorMap mA, mB;
+  CUtensorMap mA, mB, mE;
   make_map(&mA, A, d, n, d, op::BM);
   make_map(&mB, B, d, N, d, op::BN);
   if (n == N) { p.stats_out = stats; run_s<op::EPI_MAX>(mA, mB, mA, p); }
-  run_s<op::EPI_FWD>(mA, mB, mA, p);
+  if (E) {                       // stored-exponentials forward
+    make_map(&mE, E, N, n, lde, op::BM);
+    run_s<op::EPI_FWD_E>(mA, mB, mE, p);
+  } else {
+    run_s<op::EPI_FWD>(mA, mB, mA, p);
+  }
   reduce(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum, false);
   reduce(p.colpart, 4 * p.nChunks, p.ldc, N, colsum, false);
 }

@@ -39,6 +39,11 @@ void emu_augment(const void* in, int rows, int d, const float* ref, const float*
     op::augment_kernel(static_cast<const __nv_bfloat16*>(in), rows, d, ref, scale, static_cast<__nv_bfloat16*>(out), ref_q);
   });
 }
+void emu_dz_from_exp(void* E, int rows, int N, int lde, int grow0, const float* wr, const float* wc, const float* dg) {
+  emu::launch(dim3(cdiv(N, 256 * 8), cdiv(rows, op::DZE_ROWS)), dim3(256), [&] {
+    op::dz_from_exp_kernel(static_cast<__nv_bfloat16*>(E), rows, N, lde, grow0, wr, wc, dg);
+  });
+}
 void emu_loss_finalize(const float* rowsum, const float* colsum, const float* diag, int N, int n, int off, int mode, const float* scale,
                        const float* stats, float* loss, float* inv_rs, float* inv_cs, int* flag, double* partial, unsigned int* counter,
                        const float* row_ref, const float* col_ref) {

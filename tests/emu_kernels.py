@@ -116,14 +116,20 @@ def _scratch(n, N):
     return torch.zeros(int(_tc().emu_s_scratch_floats(n, N)), dtype=torch.float32)
 
 
-def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None, keep=None):
     assert ag is None, "the fused all-gather is not emulated"
-    CALLS.append("fwd_sums")
+    CALLS.append("fwd_sums" if keep is None else "fwd_sums_keep")
     n, d = A.shape
     N = B_all.shape[0]
     s = _scratch(n, N)
-    _tc().emu_fwd_sums(_p(A), _p(B_all), n, N, d, _p(scale_dev), _p(stats), _p(rowsum), _p(colsum), _p(s))
+    _tc().emu_fwd_sums(_p(A), _p(B_all), n, N, d, _p(scale_dev), _p(stats), _p(rowsum), _p(colsum), _p(s), _p(keep),
+                       keep.stride(0) if keep is not None else 0)
     return scratch
+
+
+def dz_from_exp(E, rows, N, grow0, wr, wc, dg):
+    CALLS.append("dz_from_exp")
+    _vec().emu_dz_from_exp(_p(E), rows, N, E.stride(0), grow0, _p(wr), _p(wc), _p(dg))
 
 
 def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum, inv_colsum, flag,

@@ -57,13 +57,23 @@ def fwd_scratch_bytes(n, N):
     return 16
 
 
-def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None):
-    CALLS.append("fwd_sums")
+def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None, keep=None):
+    CALLS.append("fwd_sums" if keep is None else "fwd_sums_keep")
     c, G = _G(scale_dev, stats)
     E = torch.exp2(c * (A.double() @ B_all.double().T) - G)
     rowsum.copy_(E.sum(1).float())
     colsum.copy_(E.sum(0).float())
+    if keep is not None:
+        keep[:A.shape[0], :B_all.shape[0]] = E.float().to(torch.bfloat16)
     return scratch
+
+
+def dz_from_exp(E, rows, N, grow0, wr, wc, dg):
+    CALLS.append("dz_from_exp")
+    W = E[:rows, :N].double() * (wr[:rows].double()[:, None] + wc.double()[None, :])
+    idx = torch.arange(rows)
+    W[idx, grow0 + idx] -= dg[:rows].double()
+    E[:rows, :N] = W.float().to(torch.bfloat16)
 
 
 def loss_finalize(rowsum_all, colsum_all, diag_all, n, row_offset, mode, scale_dev, stats, loss_out, inv_rowsum,

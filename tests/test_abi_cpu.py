@@ -33,6 +33,24 @@ def test_header_symbols_are_exported_and_bound(lib):
     assert sorted(_lib.SIGNATURES) == declared
 
 
+def test_ctypes_signatures_have_the_headers_argument_counts():
+    """A wrong argtypes list is a silent stack mismatch on a GPU box: every prototype of the header and its ctypes
+    signature must agree on the number of parameters (and on pointer vs. integer for each of them)."""
+    from oneprot_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "oneprot_clip.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(oneprot_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text)
+    assert len(protos) == len(_declared_symbols())
+    for name, params in protos:
+        params = [q.strip() for q in params.split(",")] if params.strip() not in ("", "void") else []
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters, _lib.py binds {len(argtypes)}"
+        for q, t in zip(params, argtypes):
+            is_ptr_c = "*" in q
+            is_ptr_py = t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P"
+            assert is_ptr_c == is_ptr_py, f"{name}: parameter '{q}' bound as {t}"
+
+
 def test_abi_version_and_error_paths_without_gpu(lib):
     assert lib.oneprot_abi_version() == 1
     # argument validation happens before any CUDA call, so it is testable on CPU

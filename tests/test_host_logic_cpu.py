@@ -171,16 +171,16 @@ def _worker(rank, world, port, results, provider="fake"):
                 A = a.clone().requires_grad_(True)
                 B = b.clone().requires_grad_(True)
                 ls = torch.tensor(float(g["scale"]), requires_grad=scale_grad)
-                for robust in ("off", "always"):
+                for robust in ("off", "always", "keep"):       # "keep": stored-exponentials backward (falls back where it must)
                     A = a.clone().requires_grad_(True)
                     B = b.clone().requires_grad_(True)
                     ls = torch.tensor(float(g["scale"]), requires_grad=scale_grad)
                     m = clip_loss.ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank,
                                            world_size=world, loss_dtype=torch.float32, panel_bytes=128 * 64 * 2,
-                                           robust=robust)
+                                           robust="off" if robust == "keep" else robust, keep_exp=robust == "keep")
                     loss = m(A, B, ls)
                     (loss * gout).backward()
-                    tag = f"ll{int(ll)}_gwg{int(gwg)}_sg{int(scale_grad)}" + ("_rob" if robust == "always" else "")
+                    tag = f"ll{int(ll)}_gwg{int(gwg)}_sg{int(scale_grad)}" + {"always": "_rob", "keep": "_keep", "off": ""}[robust]
                     rec[tag] = dict(loss=loss.item(), dA=A.grad.float().numpy(), dB=B.grad.float().numpy(),
                                     ds=(ls.grad.item() if scale_grad else None))
     # gather_features keeps the reference contract
@@ -211,7 +211,7 @@ def test_two_rank_gloo_conventions_vs_reference_golden(provider, port):
         for ll in (0, 1):
             for gwg in (0, 1):
                 ref = f"ll{ll}_gwg{gwg}"
-                for sg, rob in ((0, ""), (1, ""), (0, "_rob"), (1, "_rob")):
+                for sg, rob in ((0, ""), (1, ""), (0, "_rob"), (1, "_rob"), (0, "_keep"), (1, "_keep")):
                     got = rec[f"{ref}_sg{sg}{rob}"]
                     assert rel_err(got["loss"], g[f"r{r}_loss_{ref}"]) < 1e-5, (r, ref)
                     # bf16 gradients: direction AND magnitude (the W-factor conventions of SURVEY.md 8a)

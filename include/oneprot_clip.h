@@ -366,6 +366,8 @@ typedef struct {
   int n, N, d, row_offset, mode;
   int stats_rows_n;         /* rows of stats_rows */
   int stats_off;            /* row of stats_rows that holds the label of A's row 0 */
+  void* E;                  /* optional: keep the exponentials (oneprot_clip_fwd_sums_keep), else NULL */
+  int lde;                  /* row pitch of E: ceil(N / 64) * 64 */
 } oneprot_fwd_seq_t;
 
 size_t oneprot_seq_fwd_ws_bytes(int n, int N);
@@ -400,11 +402,16 @@ typedef struct {
   int n, N, d, row_offset, mode, use_gsum, world, rank;
   int want_a, want_b;
   int g_on_side;             /* gather the upstream gradients on the side stream under the dL/dZ kernel (MODE_GLOBAL) */
+  void* E;                   /* optional: the exponentials kept by the forward; rescaled in place (oneprot_clip_dz_from_exp)
+                                as ONE panel of n rows instead of the panel-wise recompute, else NULL */
+  int lde;
 } oneprot_bwd_seq_t;
 
 int oneprot_seq_create(void** out);
 void oneprot_seq_destroy(void* seq);
 size_t oneprot_seq_bwd_ws_bytes(int n, int N, int d, int world, int want_b, size_t panel_bytes);
+/* kept_panel != 0: the panel is the caller's E (one panel of n rows), the workspace holds only the vectors */
+size_t oneprot_seq_bwd_ws_bytes_ex(int n, int N, int d, int world, int want_b, size_t panel_bytes, int kept_panel);
 /* number of dL/dZ panels for a panel_bytes bound (+ rows per full panel, allocated panel rows) */
 int oneprot_seq_bwd_panels(int n, int N, int d, size_t panel_bytes, int* rows_per_panel, int* wz_rows);
 /* world > 1: this rank's one-hot upstream gradient into the symmetric slot (before the caller's barrier) */

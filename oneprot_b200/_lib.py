@@ -29,7 +29,7 @@ class FwdSeq(C.Structure):
                 ("sums", C.c_void_p), ("sums_mc", C.c_void_p), ("ag", C.POINTER(AgDesc)), ("ws", C.c_void_p),
                 ("ws_bytes", C.c_size_t), ("stream", C.c_void_p),
                 ("n", C.c_int), ("N", C.c_int), ("d", C.c_int), ("row_offset", C.c_int), ("mode", C.c_int),
-                ("stats_rows_n", C.c_int), ("stats_off", C.c_int)]
+                ("stats_rows_n", C.c_int), ("stats_off", C.c_int), ("E", C.c_void_p), ("lde", C.c_int)]
 
 
 class BwdSeq(C.Structure):
@@ -41,7 +41,7 @@ class BwdSeq(C.Structure):
                 ("dB_mc_mine", C.c_void_p), ("dB_out", C.c_void_p), ("seq", C.c_void_p),
                 ("n", C.c_int), ("N", C.c_int), ("d", C.c_int), ("row_offset", C.c_int), ("mode", C.c_int),
                 ("use_gsum", C.c_int), ("world", C.c_int), ("rank", C.c_int), ("want_a", C.c_int), ("want_b", C.c_int),
-                ("g_on_side", C.c_int)]
+                ("g_on_side", C.c_int), ("E", C.c_void_p), ("lde", C.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/oneprot_clip.h declares
@@ -104,6 +104,7 @@ SIGNATURES = {
     "oneprot_seq_create": (_i, [C.POINTER(C.c_void_p)]),
     "oneprot_seq_destroy": (None, [_vp]),
     "oneprot_seq_bwd_ws_bytes": (_sz, [_i, _i, _i, _i, _i, _sz]),
+    "oneprot_seq_bwd_ws_bytes_ex": (_sz, [_i, _i, _i, _i, _i, _sz, _i]),
     "oneprot_seq_bwd_panels": (_i, [_i, _i, _i, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "oneprot_seq_bwd_begin": (_i, [C.POINTER(BwdSeq)]),
     "oneprot_seq_bwd_main": (_i, [C.POINTER(BwdSeq)]),

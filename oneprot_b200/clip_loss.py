@@ -290,10 +290,9 @@ class _ClipLossFunction(torch.autograd.Function):
                 and 2 * ldw * ((n + 127) // 128 * 128) <= cfg.get("keep_bytes", DEFAULT_KEEP_BYTES)):
             keep = torch.empty((n + 127) // 128 * 128, ldw, dtype=torch.bfloat16, device=dev)
 
-        if (K is _cuda_kernels and keep is None and _seq.enabled(cfg)
-                and _seq.eligible(cfg, ops, comm, scale_t.requires_grad)):
+        if K is _cuda_kernels and _seq.enabled(cfg) and _seq.eligible(cfg, ops, comm, scale_t.requires_grad):
             # host-side step sequencer: the launches below, issued from one C call per phase
-            loss32, flag = _seq.forward(ctx, ops, scale_dev, cfg, comm, K)
+            loss32, flag = _seq.forward(ctx, ops, scale_dev, cfg, comm, K, keep=keep)
             ctx.cfg, ctx.ops, ctx.comm = cfg, ops, comm
             ctx.set_materialize_grads(False)
             loss_out = loss32.reshape(()).to(loss_dtype)

@@ -137,6 +137,7 @@ int check_fwd(const oneprot_fwd_seq_t* f, const char* who) {
   if ((reinterpret_cast<uintptr_t>(f->ws) & 15) || (reinterpret_cast<uintptr_t>(f->saved) & 15))
     return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": ws and saved must be 16-byte aligned");
   if (f->ws_bytes < oneprot_seq_fwd_ws_bytes(f->n, f->N)) return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": workspace too small");
+  if (f->E && f->lde != cdiv(f->N, 64) * 64) return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": lde must be ceil(N / 64) * 64");
   if ((f->sums == nullptr) != (f->sums_mc == nullptr) || (f->sums_mc != nullptr) != (f->ag != nullptr) ||
       (f->zero_ptr != nullptr) != (f->ag != nullptr))
     return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": sums, sums_mc, zero_ptr and ag go together (all NULL when the sums are complete locally)");
@@ -162,11 +163,14 @@ int panel_row_unit(int d) {
 }
 
 // the panel split of clip_loss.py::_backward_impl, line for line
-BwdPlan bwd_plan(void* base, int n, int N, int d, int world, int want_b, size_t panel_bytes) {
+// kept != nullptr: the forward kept the exponentials - they ARE the panel (one panel of n rows, rescaled in place)
+BwdPlan bwd_plan(void* base, int n, int N, int d, int world, int want_b, size_t panel_bytes, bool kept_panel = false,
+                 void* kept = nullptr) {
   BwdPlan b{};
   b.ldw = cdiv(N, 64) * 64;
   long long cap = static_cast<long long>(panel_bytes / (2 * static_cast<size_t>(b.ldw))) / 128 * 128;
   if (cap < 128) cap = 128;
+  if (kept_panel) cap = (static_cast<long long>(n) + 127) / 128 * 128;
   if (cap < n) {
     // several panels: balance them and make the dA GEMM of every full panel a whole number of waves
     const long long unit = panel_row_unit(d);
@@ -197,10 +201,17 @@ BwdPlan bwd_plan(void* base, int n, int N, int d, int world, int want_b, size_t 
     b.acc = reinterpret_cast<float*>(p + off);
     off += al256(static_cast<size_t>(N) * d * 4);
   }
-  b.Wz = p + off;
-  off += al256(static_cast<size_t>(b.wz_rows) * b.ldw * 2);
+  if (kept_panel) {
+    b.Wz = kept;
+  } else {
+    b.Wz = p + off;
+    off += al256(static_cast<size_t>(b.wz_rows) * b.ldw * 2);
+  }
   b.total = off;
   return b;
+}
+BwdPlan bwd_plan(const oneprot_bwd_seq_t* q) {
+  return bwd_plan(q->ws, q->n, q->N, q->d, q->world, q->want_b, q->panel_bytes, q->E != nullptr, q->E);
 }
 
 int check_bwd(const oneprot_bwd_seq_t* q, const char* who) {
@@ -211,8 +222,9 @@ int check_bwd(const oneprot_bwd_seq_t* q, const char* who) {
     return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": bad sizes");
   if ((q->want_a && !q->dA) || (q->want_b && !q->dB)) return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": missing gradient buffer");
   if (reinterpret_cast<uintptr_t>(q->ws) & 15) return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": ws must be 16-byte aligned");
-  if (q->ws_bytes < oneprot_seq_bwd_ws_bytes(q->n, q->N, q->d, q->world, q->want_b, q->panel_bytes))
+  if (q->ws_bytes < oneprot_seq_bwd_ws_bytes_ex(q->n, q->N, q->d, q->world, q->want_b, q->panel_bytes, q->E != nullptr))
     return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": workspace too small");
+  if (q->E && q->lde != cdiv(q->N, 64) * 64) return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": lde must be ceil(N / 64) * 64");
   if (q->world > 1) {
     if (!q->side_stream || !q->g_slot || !q->g_slot_mc || !q->dB_mc_mine || !q->dB_out || !q->seq || !q->want_b)
       return opint::fail(ONEPROT_ERR_ARG, std::string(who) + ": world > 1 needs the exchange fields (side_stream, g_slot, g_slot_mc, dB_mc_mine, dB_out, seq) and want_b");
@@ -278,8 +290,8 @@ int oneprot_seq_fwd_begin(const oneprot_fwd_seq_t* f) {
   else SQ(sq_memset(sums, static_cast<size_t>(3) * N * 4, f->stream));
   SQ(oneprot_clip_rowstats(f->A, f->stats_rows, f->n, f->stats_rows_n, f->d, f->stats_off, sums + 2 * static_cast<size_t>(N) + f->row_offset,
                            f->stats, f->stream));
-  SQ(oneprot_clip_fwd_sums_ag(f->A, f->B_all, f->n, N, f->d, f->scale, f->stats, f->ag, sums + N + f->row_offset, sums, w.fscratch,
-                              w.fscratch_bytes, f->stream));
+  SQ(oneprot_clip_fwd_sums_keep(f->A, f->B_all, f->n, N, f->d, f->scale, f->stats, f->ag, sums + N + f->row_offset, sums, w.fscratch,
+                                w.fscratch_bytes, f->E, f->lde, f->stream));
   return ONEPROT_OK;
 }
 
@@ -307,8 +319,12 @@ int oneprot_seq_fwd(const oneprot_fwd_seq_t* f) {
 
 // ---- backward ------------------------------------------------------------------------------
 size_t oneprot_seq_bwd_ws_bytes(int n, int N, int d, int world, int want_b, size_t panel_bytes) {
+  return oneprot_seq_bwd_ws_bytes_ex(n, N, d, world, want_b, panel_bytes, 0);
+}
+
+size_t oneprot_seq_bwd_ws_bytes_ex(int n, int N, int d, int world, int want_b, size_t panel_bytes, int kept_panel) {
   if (n <= 0 || N <= 0 || d <= 0 || world <= 0) return 0;
-  return bwd_plan(nullptr, n, N, d, world, want_b, panel_bytes).total;
+  return bwd_plan(nullptr, n, N, d, world, want_b, panel_bytes, kept_panel != 0).total;
 }
 
 int oneprot_seq_bwd_panels(int n, int N, int d, size_t panel_bytes, int* rows_per_panel, int* wz_rows) {
@@ -321,7 +337,7 @@ int oneprot_seq_bwd_panels(int n, int N, int d, size_t panel_bytes, int* rows_pe
 int oneprot_seq_bwd_begin(const oneprot_bwd_seq_t* q) {
   SQ(check_bwd(q, "seq_bwd_begin"));
   if (q->world == 1) return ONEPROT_OK;    // nothing to exchange
-  const BwdPlan b = bwd_plan(q->ws, q->n, q->N, q->d, q->world, q->want_b, q->panel_bytes);
+  const BwdPlan b = bwd_plan(q);
   Seq* s = static_cast<Seq*>(q->seq);
   void* xs = q->g_on_side ? q->side_stream : q->stream;
   if (q->g_on_side) {
@@ -343,7 +359,7 @@ static int dA_gemm(const oneprot_bwd_seq_t* q, const BwdPlan& b, int r0, int row
 
 int oneprot_seq_bwd_main(const oneprot_bwd_seq_t* q) {
   SQ(check_bwd(q, "seq_bwd_main"));
-  const BwdPlan b = bwd_plan(q->ws, q->n, q->N, q->d, q->world, q->want_b, q->panel_bytes);
+  const BwdPlan b = bwd_plan(q);
   Seq* s = static_cast<Seq*>(q->seq);
   const int n = q->n, N = q->N, d = q->d;
   void* mainst = q->stream;
@@ -369,8 +385,11 @@ int oneprot_seq_bwd_main(const oneprot_bwd_seq_t* q) {
     const int rows = std::min(b.rows_cap, n - r0);
     const bool first = pi == 0, last = r0 + b.rows_cap >= n;
     const void* A_rows = A + static_cast<size_t>(r0) * d * 2;
-    SQ(oneprot_clip_dz_panel(A_rows, q->B_all, rows, N, d, q->row_offset + r0, q->scale, q->stats, b.wr + r0, b.wc, b.dg + r0, b.Wz, b.ldw,
-                             mainst));
+    if (q->E)    // kept exponentials: one in-place rescale of the whole panel instead of the recompute
+      SQ(oneprot_clip_dz_from_exp(q->E, n, N, q->lde, q->row_offset, b.wr, b.wc, b.dg, mainst));
+    else
+      SQ(oneprot_clip_dz_panel(A_rows, q->B_all, rows, N, d, q->row_offset + r0, q->scale, q->stats, b.wr + r0, b.wc, b.dg + r0, b.Wz, b.ldw,
+                               mainst));
     if (wait_g) {             // the GEMM epilogues read the output scales
       SQ(sq_wait(s, EV_G, mainst));
       wait_g = false;
@@ -402,7 +421,7 @@ int oneprot_seq_bwd_end(const oneprot_bwd_seq_t* q) {
   SQ(oneprot_mc_reduce_bf16(q->dB_mc_mine, q->dB_out, static_cast<size_t>(q->n) * q->d * 2, q->side_stream));
   SQ(sq_record(s, EV_RS, q->side_stream));
   if (q->want_a) {     // last panel's dA GEMM: runs over the exchange above
-    const BwdPlan b = bwd_plan(q->ws, q->n, q->N, q->d, q->world, q->want_b, q->panel_bytes);
+    const BwdPlan b = bwd_plan(q);
     const int r0 = (b.n_panels - 1) * b.rows_cap;
     SQ(dA_gemm(q, b, r0, q->n - r0));
   }

@@ -45,11 +45,12 @@ def eligible(cfg, ops, comm, scale_requires_grad: bool) -> bool:
 
 class _State:
     """What the backward needs from the forward (kept on ctx)."""
-    __slots__ = ("saved", "B_all_ptr", "B_keep", "token", "mode", "scale_dev")
+    __slots__ = ("saved", "B_all_ptr", "B_keep", "token", "mode", "scale_dev", "E")
 
 
-def forward(ctx, ops, scale_dev, cfg, comm, K):
-    """-> (loss32 view, flag view); fills ctx.seq."""
+def forward(ctx, ops, scale_dev, cfg, comm, K, keep=None):
+    """-> (loss32 view, flag view); fills ctx.seq.  keep: bf16 panel that receives the exponentials
+    (stored-exponentials backward, clip_loss.py) or None."""
     lib = _lib.load()
     W, rank = cfg["world_size"], cfg["rank"]
     n, d = ops.n, ops.d
@@ -65,7 +66,9 @@ def forward(ctx, ops, scale_dev, cfg, comm, K):
     f.ws, f.ws_bytes, f.stream = ws.data_ptr(), ws_bytes, K.current_stream_handle()
     f.n, f.N, f.d, f.row_offset, f.mode = n, N, d, off, mode
     st = _State()
-    st.saved, st.mode, st.scale_dev = saved, mode, scale_dev
+    st.saved, st.mode, st.scale_dev, st.E = saved, mode, scale_dev, keep
+    if keep is not None:
+        f.E, f.lde = keep.data_ptr(), keep.stride(0)
     if W == 1:
         f.B_all = f.stats_rows = ops.B.data_ptr()
         f.stats_rows_n, f.stats_off = N, 0
@@ -101,7 +104,8 @@ def backward(ctx, g_loss, cfg, ops, comm, K):
     g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
            else g_loss.detach().to(device=dev, dtype=torch.float32).reshape(1))
     want_a, want_b = bool(need_a), bool(need_b or W > 1)    # with W > 1 every rank enters the exchange
-    ws_bytes = int(lib.oneprot_seq_bwd_ws_bytes(n, N, d, W, int(want_b), cfg["panel_bytes"]))
+    E, st.E = st.E, None                 # consumed (overwritten) by this backward; a second one recomputes
+    ws_bytes = int(lib.oneprot_seq_bwd_ws_bytes_ex(n, N, d, W, int(want_b), cfg["panel_bytes"], int(E is not None)))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     dA = torch.empty(n, d, dtype=torch.bfloat16, device=dev) if want_a else None
     sp = st.saved.data_ptr()
@@ -114,6 +118,8 @@ def backward(ctx, g_loss, cfg, ops, comm, K):
     q.n, q.N, q.d, q.row_offset, q.mode = n, N, d, off, st.mode
     q.use_gsum, q.world, q.rank = int(cfg["gather_with_grad"]), W, rank
     q.want_a, q.want_b = int(want_a), int(want_b)
+    if E is not None:
+        q.E, q.lde = E.data_ptr(), E.stride(0)
     if W == 1:
         dB = torch.empty(N, d, dtype=torch.bfloat16, device=dev) if want_b else None
         q.B_all = st.B_all_ptr

@@ -100,3 +100,18 @@ def test_keep_exp_with_graph_replay():
         loss.backward()
         assert rel_err(loss.item(), ref.loss) < BF16_LOSS_RTOL
         assert cosine(A.grad.float().cpu().numpy(), ref.dA) >= GRAD_COS and cosine(B.grad.float().cpu().numpy(), ref.dB) >= GRAD_COS
+
+
+@pytest.mark.parametrize("n,d", [(300, 80), (1024, 128)])
+def test_c_sequencer_with_kept_exponentials_is_bit_identical_to_python_host(n, d):
+    """Same kernels, same arguments, same order (tests/test_sequencer_cpu.py proves the traces equal): same bits."""
+    a, b = oc.synthetic_pair(n, d, seed=n)
+    out = {}
+    for seq in (False, True):
+        A = a.cuda().requires_grad_(True)
+        B = b.cuda().requires_grad_(True)
+        loss = _loss_mod(loss_dtype=torch.float32, keep_exp=True, host_sequencer=seq, panel_bytes=(n + 63) // 64 * 64 * 2 * 128)(A, B, 3.0)
+        loss.backward()
+        out[seq] = (loss.detach().cpu(), A.grad.cpu(), B.grad.cpu())
+    for x, y in zip(out[False], out[True]):
+        assert torch.equal(x, y)

@@ -333,9 +333,18 @@ def test_emulated_forward_sums(tc, n, N, d, off, sms):
     stats[0], stats[1] = float((Av ** 2).sum(-1).max()), float((Bv ** 2).sum(-1).max())
     rowsum = torch.empty(n); colsum = torch.empty(N)
     scratch = torch.zeros(tc.emu_s_scratch_floats(n, N))
-    tc.emu_fwd_sums(_p(A), _p(B), n, N, d, _p(scale), _p(stats), _p(rowsum), _p(colsum), _p(scratch))
+    tc.emu_fwd_sums(_p(A), _p(B), n, N, d, _p(scale), _p(stats), _p(rowsum), _p(colsum), _p(scratch), None, 0)
     E = np.exp2(LOG2E * (Av @ Bv.T))
     assert np.allclose(rowsum.numpy(), E.sum(1), rtol=1e-5) and np.allclose(colsum.numpy(), E.sum(0), rtol=1e-5)
+    # clip_s_kernel<FWD_E>: the same sums bit for bit, plus the exponentials as a bf16 panel clipped to n x N
+    ld = (N + 63) // 64 * 64
+    kept = torch.full((n + 5, ld), 7.0, dtype=torch.bfloat16)
+    rs2 = torch.empty(n); cs2 = torch.empty(N)
+    scratch.zero_()
+    tc.emu_fwd_sums(_p(A), _p(B), n, N, d, _p(scale), _p(stats), _p(rs2), _p(cs2), _p(scratch), _p(kept), ld)
+    assert torch.equal(rs2, rowsum) and torch.equal(cs2, colsum)
+    assert torch.all(kept[n:] == 7.0) and torch.all(kept[:, N:] == 7.0)
+    assert np.abs(kept[:n, :N].float().numpy() / E - 1).max() < 2 ** -8 + 1e-5
 
 
 def test_emulated_forward_uses_exact_maximum_when_the_norm_bound_is_loose(tc):
@@ -349,7 +358,7 @@ def test_emulated_forward_uses_exact_maximum_when_the_norm_bound_is_loose(tc):
     stats[0], stats[1] = float((Av ** 2).sum(-1).max()), float((Bv ** 2).sum(-1).max())
     rowsum = torch.empty(n); colsum = torch.empty(n)
     scratch = torch.zeros(tc.emu_s_scratch_floats(n, n))
-    tc.emu_fwd_sums(_p(A), _p(B), n, n, d, _p(scale), _p(stats), _p(rowsum), _p(colsum), _p(scratch))
+    tc.emu_fwd_sums(_p(A), _p(B), n, n, d, _p(scale), _p(stats), _p(rowsum), _p(colsum), _p(scratch), None, 0)
     X = 8.0 * LOG2E * (Av @ Bv.T)
     assert stats[3].item() == 1.0 and np.isclose(stats[2].item(), X.max(), rtol=1e-5)
     G = max(0.0, X.max() - 100.0)

@@ -125,9 +125,9 @@ def streams(monkeypatch):
 # ---------------------------------------------------------------------------------------------
 # running one fwd+bwd under the dry trace
 # ---------------------------------------------------------------------------------------------
-def _cfg(world, rank, local_loss, gwg, panel_bytes, seq):
+def _cfg(world, rank, local_loss, gwg, panel_bytes, seq, keep_exp=False):
     return dict(world_size=world, rank=rank, group=None, local_loss=local_loss, gather_with_grad=gwg, loss_dtype=torch.float32,
-                panel_bytes=panel_bytes, host_sequencer=seq)
+                panel_bytes=panel_bytes, host_sequencer=seq, keep_exp=keep_exp)
 
 
 def _run(streams, A, B, scale, cfg, comm, need=(True, True)):
@@ -218,6 +218,43 @@ def test_single_gpu_sequence_equals_python_path(streams, n, d, panel_rows, need)
     # what torch.zeros does on the Python path: header (loss, maxima, flag), finalize scratch, sums
     ms = [ln for ln in cs if ln.startswith("memset")]
     assert [int(re.search(r"bytes=(\d+)", ln).group(1)) for ln in ms] == [64, 512, 3 * n * 4]
+
+
+@pytest.mark.parametrize("n,d", [(512, 64), (300, 72), (1000, 64)])
+@pytest.mark.parametrize("need", [(True, True), (True, False), (False, True)])
+def test_single_gpu_kept_exponentials_sequence_equals_python_path(streams, n, d, need):
+    """keep_exp: forward keeps E, backward = one in-place rescale + one GEMM per gradient, whatever panel_bytes says."""
+    A, B, scale = _pair(n, d)
+    pb = 2 * ((n + 63) // 64 * 64) * 256
+    py, reg = _run(streams, A, B, scale, _cfg(1, 0, False, False, pb, False, True), comm_mod.LocalComm(K), need)
+    cs, reg2 = _run(streams, A, B, scale, _cfg(1, 0, False, False, pb, True, True), comm_mod.LocalComm(K), need)
+    cpy, ccs = _canon(py, reg), _canon(cs, reg2)
+    _assert_same(cpy, ccs)
+    kinds = [ln.split()[0] for ln in ccs]
+    assert kinds.count("dz_from_exp") == 1 and kinds.count("dz_panel") == 0 and kinds.count("keep") == 1
+    assert kinds.count("gemm") == int(need[0]) + int(need[1])
+    # the panel the forward kept is the one the backward rescales and both GEMMs read
+    e = re.search(r"keep E=(\S+)", next(ln for ln in ccs if ln.split()[0] == "keep")).group(1)
+    assert f"E={e} " in next(ln for ln in ccs if ln.startswith("dz_from_exp"))
+    assert all(f"A={e} " in ln for ln in ccs if ln.startswith("gemm"))
+
+
+@pytest.mark.parametrize("world,rank", [(2, 1), (8, 5)])
+@pytest.mark.parametrize("local_loss,gwg", [(False, True), (False, False), (True, True)])
+@pytest.mark.parametrize("need", [(True, True), (False, True)])
+def test_nvls_kept_exponentials_sequence_equals_python_path(streams, world, rank, local_loss, gwg, need):
+    n, d = 512, 64
+    A, B, scale = _pair(n, d)
+    traces = []
+    for seq in (False, True):
+        comm = FakeNvlsComm(world, rank, streams)
+        lines, reg = _run(streams, A, B, scale, _cfg(world, rank, local_loss, gwg, 2 * world * n * 128, seq, True), comm, need)
+        traces.append((lines, reg + _sym_regions(comm)))
+    (py, rpy), (cs, rcs) = traces
+    cpy, ccs = _canon(py, rpy), _canon(cs, rcs)
+    _assert_same(cpy, ccs)
+    kinds = [ln.split()[0] for ln in ccs]
+    assert kinds.count("dz_from_exp") == 1 and kinds.count("dz_panel") == 0 and kinds.count("gemm") == 1 + int(need[0])
 
 
 def test_sequencer_is_not_used_outside_its_scope(streams):

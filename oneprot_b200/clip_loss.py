@@ -51,6 +51,14 @@ DEFAULT_PANEL_BYTES = int(__import__("os").environ.get("ONEPROT_PANEL_BYTES", 5 
 DEFAULT_KEEP_BYTES = int(__import__("os").environ.get("ONEPROT_KEEP_BYTES", 8 << 30))
 
 _SCALE_CACHE = {}               # (device, python float) -> 1-element fp32 device tensor
+_RESCALE_STREAMS = {}           # device -> stream of the overlapped rescale (keep_overlap)
+
+
+def _rescale_stream(device):
+    s = _RESCALE_STREAMS.get(str(device))
+    if s is None:
+        s = _RESCALE_STREAMS[str(device)] = torch.cuda.Stream(device=device)
+    return s
 
 
 def _float_scale_on(device, value: float) -> torch.Tensor:
@@ -406,11 +414,19 @@ class _ClipLossFunction(torch.autograd.Function):
                 rows_cap = min(rows_cap, -(-target // 128) * 128)
         panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
         E = getattr(ctx, "E", None)
+        ev_rescaled, rs_stream = None, None
         if E is not None and len(passes) == 1:
             # stored exponentials: the whole n x N panel exists already; one in-place rescale replaces the dL/dZ
             # recompute.  A second backward over the same graph (retain_graph) finds E consumed and recomputes.
             ctx.E = None
-            panels, Wz = [(0, n)], E
+            Wz = E
+            if cfg.get("keep_overlap") and len(panels) > 1:
+                # keep the panel split: the HBM-bound rescale of panel q + 1 runs on its own stream under the
+                # tensor-bound GEMMs of panel q (the 128-register GEMM launch leaves room for it on every SM)
+                rs_stream = _rescale_stream(dev)
+                ev_rescaled = [None] * len(panels)
+            else:
+                panels = [(0, n)]
         else:
             E = None
             Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
@@ -442,7 +458,11 @@ class _ClipLossFunction(torch.autograd.Function):
             ev_rs, dB_async = None, None
             for qi, (r0, rows) in enumerate(panels):
                 A_rows = ops.A[r0:r0 + rows]
-                if E is not None:
+                if E is not None and rs_stream is not None:
+                    if qi == 0:
+                        _enqueue_rescale(K, rs_stream, ev_rescaled, 0, panels, E, N, off, wr, wc, dg)
+                    torch.cuda.current_stream().wait_event(ev_rescaled[qi])
+                elif E is not None:
                     K.dz_from_exp(E, n, N, off, wr, wc, dg)
                 elif ctx.dz_ops is not None:     # two-reference path: augmented operands of this direction
                     A_aug, B_aug = ctx.dz_ops[part]
@@ -450,7 +470,7 @@ class _ClipLossFunction(torch.autograd.Function):
                                dg[r0:r0 + rows], Wz)
                 else:
                     K.dz_panel(A_rows, B_all, off + r0, ctx.scale_dev, ctx.stats, wr[r0:r0 + rows], wc, dg[r0:r0 + rows], Wz)
-                Wp = Wz[:rows]
+                Wp = Wz[r0:r0 + rows] if E is not None else Wz[:rows]
                 if ev_g is not None:
                     main.wait_event(ev_g)        # GEMM epilogues read the output scales
                     ev_g = None
@@ -463,6 +483,8 @@ class _ClipLossFunction(torch.autograd.Function):
                             side.wait_event(evb)
                             dB_async = comm.reduce_scatter_db(dBp, rank, W, last_pass=last_pass)
                             ev_rs = side.record_event()
+                if rs_stream is not None and qi + 1 < len(panels):    # next panel's rescale, under this panel's GEMMs
+                    _enqueue_rescale(K, rs_stream, ev_rescaled, qi + 1, panels, E, N, off, wr, wc, dg)
                 if want_a:
                     chain_a = _GemmChain(rows, d, dA[r0:r0 + rows], sA[r0:r0 + rows], n_bp)
                     for bi, Bp in enumerate(b_pieces):
@@ -514,6 +536,17 @@ class _ClipLossFunction(torch.autograd.Function):
         return grad_a, grad_b, grad_s, None
 
 
+def _enqueue_rescale(K, rs_stream, events, qi, panels, E, N, off, wr, wc, dg):
+    """dz_from_exp of panel qi on the rescale stream, after everything the compute stream has enqueued so far
+    (the panel weights; for qi > 0 only the order matters); events[qi] marks its end."""
+    r0, rows = panels[qi]
+    ev = torch.cuda.current_stream().record_event()
+    with torch.cuda.stream(rs_stream), K.stream_scope():
+        rs_stream.wait_event(ev)
+        K.dz_from_exp(E[r0:], rows, N, off + r0, wr[r0:r0 + rows], wc, dg[r0:r0 + rows])
+        events[qi] = rs_stream.record_event()
+
+
 def _valid_rowdot(part_buf, rows, d):
     """The written entries of the rowdot partial buffer: [slabs, ldd] -> [:, :rows]."""
     ldd = (rows + 127) // 128 * 128
@@ -559,6 +592,8 @@ class ClipLoss(nn.Module):
       keep_exp     stored-exponentials backward (opt-in, also ONEPROT_KEEP_EXP=1): the forward keeps the n x N
                    exponentials as a bf16 panel (<= keep_bytes, default 8 GiB) and the backward rescales it in
                    place instead of recomputing the logits - 3 GEMM units per step instead of 4.
+      keep_overlap with keep_exp (opt-in, also ONEPROT_KEEP_OVERLAP=1): keep the panel_bytes split and rescale
+                   panel q + 1 on a second stream under the GEMMs of panel q.
       robust       "off": one common reference, validated window, device flag;
                    "always": per-row / per-column references for arbitrary inputs (2.25x the work);
                    "auto": run the normal path, read the device flag (one host sync per forward)
@@ -573,7 +608,7 @@ class ClipLoss(nn.Module):
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
                  panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
                  robust: Optional[str] = None, graph: bool = False, keep_exp: Optional[bool] = None,
-                 keep_bytes: int = DEFAULT_KEEP_BYTES):
+                 keep_bytes: int = DEFAULT_KEEP_BYTES, keep_overlap: Optional[bool] = None):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -593,6 +628,8 @@ class ClipLoss(nn.Module):
         self.graph = bool(graph)
         self.keep_exp = (__import__("os").environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
         self.keep_bytes = int(keep_bytes)
+        self.keep_overlap = ((__import__("os").environ.get("ONEPROT_KEEP_OVERLAP") == "1") if keep_overlap is None
+                             else bool(keep_overlap))
         self._graphs = {}            # (shape, dtype, gradient pattern, scale kind) -> GraphedStep
         # cache state (same attributes as the reference, loss.py:68-70)
         self.prev_num_logits = 0
@@ -665,7 +702,7 @@ class ClipLoss(nn.Module):
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
                    panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer, keep_exp=self.keep_exp,
-                   keep_bytes=self.keep_bytes)
+                   keep_bytes=self.keep_bytes, keep_overlap=self.keep_overlap)
         if self.robust is None:     # training: never sync; evaluation: fall back to the two-reference path when flagged
             cfg["robust"] = "off" if (torch.is_grad_enabled() or self.graph) else "auto"
         else:

@@ -111,3 +111,42 @@ def test_dz_from_exp_kernel_source_matches_float64(n, N, grow0):
     fake_kernels.dz_from_exp(want, n, N, grow0, wr, wc, dg)
     assert torch.equal(E[n:], E0[n:]) and torch.equal(E[:, N:], E0[:, N:])          # nothing outside rows x N is touched
     assert torch.equal(E[:n, :N], want[:n, :N])                                      # bf16 round-to-nearest of the same fp32 value
+
+
+def test_overlapped_rescale_gives_the_same_gradients(prov, monkeypatch):
+    """keep_overlap only changes WHERE the rescale of each panel is enqueued (tests/test_sequencer_cpu.py checks the
+    stream / event order); per panel it is the same arithmetic, so the gradients equal the one-panel variant's up to
+    the fp32 accumulation order of the dB terms."""
+    import contextlib
+    cl, K = prov
+
+    class _Ev:
+        pass
+
+    class _St:
+        cuda_stream = 0
+
+        def record_event(self):
+            return _Ev()
+
+        def wait_event(self, ev):
+            assert isinstance(ev, _Ev)
+
+    st = _St()
+    monkeypatch.setattr(cl, "_rescale_stream", lambda dev: st)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: st)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    a, b = oc.synthetic_pair(300, 64, seed=12)
+    ref = oc.clip_loss_closed_form(a.double().numpy(), b.double().numpy(), 1.0)
+    res = []
+    for overlap in (False, True):
+        A = a.clone().requires_grad_(True)
+        B = b.clone().requires_grad_(True)
+        m = cl.ClipLoss(loss_dtype=torch.float32, keep_exp=True, keep_overlap=overlap, panel_bytes=320 * 128 * 2)
+        del K.CALLS[:]
+        m(A, B).backward()
+        assert K.CALLS.count("dz_from_exp") == (3 if overlap else 1) and K.CALLS.count("gemm") == (6 if overlap else 2)
+        res.append((A.grad.float().numpy(), B.grad.float().numpy()))
+        assert cosine(res[-1][0], ref.dA) > 0.9999 and cosine(res[-1][1], ref.dB) > 0.9999
+    assert np.array_equal(res[0][0], res[1][0])                      # dA rows are independent of the split
+    assert cosine(res[0][1], res[1][1]) > 0.999999

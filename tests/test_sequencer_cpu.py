@@ -403,3 +403,52 @@ def test_sequencer_workspace_regions_do_not_overlap(streams, n, d, panel_rows):
         assert a0 + sz <= b0, (na, nb)
     assert regs[-1][1] + regs[-1][2] <= endb
     assert all(_addr(a["Wz"]) == _addr(dz[0]["Wz"]) for a in dz) and all(int(a["ldw"]) == ldw for a in dz)
+
+
+# ---------------------------------------------------------------------------------------------
+# keep_exp + keep_overlap: stream / event order of the overlapped rescale (Python host)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("need", [(True, True), (True, False), (False, True)])
+def test_overlapped_rescale_order(streams, monkeypatch, need):
+    """Panel q + 1 is rescaled on its own stream, enqueued between the GEMMs of panel q, and no GEMM reads a panel
+    before the compute stream has waited for that panel's rescale."""
+    RS = 0x3000
+    rs = FakeStream(RS)
+    monkeypatch.setattr(cl, "_rescale_stream", lambda dev: rs)
+    n, d, rows_cap = 1000, 64, 384
+    A, B, scale = _pair(n, d)
+    ldw = (n + 63) // 64 * 64
+    cfg = dict(_cfg(1, 0, False, False, 2 * ldw * rows_cap, False, True), keep_overlap=True)
+    lines, _ = _run(streams, A, B, scale, cfg, comm_mod.LocalComm(K), need)
+    bwd = lines[lines.index("---- backward") + 1:]
+    kinds = [ln.split()[0] for ln in bwd]
+    n_panels = -(-n // rows_cap)
+    assert kinds.count("dz_from_exp") == n_panels and kinds.count("dz_panel") == 0
+    assert kinds.count("gemm") == n_panels * (int(need[0]) + int(need[1]))
+    e_base = int(re.search(r"keep E=(0x[0-9a-f]+)", next(ln for ln in lines if ln.split()[0] == "keep")).group(1), 16)
+    done_ev, waited, rescaled_rows = {}, set(), []
+    pending = None
+    for ln in bwd:
+        k = ln.split()[0]
+        if k == "dz_from_exp":
+            assert ln.endswith(f"st={RS:#x}")                                   # on the rescale stream
+            ptr = int(re.search(r"E=(0x[0-9a-f]+)", ln).group(1), 16)
+            r0 = (ptr - e_base) // (2 * ldw)
+            assert int(re.search(r"grow0=(\d+)", ln).group(1)) == r0
+            pending = r0
+            rescaled_rows.append((r0, int(re.search(r"rows=(\d+)", ln).group(1))))
+        elif k == "record" and ln.endswith(f"st={RS:#x}"):
+            done_ev[re.search(r"ev=(\d+)", ln).group(1)] = pending
+        elif k == "wait" and ln.endswith(f"st={MAIN:#x}"):
+            ev = re.search(r"ev=(\d+)", ln).group(1)
+            if ev in done_ev:
+                waited.add(done_ev[ev])
+        elif k == "gemm":
+            assert ln.endswith(f"st={MAIN:#x}")
+            ptr = int(re.search(r" A=(0x[0-9a-f]+)", ln).group(1), 16)
+            assert (ptr - e_base) // (2 * ldw) in waited, "GEMM reads a panel whose rescale the compute stream has not waited for"
+    assert rescaled_rows == [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
+    # overlap: the rescale of panel 1 is enqueued before the compute stream waits for it and after the first GEMM of panel 0
+    first_gemm = kinds.index("gemm")
+    second_rescale = [i for i, k in enumerate(kinds) if k == "dz_from_exp"][1]
+    assert first_gemm < second_rescale or (int(need[0]) + int(need[1])) == 1

@@ -9,6 +9,7 @@
 //   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers; thread = one accumulator row)
 // The epilogues differ:
 //   clip_s_kernel<FWD>  exp-sums of the logits (row sums thread-local, column sums in registers)
+//   clip_s_kernel<FWD_E> the same + the exponentials kept as a bf16 panel (stored-exponentials backward, opt-in)
 //   clip_s_kernel<MAX>  exact maximum logit (robust tier, early-exits when the norm bound suffices)
 //   clip_s_kernel<DZ>   dL/dZ panel, bf16, staged through swizzled smem and written by TMA stores
 //   gemm_kernel         dA = Wz.B / dB = Wz^T.A with row-scale, row-dot, fp32 accumulate, and a PUSH

@@ -134,9 +134,14 @@ __global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, i
 // dL/dZ from stored exponentials, in place: W_ij = E_ij (wr_i + wc_j) - [grow0 + i == j] dg_i, bf16 in, bf16 out.
 // The forward kept e_ij = 2^(x_ij - G) (clip_s_kernel<FWD_E>), so the backward needs no second pass over the
 // logits: 2 bytes read + 2 written per logit, HBM-bound.  Block = 256 threads x 8 columns, DZE_ROWS rows; the
-// column weights of a thread stay in registers over its rows.
+// column weights of a thread stay in registers over its rows.  Rows are processed in batches of DZE_BATCH with
+// all loads of a batch issued before the first store (the panel is updated in place, so the compiler cannot
+// reorder them itself): 128 bytes in flight per thread keep the kernel at HBM speed even with ONE resident block
+// per SM, which is what it gets when it runs beside a GEMM (keep_overlap).  Streaming loads / stores: every byte
+// is touched once.
 constexpr int DZE_ROWS = 32;
-__global__ void __launch_bounds__(256) dz_from_exp_kernel(__nv_bfloat16* __restrict__ E, int rows, int N, int ld, int grow0,
+constexpr int DZE_BATCH = 8;
+__global__ void __launch_bounds__(256, 4) dz_from_exp_kernel(__nv_bfloat16* __restrict__ E, int rows, int N, int ld, int grow0,
                                                           const float* __restrict__ wr, const float* __restrict__ wc,
                                                           const float* __restrict__ dg) {
   const int c0 = (blockIdx.x * 256 + threadIdx.x) * 8;
@@ -146,19 +151,40 @@ __global__ void __launch_bounds__(256) dz_from_exp_kernel(__nv_bfloat16* __restr
 #pragma unroll
   for (int k = 0; k < 8; ++k) w[k] = (k < nv) ? __ldg(wc + c0 + k) : 0.f;
   const int r0 = blockIdx.y * DZE_ROWS, r1 = min(rows, r0 + DZE_ROWS);
-#pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    __nv_bfloat16* p = E + static_cast<size_t>(r) * ld + c0;
-    const float wri = __ldg(wr + r);
-    const int dcol = grow0 + r - c0;            // position of the diagonal among this thread's 8 columns, if any
-    const float dgi = (dcol >= 0 && dcol < 8) ? __ldg(dg + r) : 0.f;
-    if (nv == 8) {
-      float f[8];
-      bf16x8_to_float(*reinterpret_cast<const uint4*>(p), f);
+  if (nv == 8) {
+    __nv_bfloat16* base = E + static_cast<size_t>(r0) * ld + c0;
+    for (int rb = r0; rb < r1; rb += DZE_BATCH, base += static_cast<size_t>(DZE_BATCH) * ld) {
+      const int nb = min(DZE_BATCH, r1 - rb);
+      uint4 u[DZE_BATCH];
+      if (nb == DZE_BATCH) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = f[k] * (wri + w[k]) - (k == dcol ? dgi : 0.f);
-      *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-    } else {                                    // ragged right edge (N not a multiple of 8)
+        for (int t = 0; t < DZE_BATCH; ++t) u[t] = __ldcs(reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * ld));
+      } else {
+#pragma unroll
+        for (int t = 0; t < DZE_BATCH; ++t)
+          if (t < nb) u[t] = __ldcs(reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * ld));
+      }
+#pragma unroll
+      for (int t = 0; t < DZE_BATCH; ++t) {
+        if (t >= nb) break;
+        const int r = rb + t;
+        const float wri = __ldg(wr + r);
+        const int dcol = grow0 + r - c0;          // position of the diagonal among this thread's 8 columns, if any
+        const float dgi = (dcol >= 0 && dcol < 8) ? __ldg(dg + r) : 0.f;
+        float f[8];
+        bf16x8_to_float(u[t], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = f[k] * (wri + w[k]) - (k == dcol ? dgi : 0.f);
+        __stcs(reinterpret_cast<uint4*>(base + static_cast<size_t>(t) * ld),
+               make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+      }
+    }
+  } else {                                        // ragged right edge (N not a multiple of 8): one thread per row block
+    for (int r = r0; r < r1; ++r) {
+      __nv_bfloat16* p = E + static_cast<size_t>(r) * ld + c0;
+      const float wri = __ldg(wr + r);
+      const int dcol = grow0 + r - c0;
+      const float dgi = (dcol >= 0 && dcol < 8) ? __ldg(dg + r) : 0.f;
       for (int k = 0; k < nv; ++k)
         p[k] = __float2bfloat16_rn(__bfloat162float(p[k]) * (wri + w[k]) - (k == dcol ? dgi : 0.f));
     }

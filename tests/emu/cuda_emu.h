@@ -115,6 +115,8 @@ inline uint32_t float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); ret
 #define __log2f(x) log2f(x)
 #define rsqrtf(x) (1.0f / sqrtf(x))
 #define __ldg(p) (*(p))
+#define __ldcs(p) (*(p))
+#define __stcs(p, v) (*(p) = (v))
 using std::min;
 using std::max;
 

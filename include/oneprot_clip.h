@@ -328,6 +328,13 @@ int oneprot_attnpool_bwd_x(const void* g, const float* p, const float* ds, const
                            void* stream);
 /* out[k] = sum_s part[s * ld + k], k < count, in slot order (deterministic) */
 int oneprot_sum_slots_f32(const float* part, int slots, int ld, int count, float* out, void* stream);
+/* L1 regulariser of the training step (oneprot_module.py:43-44, 99-101): out[0] = sum |x| / true_count over `count`
+ * elements (multiple of 8; elements beyond true_count must be zero padding), deterministic;
+ * backward gx = g[0] sign(x) / true_count. */
+size_t oneprot_abs_mean_scratch_bytes(size_t count);
+int oneprot_abs_mean_fwd(const void* x, size_t count, size_t true_count, int is_fp32, float* out, void* scratch,
+                         size_t scratch_bytes, void* stream);
+int oneprot_abs_mean_bwd(const void* x, const float* g, size_t count, size_t true_count, int is_fp32, void* gx, void* stream);
 
 /* ---- host-side step sequencer (oneprot_b200/csrc/clip_sequence.cu) -------------------------------
  * One call enqueues a whole PHASE of ClipLoss.forward / its autograd backward (loss.py:103-114 and

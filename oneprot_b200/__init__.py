@@ -26,4 +26,7 @@ def __getattr__(name):
     if name in ("BaseEncoder", "LayerNorm", "Linear", "GELU", "MeanPooling", "CLSTokenPooling"):
         from . import heads
         return getattr(heads, name)
+    if name in ("ModalitySteps", "mean_abs"):
+        from . import module_steps
+        return getattr(module_steps, name)
     raise AttributeError(name)

@@ -95,6 +95,9 @@ SIGNATURES = {
     "oneprot_softmax_rows_bwd": (_i, [_fp, _fp, _fp, _i, _i, _vp]),
     "oneprot_attnpool_bwd_x": (_i, [_vp, _fp, _fp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "oneprot_sum_slots_f32": (_i, [_fp, _i, _i, _i, _fp, _vp]),
+    "oneprot_abs_mean_scratch_bytes": (_sz, [_sz]),
+    "oneprot_abs_mean_fwd": (_i, [_vp, _sz, _sz, _i, _fp, _vp, _sz, _vp]),
+    "oneprot_abs_mean_bwd": (_i, [_vp, _fp, _sz, _sz, _i, _vp, _vp]),
     "oneprot_meanpool_bwd": (_i, [_vp, _fp, _fp, _vp, _i, _i, _i, _i, _vp]),
     # host-side step sequencer + launch trace (csrc/clip_sequence.cu)
     "oneprot_seq_fwd_ws_bytes": (_sz, [_i, _i]),

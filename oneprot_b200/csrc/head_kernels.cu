@@ -282,6 +282,58 @@ __global__ void sum_slots_f32_kernel(const float* __restrict__ part, int slots, 
   out[k] = acc;
 }
 
+// ---- L1 regulariser of the training step: mean |x| over all elements (oneprot_module.py:43-44, 99-101) ----
+// Every block adds |x| over a fixed grid-stride slice and writes one partial; the last kernel adds the partials in
+// block order and divides (deterministic).  Algorithmic bytes: one read of x forward, one read + one write backward.
+constexpr int ABS_MAX_BLOCKS = 4096;
+template <bool FP32>
+__global__ void __launch_bounds__(256) abs_sum_kernel(const void* __restrict__ x, size_t total8, float* __restrict__ part) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float f[8];
+    load8<FP32>(x, i * 8, f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += fabsf(f[u]);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    part[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) abs_mean_final_kernel(const float* __restrict__ part, int blocks, float inv_count, float* __restrict__ out) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < blocks; i += 256) acc += part[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 256; ++i) t += red[i];
+    out[0] = t * inv_count;
+  }
+}
+
+// gx = g[0] * coef * sign(x)  (sign(0) = 0, the gradient torch.abs uses)
+template <bool FP32>
+__global__ void abs_mean_bwd_kernel(const void* __restrict__ x, const float* __restrict__ g, float coef, void* __restrict__ gx, size_t total8) {
+  const float c = g[0] * coef;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float f[8], o[8];
+    load8<FP32>(x, i * 8, f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o[u] = f[u] > 0.f ? c : (f[u] < 0.f ? -c : 0.f);
+    store8<FP32>(gx, i * 8, o);
+  }
+}
+
 // ---- GELU (exact, erf) -------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float v) {
@@ -653,6 +705,48 @@ int oneprot_attnpool_bwd_x(const void* g, const float* p, const float* ds, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_fp32) oph::attnpool_bwd_x_kernel<true><<<grid, 256, 0, st>>>(g, p, ds, w, gx, L, D);
   else oph::attnpool_bwd_x_kernel<false><<<grid, 256, 0, st>>>(g, p, ds, w, gx, L, D);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+static int abs_blocks(size_t total8) {
+  return static_cast<int>(std::min<size_t>(std::min<size_t>((total8 + 255) / 256, static_cast<size_t>(oneprot_num_sms()) * 16), oph::ABS_MAX_BLOCKS));
+}
+
+size_t oneprot_abs_mean_scratch_bytes(size_t count) { return sizeof(float) * static_cast<size_t>(oph::ABS_MAX_BLOCKS); (void)count; }
+
+int oneprot_abs_mean_fwd(const void* x, size_t count, size_t true_count, int is_fp32, float* out, void* scratch, size_t scratch_bytes,
+                         void* stream) {
+  if (!x || !out || !scratch || count == 0 || count % 8 || true_count == 0 || true_count > count)
+    return opint::fail(ONEPROT_ERR_ARG, "abs_mean_fwd: need a positive element count that is a multiple of 8 and 0 < true_count <= count");
+  if (!al16(x) || scratch_bytes < oneprot_abs_mean_scratch_bytes(count)) return opint::fail(ONEPROT_ERR_ARG, "abs_mean_fwd: x must be 16-byte aligned, scratch of oneprot_abs_mean_scratch_bytes");
+  if (optrace::recording()) optrace::add("abs_mean_fwd x=%p count=%zu true_count=%zu fp32=%d out=%p scratch=%p st=%p", x, count, true_count, is_fp32, (void*)out, scratch, stream);
+  opint::count_launch(2);
+  if (optrace::dry()) return ONEPROT_OK;
+  const size_t total8 = count / 8;
+  const int blocks = abs_blocks(total8);
+  float* part = static_cast<float*>(scratch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_fp32) oph::abs_sum_kernel<true><<<blocks, 256, 0, st>>>(x, total8, part);
+  else oph::abs_sum_kernel<false><<<blocks, 256, 0, st>>>(x, total8, part);
+  oph::abs_mean_final_kernel<<<1, 256, 0, st>>>(part, blocks, 1.0f / static_cast<float>(true_count), out);
+  HD_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+int oneprot_abs_mean_bwd(const void* x, const float* g, size_t count, size_t true_count, int is_fp32, void* gx, void* stream) {
+  if (!x || !g || !gx || count == 0 || count % 8 || true_count == 0 || true_count > count)
+    return opint::fail(ONEPROT_ERR_ARG, "abs_mean_bwd: need a positive element count that is a multiple of 8 and 0 < true_count <= count");
+  if (!al16(x) || !al16(gx)) return opint::fail(ONEPROT_ERR_ARG, "abs_mean_bwd: pointers must be 16-byte aligned");
+  if (optrace::recording()) optrace::add("abs_mean_bwd x=%p g=%p count=%zu true_count=%zu fp32=%d gx=%p st=%p", x, (const void*)g, count, true_count, is_fp32, gx, stream);
+  opint::count_launch(1);
+  if (optrace::dry()) return ONEPROT_OK;
+  const size_t total8 = count / 8;
+  const int blocks = abs_blocks(total8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float coef = 1.0f / static_cast<float>(true_count);
+  if (is_fp32) oph::abs_mean_bwd_kernel<true><<<blocks, 256, 0, st>>>(x, g, coef, gx, total8);
+  else oph::abs_mean_bwd_kernel<false><<<blocks, 256, 0, st>>>(x, g, coef, gx, total8);
   HD_CUDA(cudaGetLastError());
   return ONEPROT_OK;
 }

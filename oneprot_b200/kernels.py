@@ -432,6 +432,23 @@ def attnpool_bwd_x(g, p, ds, w, gx):
           "oneprot_attnpool_bwd_x")
 
 
+def abs_mean_fwd(x, true_count: int, out):
+    """out[0] = sum |x| / true_count (x flat, element count a multiple of 8, zero padded beyond true_count)."""
+    _need_cuda(x, out)
+    lib = _lib.load()
+    nbytes = int(lib.oneprot_abs_mean_scratch_bytes(x.numel()))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib.oneprot_abs_mean_fwd(ptr(x), x.numel(), int(true_count), _is32(x), ptr(out), ptr(scratch), nbytes, _stream()),
+          "oneprot_abs_mean_fwd")
+
+
+def abs_mean_bwd(x, g, true_count: int, gx):
+    """gx = g[0] sign(x) / true_count."""
+    _need_cuda(x, g, gx)
+    check(_lib.load().oneprot_abs_mean_bwd(ptr(x), ptr(g), x.numel(), int(true_count), _is32(x), ptr(gx), _stream()),
+          "oneprot_abs_mean_bwd")
+
+
 def sum_slots_f32(part, out):
     """out[k] = sum_s part[s, k] (part: slots x count fp32, fixed order)."""
     _need_cuda(part, out)

@@ -73,13 +73,13 @@ def install(provider=None):
         kernels._DRY = lambda: 0            # accept CPU tensors; "current stream" handle 0
         _install_torch_stubs()
         return
-    from oneprot_b200 import clip_loss, epilogue, heads, retrieval
+    from oneprot_b200 import clip_loss, epilogue, heads, module_steps, retrieval
     if provider == "emu":
         from tests import emu_kernels as fake_kernels
     else:
         from tests import fake_kernels
     _install_torch_stubs()
-    for mod in (clip_loss, epilogue, heads, retrieval):
+    for mod in (clip_loss, epilogue, heads, module_steps, retrieval):
         mod._KERNELS = fake_kernels
 
 

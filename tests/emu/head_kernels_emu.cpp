@@ -58,6 +58,23 @@ void emu_gelu(const void* x, const void* gy, void* out, size_t count, int fp32) 
   });
 }
 
+void emu_abs_mean_fwd(const void* x, size_t count, size_t true_count, int fp32, float* out, float* part) {
+  const size_t total8 = count / 8;
+  const int blocks = static_cast<int>(std::min<size_t>(std::min<size_t>((total8 + 255) / 256, SMS * 16), oph::ABS_MAX_BLOCKS));
+  emu::launch(dim3(blocks), dim3(256), [&] {
+    if (fp32) oph::abs_sum_kernel<true>(x, total8, part); else oph::abs_sum_kernel<false>(x, total8, part);
+  });
+  emu::launch(dim3(1), dim3(256), [&] { oph::abs_mean_final_kernel(part, blocks, 1.0f / static_cast<float>(true_count), out); });
+}
+void emu_abs_mean_bwd(const void* x, const float* g, size_t count, size_t true_count, int fp32, void* gx) {
+  const size_t total8 = count / 8;
+  const int blocks = static_cast<int>(std::min<size_t>((total8 + 255) / 256, SMS * 16));
+  emu::launch(dim3(blocks), dim3(256), [&] {
+    if (fp32) oph::abs_mean_bwd_kernel<true>(x, g, 1.0f / static_cast<float>(true_count), gx, total8);
+    else oph::abs_mean_bwd_kernel<false>(x, g, 1.0f / static_cast<float>(true_count), gx, total8);
+  });
+}
+
 void emu_meanpool_fwd(const void* x, const float* mask, void* y, float* inv, int B, int L, int D, int fp32, int normalize) {
   emu::launch(dim3(B, cdiv(D, 256)), dim3(256), [&] {
     if (fp32) oph::meanpool_fwd_kernel<true>(x, mask, y, inv, L, D, normalize);

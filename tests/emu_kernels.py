@@ -267,6 +267,17 @@ def gelu(x, out, gy=None):
     _head().emu_gelu(_p(x), _p(gy), _p(out), C.c_size_t(x.numel()), _f32(x))
 
 
+def abs_mean_fwd(x, true_count, out):
+    CALLS.append("abs_mean_fwd")
+    part = torch.zeros(4096, dtype=torch.float32)
+    _head().emu_abs_mean_fwd(_p(x), C.c_size_t(x.numel()), C.c_size_t(int(true_count)), _f32(x), _p(out), _p(part))
+
+
+def abs_mean_bwd(x, g, true_count, gx):
+    CALLS.append("abs_mean_bwd")
+    _head().emu_abs_mean_bwd(_p(x), _p(g), C.c_size_t(x.numel()), C.c_size_t(int(true_count)), _f32(x), _p(gx))
+
+
 def meanpool_fwd(x, mask, y, inv_count, normalize=True):
     CALLS.append("meanpool_fwd")
     B, L, D = x.shape

@@ -372,3 +372,13 @@ def siglip_dz_panel(A_rows, B_all, grow0, scale_dev, bias_dev, wr, dg, Wz, sig_r
     idx = torch.arange(rows)
     Wd[idx, grow0 + idx] -= dg.double()
     Wz[:rows, :N] = Wd.to(torch.bfloat16)
+
+
+def abs_mean_fwd(x, true_count, out):
+    CALLS.append("abs_mean_fwd")
+    out[0] = float(x.double().abs().sum() / true_count)
+
+
+def abs_mean_bwd(x, g, true_count, gx):
+    CALLS.append("abs_mean_bwd")
+    gx.copy_((torch.sign(x.double()) * float(g[0]) / true_count).to(gx.dtype))

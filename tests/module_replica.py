@@ -1,6 +1,6 @@
-"""Replica of the reference's manual-optimisation steps (oneprot_module.py:80-146: training_step with the
-L1 term, validation_step with RetrievalMetric, test_step with the tensor logit_scale) built ONLY from
-this package's drop-ins (ClipLoss, BaseEncoder, RetrievalMetric), replayed on the inputs and initial
+"""The reference's manual-optimisation steps (oneprot_module.py:80-146: training_step with the L1 term,
+validation_step with RetrievalMetric, test_step with the tensor logit_scale) run through this package's
+driver and drop-ins (ModalitySteps, ClipLoss, BaseEncoder, RetrievalMetric) on the inputs and initial
 parameters of tests/golden/module_steps.npz - the fixture recorded from the reference's own
 OneProtLitModule (oracle/make_golden.py::module_cases).  Shared by the CPU and GPU tests."""
 import ast
@@ -13,7 +13,7 @@ from tests.helpers import bf16_from_bits, load_golden
 
 
 def run_replica(dtype, device="cpu"):
-    from oneprot_b200 import BaseEncoder, ClipLoss, RetrievalMetric
+    from oneprot_b200 import BaseEncoder, ClipLoss, ModalitySteps, RetrievalMetric
     g = load_golden("module_steps.npz")
     spec = ast.literal_eval(g["spec"].item().decode())
     net = nn.ModuleDict({k: BaseEncoder(dm, 32, proj_type=pt, use_logit_scale=uls, learnable_logit_scale=False, pooling_type=pool)
@@ -28,30 +28,24 @@ def run_replica(dtype, device="cpu"):
         x = bf16_from_bits(g[f"{tag}:{mod}:mod_bf16"]).reshape(tuple(g[f"{tag}:{mod}:mod_shape"]))
         return seq.to(device=device, dtype=dtype), x.to(device=device, dtype=dtype)
 
+    mods = ("text", "struct_graph")
+    metrics = {f"val_{m}": RetrievalMetric() for m in mods}
+    steps = ModalitySteps(net, loss_fn, opt, use_l1_regularization=True, metrics=metrics)       # oneprot_module.py:10-41
     out = {"train": [], "val": [], "test": [], "valmetric": {}}
     for s in range(len(g["train_losses"]) // 2):
-        for mod in ("text", "struct_graph"):                                    # :92-108
+        b = {}
+        for mod in mods:
             seq, x = batch(f"train{s}", mod)
-            sf, mf = net["sequence"](seq), net[mod](x)
-            opt.zero_grad()
-            loss = loss_fn(sf, mf)
-            loss = loss + 0.01 * (torch.abs(sf).mean() + torch.abs(mf).mean())   # :99-101
-            out["train"].append(float(loss))
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
-            opt.step()
-    with torch.no_grad():
-        for mod in ("text", "struct_graph"):                                    # :110-121
-            seq, x = batch("val", mod)
-            sf, mf = net["sequence"](seq), net[mod](x)
-            m = RetrievalMetric()
-            m.update(sf, mf)
-            out["val"].append(float(loss_fn(sf, mf)))
-            out["valmetric"][mod] = m.compute()
-        for mod in ("text", "struct_graph"):                                    # :137-146
-            seq, x = batch("val", mod)
-            sf, mf = net["sequence"](seq), net[mod](x)
-            out["test"].append(float(loss_fn(sf, mf, net[mod].norm[1].log_logit_scale.exp())))
+            b[mod] = (seq, x, None, None)
+        out["train"] += [float(v) for v in steps.training_step(b)]               # :80-108
+    vb = {}
+    for mod in mods:
+        seq, x = batch("val", mod)
+        vb[mod] = (seq, x, None, None)
+        out["val"].append(float(steps.validation_step((seq, x, mod, None))))     # :110-121
+        out["valmetric"][mod] = metrics["val_" + mod].compute()
+    out["test"] = [float(v) for v in steps.test_step(vb).values()]               # :137-146
+    assert steps.global_step == len(g["train_losses"])
     out["final"] = {k: v.detach().double().cpu().numpy() for k, v in net.state_dict().items()}
     return g, out
 

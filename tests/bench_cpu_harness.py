@@ -16,7 +16,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("ONEPROT_BENCH_N", "256")
+os.environ.setdefault("ONEPROT_BENCH_N", "128" if len(sys.argv) > 1 and sys.argv[1].startswith("lib") else "256")
 os.environ.setdefault("ONEPROT_BENCH_D", "64")
 
 import torch  # noqa: E402

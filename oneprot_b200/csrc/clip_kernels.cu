@@ -289,16 +289,17 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
 enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4,    // RCMAX: row/col maxima; RANK: retrieval ranks
        EPI_SFWD = 5, EPI_SDZ = 6,     // SigLIP: row sums of softplus(z) / dL/dZ panel sigma(z) wr_i - [i == j] dg_i
        EPI_DZ_L2 = 7,                 // EPI_DZ with L2 hints: panel stores evict-first, operand loads evict-last (A/B experiment)
-       EPI_FWD_E = 8 };               // EPI_FWD that also keeps the exponentials e_ij as a bf16 panel: the backward then
+       EPI_FWD_E = 8,                 // EPI_FWD that also keeps the exponentials e_ij as a bf16 panel: the backward then
                                       // rescales them in place (dz_from_exp_kernel) instead of recomputing the logits
+       EPI_FWD_E_L2 = 9 };            // EPI_FWD_E with the L2 hints of EPI_DZ_L2 (same A/B experiment)
 
 template <int EPI>
 struct SCfg {
   static constexpr int NS = 4;                                             // operand ring depth
   static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ || EPI == EPI_DZ_L2);   // writes a bf16 dL/dZ panel by TMA stores
-  static constexpr bool L2_HINTS = (EPI == EPI_DZ_L2);
-  static constexpr bool SUMS = (EPI == EPI_FWD || EPI == EPI_FWD_E);          // row / column exp-sums (+ the fused all-gather)
-  static constexpr bool KEEP_E = (EPI == EPI_FWD_E);
+  static constexpr bool L2_HINTS = (EPI == EPI_DZ_L2 || EPI == EPI_FWD_E_L2);
+  static constexpr bool KEEP_E = (EPI == EPI_FWD_E || EPI == EPI_FWD_E_L2);
+  static constexpr bool SUMS = (EPI == EPI_FWD || KEEP_E);                    // row / column exp-sums (+ the fused all-gather)
   static constexpr int STAGING = (PANEL || KEEP_E) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX / RANK / SFWD need none
   static constexpr int SMEM = smem_bytes(NS, STAGING);
 };
@@ -592,7 +593,8 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 fence_proxy_async();
                 named_bar_sync(2 + h, 128);
                 if (store_issuer) {
-                  tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
+                  if (SCfg<EPI>::L2_HINTS) tma_store_2d_hint(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM, pol_stream);
+                  else tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
                   bulk_commit();
                 }
               }
@@ -1337,8 +1339,14 @@ int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, i
   }
   if (E) {
     constexpr int smem_e = op::SCfg<op::EPI_FWD_E>::SMEM;
-    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E>, smem_e))) return rc;
-    op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
+    static const bool l2_hints = getenv("ONEPROT_DZ_L2_HINTS") != nullptr;    // experiment knob, as in oneprot_clip_dz_panel
+    if (l2_hints) {
+      if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E_L2>, smem_e))) return rc;
+      op::clip_s_kernel<op::EPI_FWD_E_L2><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
+    } else {
+      if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E>, smem_e))) return rc;
+      op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
+    }
   } else {
     op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   }

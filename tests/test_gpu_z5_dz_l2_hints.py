@@ -18,17 +18,18 @@ from oneprot_b200 import ClipLoss
 from tools.synthetic import synthetic_pair
 a, b = synthetic_pair(1536, 256, seed=9)
 A = a.cuda().requires_grad_(True); B = b.cuda().requires_grad_(True)
-loss = ClipLoss(loss_dtype=torch.float32, panel_bytes=2 * 1536 * 640)(A, B)     # three panels
+keep = len(sys.argv) > 2 and sys.argv[2] == "keep"                                # stored-exponentials forward (clip_s_kernel<FWD_E[_L2]>)
+loss = ClipLoss(loss_dtype=torch.float32, panel_bytes=2 * 1536 * 640, keep_exp=keep)(A, B)     # three panels
 loss.backward(); torch.cuda.synchronize()
 torch.save({"loss": loss.detach().cpu(), "dA": A.grad.cpu(), "dB": B.grad.cpu()}, sys.argv[1])
 """
 
 
-def _run(tmp_path, name, env_extra):
+def _run(tmp_path, name, env_extra, *extra):
     out = str(tmp_path / name)
     env = dict(os.environ, **env_extra)
     env.pop("ONEPROT_DZ_L2_HINTS", None) if not env_extra else None
-    p = subprocess.run([sys.executable, "-c", SCRIPT % ROOT, out], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    p = subprocess.run([sys.executable, "-c", SCRIPT % ROOT, out, *extra], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     return torch.load(out)
 
@@ -36,5 +37,12 @@ def _run(tmp_path, name, env_extra):
 def test_l2_hinted_panel_kernel_is_bit_identical(tmp_path):
     base = _run(tmp_path, "base.pt", {})
     hint = _run(tmp_path, "hint.pt", {"ONEPROT_DZ_L2_HINTS": "1"})
+    assert base["loss"].item() == hint["loss"].item()
+    assert torch.equal(base["dA"], hint["dA"]) and torch.equal(base["dB"], hint["dB"])
+
+
+def test_l2_hinted_keeping_forward_is_bit_identical(tmp_path):
+    base = _run(tmp_path, "kbase.pt", {}, "keep")
+    hint = _run(tmp_path, "khint.pt", {"ONEPROT_DZ_L2_HINTS": "1"}, "keep")
     assert base["loss"].item() == hint["loss"].item()
     assert torch.equal(base["dA"], hint["dA"]) and torch.equal(base["dB"], hint["dB"])

@@ -20,6 +20,7 @@ run dz_default    python tools/run_kernel.py dz 16384 32768 1024 10
 run k_fwd         python tools/run_kernel.py fwd 32768 32768 1024 10
 run k_fwd_e       python tools/run_kernel.py fwd_e 32768 32768 1024 10
 run k_dz_e        python tools/run_kernel.py dz_e 32768 32768 1024 10
+ONEPROT_DZ_L2_HINTS=1 run k_fwd_e_l2 python tools/run_kernel.py fwd_e 32768 32768 1024 10
 ONEPROT_DZ_L2_HINTS=1 run dz_l2_hints python tools/run_kernel.py dz 16384 32768 1024 10
 ONEPROT_DZ_L2_HINTS=1 run bench_dz_l2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run host_1024     python tools/host_overhead.py 1024

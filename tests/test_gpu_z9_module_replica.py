@@ -26,7 +26,7 @@ def test_fused_l1_term_matches_torch(shape, dtype):
     x = xh.to(dtype).cuda().requires_grad_(True)
     y = mean_abs(x)
     want = x.detach().double().abs().mean()
-    assert abs(float(y.detach()) - float(want)) <= (1e-6 if dtype == torch.float32 else 4e-3) * float(want)
+    assert abs(float(y.detach()) - float(want)) <= (3e-6 if dtype == torch.float32 else 4e-3) * float(want)
     (y * 3.0).backward()
     ref = 3.0 * torch.sign(x.detach().double()) / x.numel()
     assert torch.allclose(x.grad.double(), ref, rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=0)

@@ -420,9 +420,10 @@ class _ClipLossFunction(torch.autograd.Function):
             # recompute.  A second backward over the same graph (retain_graph) finds E consumed and recomputes.
             ctx.E = None
             Wz = E
-            if cfg.get("keep_overlap") and len(panels) > 1:
-                # keep the panel split: the HBM-bound rescale of panel q + 1 runs on its own stream under the
-                # tensor-bound GEMMs of panel q (the 128-register GEMM launch leaves room for it on every SM)
+            if cfg.get("keep_overlap") and len(panels) > 1 and passes[0][2]:
+                # keep the panel split for the dB GEMM (a split of its K dimension: no tile is lost): the HBM-bound
+                # rescale of panel q + 1 runs on its own stream under the tensor-bound dB GEMM of panel q (the
+                # 128-register GEMM launch leaves room for it on every SM); dA is ONE GEMM over all rows at the end
                 rs_stream = _rescale_stream(dev)
                 ev_rescaled = [None] * len(panels)
             else:
@@ -456,6 +457,20 @@ class _ClipLossFunction(torch.autograd.Function):
             rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
             last_pass = pi == len(passes) - 1
             ev_rs, dB_async = None, None
+
+            def run_dA(r0, rows, Wp, A_rows):
+                chain_a = _GemmChain(rows, d, dA[r0:r0 + rows], sA[r0:r0 + rows], n_bp)
+                for bi, Bp in enumerate(b_pieces):
+                    if rd_global and bi == n_bp - 1:   # last piece: the accumulated (unscaled) value
+                        part_buf = torch.empty(K.gemm_rowdot_scratch_floats(rows, d), dtype=torch.float32, device=dev)
+                        chain_a.add(Wp, False, Bp, True, N, dot_mat=ops.a_head(A_rows), rowdot_part=part_buf)
+                        t = torch.empty(1, dtype=torch.float32, device=dev)
+                        # rows >= `rows` of a slab are never written: sum only the valid part
+                        K.sum_f32(_valid_rowdot(part_buf, rows, d), t)
+                        ds_terms.append(("unit", t))
+                    else:
+                        chain_a.add(Wp, False, Bp, True, N)
+
             for qi, (r0, rows) in enumerate(panels):
                 A_rows = ops.A[r0:r0 + rows]
                 if E is not None and rs_stream is not None:
@@ -483,20 +498,12 @@ class _ClipLossFunction(torch.autograd.Function):
                             side.wait_event(evb)
                             dB_async = comm.reduce_scatter_db(dBp, rank, W, last_pass=last_pass)
                             ev_rs = side.record_event()
-                if rs_stream is not None and qi + 1 < len(panels):    # next panel's rescale, under this panel's GEMMs
+                if rs_stream is not None and qi + 1 < len(panels):    # next panel's rescale, under this panel's dB GEMM
                     _enqueue_rescale(K, rs_stream, ev_rescaled, qi + 1, panels, E, N, off, wr, wc, dg)
-                if want_a:
-                    chain_a = _GemmChain(rows, d, dA[r0:r0 + rows], sA[r0:r0 + rows], n_bp)
-                    for bi, Bp in enumerate(b_pieces):
-                        if rd_global and bi == n_bp - 1:   # last piece: the accumulated (unscaled) value
-                            part_buf = torch.empty(K.gemm_rowdot_scratch_floats(rows, d), dtype=torch.float32, device=dev)
-                            chain_a.add(Wp, False, Bp, True, N, dot_mat=ops.a_head(A_rows), rowdot_part=part_buf)
-                            t = torch.empty(1, dtype=torch.float32, device=dev)
-                            # rows >= `rows` of a slab are never written: sum only the valid part
-                            K.sum_f32(_valid_rowdot(part_buf, rows, d), t)
-                            ds_terms.append(("unit", t))
-                        else:
-                            chain_a.add(Wp, False, Bp, True, N)
+                if want_a and rs_stream is None:
+                    run_dA(r0, rows, Wp, A_rows)
+            if want_a and rs_stream is not None:          # overlapped rescale: every panel is rescaled by now
+                run_dA(0, n, E[:n], ops.A)
             if want_b and exchange_b and push is not None:
                 dBp = comm.finish_pushed_db(n, d, rank, W, last_pass=last_pass)
             elif want_b and exchange_b:

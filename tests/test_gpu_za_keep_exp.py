@@ -143,3 +143,56 @@ def test_overlapped_rescale_matches_one_panel_variant():
         if first is None:
             first = dB1
         assert torch.equal(dB1, first)                                # deterministic run to run
+
+
+# ---- multi-GPU (NVLS or NCCL provider) -------------------------------------------------------------
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _worker(rank, world, port, n, d, results):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oneprot_b200 import ClipLoss
+    a, b = oc.synthetic_pair(n, d, seed=77, rank=rank)
+    variants = {"default": {}, "keep": dict(keep_exp=True), "keep_overlap": dict(keep_exp=True, keep_overlap=True),
+                "keep_seq": dict(keep_exp=True, host_sequencer=True)}
+    rec = {}
+    for ll, gwg in ((False, True), (False, False), (True, True), (True, False)):     # the last one falls back to the recompute
+        for name, kw in variants.items():
+            for rep in range(2):          # twice: both parities of the double-buffered NVLS workspace
+                A = a.cuda().requires_grad_(True)
+                B = b.cuda().requires_grad_(True)
+                m = ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world,
+                             loss_dtype=torch.float32, panel_bytes=2 * (world * n) * 384, **kw)
+                loss = m(A, B)
+                (loss * (1.0 + 0.25 * rank)).backward()
+                torch.cuda.synchronize()
+                m.check_last_call()
+            rec[(ll, gwg, name)] = (loss.item(), A.grad.float().cpu(), B.grad.float().cpu())
+    results[rank] = rec
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("n,d", [(1024, 256)])
+def test_multi_gpu_kept_exponentials_match_the_recompute_path(n, d):
+    import torch.multiprocessing as mp
+    world = min(_ngpu(), 8)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, 29893, n, d, results), nprocs=world, join=True)
+    for r in range(world):
+        rec = results[r]
+        for ll, gwg in ((False, True), (False, False), (True, True), (True, False)):
+            l0, ga0, gb0 = rec[(ll, gwg, "default")]
+            for name in ("keep", "keep_overlap", "keep_seq"):
+                l1, ga1, gb1 = rec[(ll, gwg, name)]
+                assert rel_err(l1, l0) < 1e-6, (r, ll, gwg, name)
+                assert cosine(ga1.numpy(), ga0.numpy()) >= 0.99999 and cosine(gb1.numpy(), gb0.numpy()) >= 0.99999, (r, ll, gwg, name)
+                assert abs(ga1.norm().item() / ga0.norm().item() - 1) < 2e-3 and abs(gb1.norm().item() / gb0.norm().item() - 1) < 2e-3

@@ -159,6 +159,13 @@ int oneprot_retrieval_ranks(const void* S, const void* M, int N, int d, const fl
  * bias_dev may be NULL (no logit_bias). */
 int oneprot_siglip_fwd(const void* A, const void* B_all, int n, int N, int d, const float* scale_dev, const float* bias_dev,
                        float* rowsum, void* scratch, size_t scratch_bytes, void* stream);
+/* Kept-panel variant (opt-in): also writes S[i][j] = sigma(z_ij) - [grow0 + i == j] as bf16 (n rows, row pitch lds >= N,
+ * multiple of 8) - dL/dz up to the constant g / n, so the backward is the two GEMMs on S as it is - and, when sig_rowsum
+ * is not NULL, sig_rowsum[i] = sum_j sigma(z_ij).  Scratch: oneprot_siglip_fwd_keep_scratch_bytes(n, N). */
+size_t oneprot_siglip_fwd_keep_scratch_bytes(int n, int N);
+int oneprot_siglip_fwd_keep(const void* A, const void* B_all, int n, int N, int d, int grow0, const float* scale_dev,
+                            const float* bias_dev, float* rowsum, float* sig_rowsum, void* scratch, size_t scratch_bytes,
+                            void* S, int lds, void* stream);
 int oneprot_siglip_finalize(const float* rowsum, const float* diag, int n, const float* scale_dev, const float* bias_dev,
                             float* loss_out, void* stream);
 size_t oneprot_siglip_dz_scratch_bytes(int rows, int N);

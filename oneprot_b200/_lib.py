@@ -81,6 +81,8 @@ SIGNATURES = {
     "oneprot_mc_reduce_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "oneprot_split_fp32": (_i, [_fp, _vp, _i, _i, _i, _i, _vp]),
     "oneprot_siglip_fwd": (_i, [_vp, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "oneprot_siglip_fwd_keep_scratch_bytes": (_sz, [_i, _i]),
+    "oneprot_siglip_fwd_keep": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _sz, _vp, _i, _vp]),
     "oneprot_siglip_finalize": (_i, [_fp, _fp, _i, _fp, _fp, _fp, _vp]),
     "oneprot_siglip_dz_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_siglip_dz_panel": (_i, [_vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _vp, _i, _fp, _vp, _sz, _vp]),

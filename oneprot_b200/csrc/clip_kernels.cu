@@ -291,7 +291,9 @@ enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4,    // 
        EPI_DZ_L2 = 7,                 // EPI_DZ with L2 hints: panel stores evict-first, operand loads evict-last (A/B experiment)
        EPI_FWD_E = 8,                 // EPI_FWD that also keeps the exponentials e_ij as a bf16 panel: the backward then
                                       // rescales them in place (dz_from_exp_kernel) instead of recomputing the logits
-       EPI_FWD_E_L2 = 9 };            // EPI_FWD_E with the L2 hints of EPI_DZ_L2 (same A/B experiment)
+       EPI_FWD_E_L2 = 9,              // EPI_FWD_E with the L2 hints of EPI_DZ_L2 (same A/B experiment)
+       EPI_SFWD_K = 10 };             // EPI_SFWD that also keeps sigma(z_ij) - [i == j] as a bf16 panel: dL/dz up to the constant
+                                      // g / n, so the SigLIP backward needs neither a recompute nor a rescale pass
 
 template <int EPI>
 struct SCfg {
@@ -300,9 +302,37 @@ struct SCfg {
   static constexpr bool L2_HINTS = (EPI == EPI_DZ_L2 || EPI == EPI_FWD_E_L2);
   static constexpr bool KEEP_E = (EPI == EPI_FWD_E || EPI == EPI_FWD_E_L2);
   static constexpr bool SUMS = (EPI == EPI_FWD || KEEP_E);                    // row / column exp-sums (+ the fused all-gather)
-  static constexpr int STAGING = (PANEL || KEEP_E) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX / RANK / SFWD need none
+  static constexpr bool KEEP_S = (EPI == EPI_SFWD_K);
+  static constexpr int STAGING = (PANEL || KEEP_E || KEEP_S) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX / RANK / SFWD need none
   static constexpr int SMEM = smem_bytes(NS, STAGING);
 };
+
+// Kept-panel forwards (FWD_E, SFWD_K): 32 columns of this thread's row -> bf16 -> the warp group's SWIZZLE_128B staging
+// box {64 cols, 128 rows}; every second call the box goes out by one TMA store (the box protocol of the dL/dZ panel).
+template <bool HINT>
+__device__ __forceinline__ void keep_stage_store(const float (&v)[32], int cc, int r, int h, uint32_t stage_s, const uint8_t* box,
+                                                 bool store_issuer, const CUtensorMap* map, int col0, int row0, uint64_t policy) {
+  if ((cc & 1) == 0) {
+    if (store_issuer) bulk_wait_read<0>();       // the previous TMA store must have finished reading the staging box
+    named_bar_sync(2 + h, 128);
+  }
+  const uint32_t line = stage_s + r * 128;       // row r of the box: 128-byte line, 16-byte slots XOR-swizzled by (r % 8)
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4) {
+    const uint32_t slot = static_cast<uint32_t>(((cc & 1) * 4 + v4) ^ (r & 7));
+    st_shared_v4(line + slot * 16, pack_bf16x2(v[v4 * 8], v[v4 * 8 + 1]), pack_bf16x2(v[v4 * 8 + 2], v[v4 * 8 + 3]),
+                 pack_bf16x2(v[v4 * 8 + 4], v[v4 * 8 + 5]), pack_bf16x2(v[v4 * 8 + 6], v[v4 * 8 + 7]));
+  }
+  if (cc & 1) {
+    fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA engine
+    named_bar_sync(2 + h, 128);
+    if (store_issuer) {
+      if (HINT) tma_store_2d_hint(map, box, col0, row0, policy);
+      else tma_store_2d(map, box, col0, row0);
+      bulk_commit();
+    }
+  }
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -426,10 +456,10 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int r = q * 32 + lane; // row inside the tile
     float c, negG;
     constexpr bool PANEL = SCfg<EPI>::PANEL;
-    constexpr bool SUMS = SCfg<EPI>::SUMS, KEEP_E = SCfg<EPI>::KEEP_E;
+    constexpr bool SUMS = SCfg<EPI>::SUMS, KEEP_E = SCfg<EPI>::KEEP_E, KEEP_S = SCfg<EPI>::KEEP_S;
     if (EPI == EPI_MAX || EPI == EPI_RCMAX) { c = __ldg(p.scale) * LOG2E; negG = 0.f; }
     else if (EPI == EPI_RANK) { c = 1.f; negG = 0.f; }
-    else if (EPI == EPI_SFWD || EPI == EPI_SDZ) {
+    else if (EPI == EPI_SFWD || EPI == EPI_SDZ || KEEP_S) {
       // SigLIP: x = log2(e) (logit_scale <a, b> + logit_bias); the bias pointer travels in p.wc (no column weights here)
       c = __ldg(p.scale) * LOG2E;
       negG = p.wc ? __ldg(p.wc) * LOG2E : 0.f;
@@ -469,6 +499,8 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         bool diag_tile = false;
         if (PANEL) {
           if (rowok) { wr_i = __ldg(p.wr + i); dg_i = __ldg(p.dg + i); }
+        }
+        if (PANEL || KEEP_S) {
           const int g0 = p.grow0 + ib * BM;       // global rows [g0, g0+128)
           diag_tile = (g0 < j0 + 128) && (j0 < g0 + BM);
         }
@@ -476,6 +508,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
         float rsum = 0.f;
+        float rsum2 = 0.f;                        // SFWD_K: row sum of sigma(z) (for d logit_bias)
         // DZ keeps no per-column accumulators, so the whole 128-column row slice fits in registers:
         // read it at once and hand the TMEM buffer back before the (store-paced) rest of the epilogue.
         float vall[PANEL ? 4 : 1][32];
@@ -541,7 +574,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
             continue;
           }
-          if (EPI == EPI_SFWD) {
+          if (EPI == EPI_SFWD || KEEP_S) {
             // softplus in log2 units, overflow-free: log2(1 + 2^x) = max(x, 0) + log2(1 + 2^-|x|)
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
@@ -553,7 +586,15 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               const float l = (e < 9.765625e-4f) ? e * fmaf(-0.72134752f, e, LOG2E) : __log2f(1.f + e);
               const float sp = fmaxf(x, 0.f) + l;
               rsum += ok ? sp : 0.f;
+              if (KEEP_S) {
+                // sigma(z) = 1 / (1 + 2^-x) from the same exponential: 1 / (1 + e) for x >= 0, e / (1 + e) below
+                const float sg = ok ? __fdividef(x >= 0.f ? 1.f : e, 1.f + e) : 0.f;
+                rsum2 += sg;
+                v[k] = sg - ((diag_tile && p.grow0 + i == j0 + cc * 32 + k) ? 1.f : 0.f);
+              }
             }
+            if (KEEP_S)
+              keep_stage_store<false>(v, cc, r, h, stage_s, s.staging + h * 16384, store_issuer, &mapW, j0 + (cc >> 1) * 64, ib * BM, 0);
             continue;
           }
           if (SUMS) {
@@ -575,30 +616,9 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 if (KEEP_E) v[k] = e;
               }
             }
-            if (KEEP_E) {
-              // the exponentials of this 32-column slice -> bf16 -> the staging box of this warp group -> TMA store
-              // (same box protocol as the dL/dZ panel below)
-              if ((cc & 1) == 0) {
-                if (store_issuer) bulk_wait_read<0>();
-                named_bar_sync(2 + h, 128);
-              }
-              const uint32_t line = stage_s + r * 128;
-#pragma unroll
-              for (int v4 = 0; v4 < 4; ++v4) {
-                const uint32_t slot = static_cast<uint32_t>(((cc & 1) * 4 + v4) ^ (r & 7));
-                st_shared_v4(line + slot * 16, pack_bf16x2(v[v4 * 8], v[v4 * 8 + 1]), pack_bf16x2(v[v4 * 8 + 2], v[v4 * 8 + 3]),
-                             pack_bf16x2(v[v4 * 8 + 4], v[v4 * 8 + 5]), pack_bf16x2(v[v4 * 8 + 6], v[v4 * 8 + 7]));
-              }
-              if (cc & 1) {
-                fence_proxy_async();
-                named_bar_sync(2 + h, 128);
-                if (store_issuer) {
-                  if (SCfg<EPI>::L2_HINTS) tma_store_2d_hint(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM, pol_stream);
-                  else tma_store_2d(&mapW, s.staging + h * 16384, j0 + (cc >> 1) * 64, ib * BM);
-                  bulk_commit();
-                }
-              }
-            }
+            if (KEEP_E)   // the exponentials of this 32-column slice join the kept panel
+              keep_stage_store<SCfg<EPI>::L2_HINTS>(v, cc, r, h, stage_s, s.staging + h * 16384, store_issuer, &mapW,
+                                                    j0 + (cc >> 1) * 64, ib * BM, pol_stream);
           } else {
             if ((cc & 1) == 0) {
               // the previous TMA store must have finished reading the staging box
@@ -654,9 +674,10 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
           }
         }
-        if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD || (EPI == EPI_SDZ && p.rowpart)) {
+        if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK || EPI == EPI_SFWD || KEEP_S || (EPI == EPI_SDZ && p.rowpart)) {
           p.rowpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum;   // ldr covers nI*128 rows
         }
+        if (KEEP_S && p.colpart) p.colpart[static_cast<size_t>(jb * 2 + h) * p.ldr + i] = rsum2;   // second row-partial buffer
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK) {
@@ -671,7 +692,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
       }
     }
-    if ((PANEL || KEEP_E) && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
+    if ((PANEL || KEEP_E || KEEP_S) && store_issuer) bulk_wait<0>();   // panel fully written before the CTA retires
     if (EPI == EPI_MAX) {
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
@@ -1559,6 +1580,46 @@ int oneprot_siglip_fwd(const void* A, const void* B_all, int n, int N, int d, co
   op::clip_s_kernel<op::EPI_SFWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   op::reduce_slots_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
   g_launches += 2;
+  OP_CUDA(cudaGetLastError());
+  return ONEPROT_OK;
+}
+
+size_t oneprot_siglip_fwd_keep_scratch_bytes(int n, int N) { return 2 * oneprot_clip_fwd_scratch_bytes(n, N); }
+
+int oneprot_siglip_fwd_keep(const void* A, const void* B_all, int n, int N, int d, int grow0, const float* scale_dev,
+                            const float* bias_dev, float* rowsum, float* sig_rowsum, void* scratch, size_t scratch_bytes, void* S,
+                            int lds, void* stream) {
+  if (!A || !B_all || !scale_dev || !rowsum || !scratch || !S) return fail(ONEPROT_ERR_ARG, "siglip_fwd_keep: null pointer");
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8 || grow0 < 0 || grow0 + n > N) return fail(ONEPROT_ERR_ARG, "siglip_fwd_keep: bad sizes");
+  if (lds < N || lds % 8 || (reinterpret_cast<uintptr_t>(S) & 15))
+    return fail(ONEPROT_ERR_ARG, "siglip_fwd_keep: S must be 16-byte aligned with a row pitch lds >= N that is a multiple of 8");
+  if (scratch_bytes < oneprot_siglip_fwd_keep_scratch_bytes(n, N)) return fail(ONEPROT_ERR_ARG, "siglip_fwd_keep: scratch too small");
+  if (optrace::recording())
+    optrace::add("siglip_fwd_keep A=%p B=%p n=%d N=%d d=%d grow0=%d scale=%p bias=%p rowsum=%p sig_rowsum=%p scratch=%p S=%p lds=%d st=%p", A, B_all,
+                 n, N, d, grow0, (const void*)scale_dev, (const void*)bias_dev, (void*)rowsum, (void*)sig_rowsum, scratch, S, lds, stream);
+  const int launches = sig_rowsum ? 3 : 2;
+  if (optrace::dry()) { g_launches += launches; return ONEPROT_OK; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  op::SParams p{};
+  s_schedule(n, N, 2, p);
+  p.rows = n; p.N = N; p.nK = cdiv(d, op::BK); p.grow0 = grow0;
+  p.scale = scale_dev; p.wc = bias_dev;
+  p.ldr = p.nI * op::BM; p.ldc = p.nJ * op::BN;
+  p.rowpart = static_cast<float*>(scratch);
+  // second row-partial buffer (row sums of sigma), same [2 nJ][ldr] layout, in the second half of the scratch
+  p.colpart = sig_rowsum ? reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + oneprot_clip_fwd_scratch_bytes(n, N)) : nullptr;
+  CUtensorMap mapA, mapB, mapS;
+  int rc;
+  if ((rc = make_map(&mapA, A, d, n, d, op::BM))) return rc;
+  if ((rc = make_map(&mapB, B_all, d, N, d, op::BN))) return rc;
+  if ((rc = make_map(&mapS, S, N, n, lds, op::BM))) return rc;
+  constexpr int smem = op::SCfg<op::EPI_SFWD_K>::SMEM;
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_SFWD_K>, smem))) return rc;
+  const int grid = std::min(num_sms(), p.nJ * p.nChunks);
+  op::clip_s_kernel<op::EPI_SFWD_K><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapS, p);
+  op::reduce_slots_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum);
+  if (sig_rowsum) op::reduce_slots_kernel<<<cdiv(n, 32), 256, 0, st>>>(p.colpart, 2 * p.nJ, p.ldr, n, sig_rowsum);
+  g_launches += launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
 }

@@ -261,6 +261,22 @@ def siglip_fwd(A, B_all, scale_dev, bias_dev, rowsum, scratch=None):
     return scratch
 
 
+def siglip_fwd_keep(A, B_all, grow0: int, scale_dev, bias_dev, rowsum, S, sig_rowsum=None):
+    """siglip_fwd that also keeps S[i, j] = sigma(z_ij) - [grow0+i == j] (bf16, >= n rows, row pitch >= N) and, optionally,
+    the row sums of sigma."""
+    _need_cuda(A, B_all, scale_dev, bias_dev, rowsum, S, sig_rowsum)
+    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all"); _need(S, torch.bfloat16, "S")
+    n, d = A.shape
+    N = B_all.shape[0]
+    if S.dim() != 2 or S.shape[0] < n or S.stride(1) != 1:
+        raise ValueError("S must be a row-major 2-D tensor with at least n rows")
+    lib = _lib.load()
+    need = int(lib.oneprot_siglip_fwd_keep_scratch_bytes(n, N))
+    scratch = torch.empty(need, dtype=torch.uint8, device=A.device)
+    check(lib.oneprot_siglip_fwd_keep(ptr(A), ptr(B_all), n, N, d, grow0, ptr(scale_dev), ptr(bias_dev), ptr(rowsum), ptr(sig_rowsum),
+                                      ptr(scratch), need, ptr(S), S.stride(0), _stream()), "oneprot_siglip_fwd_keep")
+
+
 def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
     _need_cuda(rowsum, diag, scale_dev, bias_dev, loss_out)
     check(_lib.load().oneprot_siglip_finalize(ptr(rowsum), ptr(diag), rowsum.numel(), ptr(scale_dev), ptr(bias_dev), ptr(loss_out),

@@ -126,6 +126,21 @@ void emu_siglip_fwd(const void* A, const void* B, int n, int N, int d, const flo
   reduce(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum, false);
 }
 
+void emu_siglip_fwd_keep(const void* A, const void* B, int n, int N, int d, int grow0, const float* scale, const float* bias,
+                         float* rowsum, float* sig_rowsum, float* scratch, float* scratch2, void* S, int lds) {
+  op::SParams p{};
+  s_common(p, n, N, d, 2, scratch);
+  p.grow0 = grow0; p.scale = scale; p.wc = bias;
+  p.colpart = sig_rowsum ? scratch2 : nullptr;
+  CUtensorMap mA, mB, mS;
+  make_map(&mA, A, d, n, d, op::BM);
+  make_map(&mB, B, d, N, d, op::BN);
+  make_map(&mS, S, N, n, lds, op::BM);
+  run_s<op::EPI_SFWD_K>(mA, mB, mS, p);
+  reduce(p.rowpart, 2 * p.nJ, p.ldr, n, rowsum, false);
+  if (sig_rowsum) reduce(p.colpart, 2 * p.nJ, p.ldr, n, sig_rowsum, false);
+}
+
 void emu_siglip_dz(const void* A_rows, const void* B, int rows, int N, int d, int grow0, const float* scale, const float* bias,
                    const float* wr, const float* dg, void* Wz, int ldw, float* sig_rowsum, float* scratch) {
   op::SParams p{};

@@ -213,6 +213,15 @@ def siglip_fwd(A, B_all, scale_dev, bias_dev, rowsum, scratch=None):
     return scratch
 
 
+def siglip_fwd_keep(A, B_all, grow0, scale_dev, bias_dev, rowsum, S, sig_rowsum=None):
+    CALLS.append("siglip_fwd_keep")
+    n, d = A.shape
+    N = B_all.shape[0]
+    s1, s2 = _scratch(n, N), _scratch(n, N)
+    _tc().emu_siglip_fwd_keep(_p(A), _p(B_all), n, N, d, grow0, _p(scale_dev), _p(bias_dev), _p(rowsum), _p(sig_rowsum), _p(s1), _p(s2),
+                              _p(S), S.stride(0))
+
+
 def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
     CALLS.append("siglip_finalize")
     _vec().emu_siglip_finalize(_p(rowsum), _p(diag), rowsum.numel(), _p(scale_dev), _p(bias_dev), _p(loss_out))

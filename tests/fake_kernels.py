@@ -354,6 +354,20 @@ def siglip_fwd(A, B_all, scale_dev, bias_dev, rowsum, scratch=None):
     return scratch
 
 
+def siglip_fwd_keep(A, B_all, grow0, scale_dev, bias_dev, rowsum, S, sig_rowsum=None):
+    CALLS.append("siglip_fwd_keep")
+    b = 0.0 if bias_dev is None else float(bias_dev[0])
+    x = LOG2E * (float(scale_dev[0]) * (A.double() @ B_all.double().T) + b)
+    rowsum.copy_((torch.clamp(x, min=0) + torch.log2(1 + torch.exp2(-x.abs()))).sum(1).float())
+    sg = 1.0 / (1.0 + torch.exp2(-x))
+    if sig_rowsum is not None:
+        sig_rowsum.copy_(sg.sum(1).float())
+    n, N = x.shape
+    idx = torch.arange(n)
+    sg[idx, grow0 + idx] -= 1.0
+    S[:n, :N] = sg.float().to(torch.bfloat16)
+
+
 def siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss_out):
     CALLS.append("siglip_finalize")
     b = 0.0 if bias_dev is None else float(bias_dev[0])

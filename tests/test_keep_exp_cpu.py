@@ -150,3 +150,31 @@ def test_overlapped_rescale_gives_the_same_gradients(prov, monkeypatch):
         assert cosine(res[-1][0], ref.dA) > 0.9999 and cosine(res[-1][1], ref.dB) > 0.9999
     assert np.array_equal(res[0][0], res[1][0])                      # dA rows are independent of the split
     assert cosine(res[0][1], res[1][1]) > 0.999999
+
+
+@pytest.mark.parametrize("n,N,d,off", [(25, 25, 64, 0), (130, 700, 72, 400), (256, 512, 128, 256)])
+def test_siglip_keeping_forward_kernel_source_matches_float64(n, N, d, off):
+    """clip_s_kernel<SFWD_K> (CPU emulation): softplus row sums as SFWD, S = sigma(z) - [i == j] as a bf16 panel clipped to
+    n x N, row sums of sigma."""
+    K = _provider("emu")
+    gen = torch.Generator().manual_seed(n + N)
+    A = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1).to(torch.bfloat16)
+    B = torch.nn.functional.normalize(torch.randn(N, d, generator=gen), dim=-1).to(torch.bfloat16)
+    scale, bias = torch.tensor([9.0]), torch.tensor([-4.0])
+    ld = (N + 63) // 64 * 64
+    out = {}
+    for name, P in (("emu", K), ("fake", fake_kernels)):
+        S = torch.full((n + 3, ld), 7.0, dtype=torch.bfloat16)
+        rs, sig = torch.empty(n), torch.empty(n)
+        P.siglip_fwd_keep(A, B, off, scale, bias, rs, S, sig_rowsum=sig)
+        out[name] = (S, rs, sig)
+    S, rs, sig = out["emu"]
+    S0, rs0, sig0 = out["fake"]
+    rs_plain = torch.empty(n)
+    K.siglip_fwd(A, B, scale, bias, rs_plain)
+    assert torch.equal(rs, rs_plain)                                                  # the softplus sums are SFWD's
+    assert np.allclose(rs.numpy(), rs0.numpy(), rtol=1e-5) and np.allclose(sig.numpy(), sig0.numpy(), rtol=1e-5)
+    assert torch.all(S[n:] == 7.0) and torch.all(S[:, N:] == 7.0)                   # clipped stores
+    assert float((S[:n, :N].float() - S0[:n, :N].float()).abs().max()) <= 2 ** -8     # one bf16 ulp of values in [-1, 1]
+    idx = torch.arange(n)
+    assert torch.all(S[idx, off + idx].float() < 0) and torch.all(S[:n, :N].float() <= 1)

@@ -74,7 +74,20 @@ class _SigLipFunction(torch.autograd.Function):
             stats = torch.zeros(4, dtype=torch.float32, device=dev)
             K.rowstats(ops.A, B_all, off, diag, stats)                  # diag[i] = <a_i, b_{off+i}>: the label logits
             rowsum = torch.empty(n, dtype=torch.float32, device=dev)
-            K.siglip_fwd(ops.A, B_all, scale_dev, bias_dev, rowsum)
+            # Kept-panel backward (opt-in): dL/dz_ij = (g / n) (sigma(z_ij) - [i == j]) has a constant weight, so a forward
+            # that keeps S = sigma - [i == j] as a bf16 panel makes the backward the two GEMMs on S as it is - no
+            # recompute, no rescale pass (3 GEMM units per step instead of 4).
+            N = W * n
+            ldw = (N + 63) // 64 * 64
+            ctx.S = ctx.sig = None
+            if (cfg.get("keep_exp") and not ops.split and any(ctx.needs_input_grad[:4])
+                    and 2 * ldw * ((n + 127) // 128 * 128) <= cfg.get("keep_bytes", _cl.DEFAULT_KEEP_BYTES)):
+                ctx.S = torch.empty((n + 127) // 128 * 128, ldw, dtype=torch.bfloat16, device=dev)
+                if bias_dev is not None and ctx.needs_input_grad[3]:
+                    ctx.sig = torch.empty(n, dtype=torch.float32, device=dev)
+                K.siglip_fwd_keep(ops.A, B_all, off, scale_dev, bias_dev, rowsum, ctx.S, sig_rowsum=ctx.sig)
+            else:
+                K.siglip_fwd(ops.A, B_all, scale_dev, bias_dev, rowsum)
             loss32 = torch.empty(1, dtype=torch.float32, device=dev)
             K.siglip_finalize(rowsum, diag, scale_dev, bias_dev, loss32)
             ctx.cfg, ctx.ops, ctx.B_all, ctx.scale_dev, ctx.bias_dev = cfg, ops, B_all, scale_dev, bias_dev
@@ -102,6 +115,17 @@ class _SigLipFunction(torch.autograd.Function):
             want_a, want_b = bool(need_a or need_s), bool(need_b or W > 1)   # with W > 1 every rank enters the reduce-scatter
             grad_dtype = torch.float32 if ops.split else torch.bfloat16
             ldw = (N + 63) // 64 * 64
+            if ctx.S is not None:
+                # kept panel: S already is dL/dz / (logit_scale g / n); the constant goes into the GEMM epilogues' row scale
+                S = ctx.S[:n]
+                dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
+                dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
+                if want_b:
+                    coef_N = (ctx.scale_dev * g32 / n).expand(N).contiguous()
+                    _cl._GemmChain(N, d, dBp, coef_N, 1).add(S, True, ops.A, True, n)
+                if want_a:
+                    _cl._GemmChain(n, d, dA, coef, 1).add(S, False, B_all, True, N)
+                return _SigLipFunction._finish(ctx, K, dA, dBp, ctx.sig, g32, need_a, need_b, need_s, need_bias)
             rows_cap = max(128, (cfg["panel_bytes"] // (2 * ldw)) // 128 * 128)
             if rows_cap < n:                                           # balanced, wave-aligned panels (as clip_loss.py)
                 unit = K.panel_row_unit(d)
@@ -132,28 +156,39 @@ class _SigLipFunction(torch.autograd.Function):
                     chain_a = _cl._GemmChain(rows, d, dA[r0:r0 + rows], None, n_bp)
                     for Bp in b_pieces:
                         chain_a.add(Wp, False, Bp, True, N)
-            if want_b and W > 1:
-                dBp = _reduce_scatter_rows(dBp, rank, W, group)
-            grad_s = grad_bias = None
-            if need_s:      # d loss / d scale = sum_ij dL/dz_ij <a_i, b_j> = (1 / scale) sum_i <a_i, dA_i>
-                sdt, sdev, sshape = ctx.scalar_meta[0]
-                grad_s = (_cl._rowdot_sum(ops.a_head(ops.A), dA) / ctx.scale_dev).reshape(sshape).to(device=sdev, dtype=sdt)
-            if need_bias:   # d loss / d bias = sum_ij dL/dz_ij = (g / n) (sum_ij sigma(z_ij) - n)
-                bdt, bdev, bshape = ctx.scalar_meta[1]
-                tot = torch.empty(1, dtype=torch.float32, device=dev)
-                K.sum_f32(sig, tot)
-                grad_bias = ((tot - n) * g32 / n).reshape(bshape).to(device=bdev, dtype=bdt)
-            return _cl._finish_grad(dA, ops, need_a), _cl._finish_grad(dBp, ops, need_b), grad_s, grad_bias, None
+            return _SigLipFunction._finish(ctx, K, dA, dBp, sig, g32, need_a, need_b, need_s, need_bias)
+
+    @staticmethod
+    def _finish(ctx, K, dA, dBp, sig, g32, need_a, need_b, need_s, need_bias):
+        """Exchange of the partial dB, scalar gradients, final dtypes (shared by the panel and the kept-panel backward)."""
+        cfg, ops = ctx.cfg, ctx.ops
+        W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
+        n, dev = ops.n, ops.A.device
+        if dBp is not None and W > 1:
+            dBp = _reduce_scatter_rows(dBp, rank, W, group)
+        grad_s = grad_bias = None
+        if need_s:      # d loss / d scale = sum_ij dL/dz_ij <a_i, b_j> = (1 / scale) sum_i <a_i, dA_i>
+            sdt, sdev, sshape = ctx.scalar_meta[0]
+            grad_s = (_cl._rowdot_sum(ops.a_head(ops.A), dA) / ctx.scale_dev).reshape(sshape).to(device=sdev, dtype=sdt)
+        if need_bias:   # d loss / d bias = sum_ij dL/dz_ij = (g / n) (sum_ij sigma(z_ij) - n)
+            bdt, bdev, bshape = ctx.scalar_meta[1]
+            tot = torch.empty(1, dtype=torch.float32, device=dev)
+            K.sum_f32(sig, tot)
+            grad_bias = ((tot - n) * g32 / n).reshape(bshape).to(device=bdev, dtype=bdt)
+        return _cl._finish_grad(dA, ops, need_a), _cl._finish_grad(dBp, ops, need_b), grad_s, grad_bias, None
 
 
 class SigLipLoss(nn.Module):
     """B200-native drop-in for the reference ``SigLipLoss`` (loss.py:204-311).
 
     Extra keyword-only arguments: ``loss_dtype`` (dtype of the returned scalar, default = input dtype
-    like the reference), ``panel_bytes`` (bound of the bf16 dL/dZ panel), ``group`` (process group)."""
+    like the reference), ``panel_bytes`` (bound of the bf16 dL/dZ panel), ``group`` (process group),
+    ``keep_exp`` / ``keep_bytes`` (opt-in, also ONEPROT_KEEP_EXP=1: the forward keeps sigma(z) - [i == j] as a
+    bf16 n x N panel and the backward is the two GEMMs on it - no recompute, no panel kernel)."""
 
     def __init__(self, cache_labels=False, rank=0, world_size=1, bidir=True, use_horovod=False, *,
-                 loss_dtype: Optional[torch.dtype] = None, panel_bytes: int = _cl.DEFAULT_PANEL_BYTES, group=None):
+                 loss_dtype: Optional[torch.dtype] = None, panel_bytes: int = _cl.DEFAULT_PANEL_BYTES, group=None,
+                 keep_exp: Optional[bool] = None, keep_bytes: int = _cl.DEFAULT_KEEP_BYTES):
         super().__init__()
         self.cache_labels = cache_labels
         self.rank = rank
@@ -164,6 +199,8 @@ class SigLipLoss(nn.Module):
         self.loss_dtype = loss_dtype
         self.panel_bytes = int(panel_bytes)
         self.group = group
+        self.keep_exp = (__import__("os").environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
+        self.keep_bytes = int(keep_bytes)
         self.prev_num_logits = 0
         self.labels = {}
         self.last_loss_fp32 = None
@@ -196,7 +233,7 @@ class SigLipLoss(nn.Module):
             if dist.get_world_size(self.group) != self.world_size:
                 raise RuntimeError("SigLipLoss world_size does not match the process group")
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, loss_dtype=self.loss_dtype,
-                   panel_bytes=self.panel_bytes)
+                   panel_bytes=self.panel_bytes, keep_exp=self.keep_exp, keep_bytes=self.keep_bytes)
         loss, loss32 = _SigLipFunction.apply(A, B, _scalar_in(logit_scale, A.device), _scalar_in(logit_bias, A.device), cfg)
         self.last_loss_fp32 = loss32
         return {"contrastive_loss": loss} if output_dict else loss

@@ -18,14 +18,15 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("tag", ["train", "paper", "odd"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_siglip_golden_single_gpu(tag, dtype):
+@pytest.mark.parametrize("keep", [False, True])          # True: kept sigma panel (clip_s_kernel<SFWD_K>), no panel kernel in the backward
+def test_siglip_golden_single_gpu(tag, dtype, keep):
     from oneprot_b200.siglip_loss import SigLipLoss
     g = load_golden("siglip_single.npz")
     a, b = bf16_from_bits(g[f"{tag}_A_bf16"]), bf16_from_bits(g[f"{tag}_B_bf16"])
     A = a.to(dtype).cuda().requires_grad_(True)
     B = b.to(dtype).cuda().requires_grad_(True)
     bias = float(g[f"{tag}_bias"]) if bool(g[f"{tag}_has_bias"]) else None
-    m = SigLipLoss()
+    m = SigLipLoss(keep_exp=keep)
     st = torch.tensor(float(g[f"{tag}_scale"]), device="cuda", requires_grad=True)
     bt = None if bias is None else torch.tensor(bias, device="cuda", requires_grad=True)
     loss = m(A, B, st, bt)
@@ -40,9 +41,10 @@ def test_siglip_golden_single_gpu(tag, dtype):
         assert abs(np.linalg.norm(got.double().cpu().numpy()) / np.linalg.norm(want) - 1) < 1e-2
 
 
+@pytest.mark.parametrize("keep", [False, True])
 @pytest.mark.parametrize("n,d,scale,bias,panel_rows", [(1000, 256, 10.0, -10.0, None), (2048, 1024, 1.0, None, 768),
                                                         (300, 64, 25.0, 3.0, None)])
-def test_siglip_vs_closed_form(n, d, scale, bias, panel_rows):
+def test_siglip_vs_closed_form(n, d, scale, bias, panel_rows, keep):
     from oneprot_b200.siglip_loss import SigLipLoss
     a, b = oc.synthetic_pair(n, d, seed=n + d, temperature_into_b=(bias is None))
     ref = oc.siglip_closed_form(a.double().numpy(), b.double().numpy(), scale, 0.0 if bias is None else bias)
@@ -51,7 +53,7 @@ def test_siglip_vs_closed_form(n, d, scale, bias, panel_rows):
     for _ in range(2):                                 # twice: bit-reproducible
         A = a.cuda().requires_grad_(True)
         B = b.cuda().requires_grad_(True)
-        m = SigLipLoss(loss_dtype=torch.float32, **kw)
+        m = SigLipLoss(loss_dtype=torch.float32, keep_exp=keep, **kw)
         loss = m(A, B, scale, None if bias is None else torch.tensor(bias))
         loss.backward()
         outs.append((loss.item(), A.grad.clone(), B.grad.clone()))

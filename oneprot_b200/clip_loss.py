@@ -25,6 +25,7 @@ reduce-scattered.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -45,10 +46,10 @@ except ImportError:  # pragma: no cover
 _KERNELS = _cuda_kernels
 
 # bound of the bf16 dL/dZ panel workspace: 1.25 GiB lets N = 32768 run as two wave-aligned panels
-DEFAULT_PANEL_BYTES = int(__import__("os").environ.get("ONEPROT_PANEL_BYTES", 5 << 28))
+DEFAULT_PANEL_BYTES = int(os.environ.get("ONEPROT_PANEL_BYTES", 5 << 28))
 
 # bound of the stored-exponentials panel (keep_exp=True): n x N bf16 per rank, 2 GiB at N = 32768 on one GPU
-DEFAULT_KEEP_BYTES = int(__import__("os").environ.get("ONEPROT_KEEP_BYTES", 8 << 30))
+DEFAULT_KEEP_BYTES = int(os.environ.get("ONEPROT_KEEP_BYTES", 8 << 30))
 
 _SCALE_CACHE = {}               # (device, python float) -> 1-element fp32 device tensor
 _RESCALE_STREAMS = {}           # device -> stream of the overlapped rescale (keep_overlap)
@@ -633,9 +634,9 @@ class ClipLoss(nn.Module):
         if graph and (world_size != 1 or robust == "auto"):
             raise ValueError("graph=True needs world_size == 1 and a robust mode that is decided on the host side up front")
         self.graph = bool(graph)
-        self.keep_exp = (__import__("os").environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
+        self.keep_exp = (os.environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
         self.keep_bytes = int(keep_bytes)
-        self.keep_overlap = ((__import__("os").environ.get("ONEPROT_KEEP_OVERLAP") == "1") if keep_overlap is None
+        self.keep_overlap = ((os.environ.get("ONEPROT_KEEP_OVERLAP") == "1") if keep_overlap is None
                              else bool(keep_overlap))
         self._graphs = {}            # (shape, dtype, gradient pattern, scale kind) -> GraphedStep
         # cache state (same attributes as the reference, loss.py:68-70)

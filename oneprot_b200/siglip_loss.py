@@ -24,6 +24,7 @@ parameters later).  Exchanges go through torch.distributed (all-gather / reduce-
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -199,7 +200,7 @@ class SigLipLoss(nn.Module):
         self.loss_dtype = loss_dtype
         self.panel_bytes = int(panel_bytes)
         self.group = group
-        self.keep_exp = (__import__("os").environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
+        self.keep_exp = (os.environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
         self.keep_bytes = int(keep_bytes)
         self.prev_num_logits = 0
         self.labels = {}

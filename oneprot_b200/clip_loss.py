@@ -24,7 +24,6 @@ reduce-scattered.
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Optional
 

@@ -1,4 +1,4 @@
-import os, sys, time
+import os
 import torch, torch.distributed as dist
 import torch.distributed._symmetric_memory as symm
 world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"])

@@ -1,5 +1,5 @@
 """Kernel timeline of ClipLoss steps on rank 0 (torch.profiler / CUPTI): per-kernel durations and idle gaps."""
-import os, sys, json, collections
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 from torch.profiler import profile, ProfilerActivity

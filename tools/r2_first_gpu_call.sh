@@ -16,6 +16,7 @@ ONEPROT_SEQ=1 run bench_seq python bench.py --steps 10 --warmup 3 --no-cpu-basel
 ONEPROT_KEEP_EXP=1 run bench_keep_exp python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 run bench_keep_overlap2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 ONEPROT_PANEL_BYTES=$((640<<20)) run bench_keep_overlap4 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 ONEPROT_PANEL_BYTES=$((320<<20)) run bench_keep_overlap8 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run dz_default    python tools/run_kernel.py dz 16384 32768 1024 10
 run k_fwd         python tools/run_kernel.py fwd 32768 32768 1024 10
 run k_fwd_e       python tools/run_kernel.py fwd_e 32768 32768 1024 10
@@ -27,5 +28,5 @@ run host_1024     python tools/host_overhead.py 1024
 run host_4096     python tools/host_overhead.py 4096
 run eager_bar     python tests/perf_eager_bar.py --sizes 8192,32768 --reps 5
 run heads_bench   python tools/bench_heads.py
-grep -h '"metric"' gpurun_out/bench_default.log gpurun_out/bench_seq.log gpurun_out/bench_keep_exp.log gpurun_out/bench_keep_overlap2.log gpurun_out/bench_keep_overlap4.log > gpurun_out/r2_bench_lines.json
+grep -h '"metric"' gpurun_out/bench_default.log gpurun_out/bench_seq.log gpurun_out/bench_keep_exp.log gpurun_out/bench_keep_overlap2.log gpurun_out/bench_keep_overlap4.log gpurun_out/bench_keep_overlap8.log > gpurun_out/r2_bench_lines.json
 echo done

@@ -22,5 +22,12 @@ ncu --set full --clock-control none --import-source on -k regex:clip_s_kernel -s
 ONEPROT_DZ_L2_HINTS=1 python tools/run_kernel.py dz 16384 32768 1024 3 > gpurun_out/r2_dz_l2_plain.log 2>&1 &&
 ONEPROT_DZ_L2_HINTS=1 ncu --set full --clock-control none --import-source on -k regex:clip_s_kernel -s 1 -c 1 -o gpurun_out/r2_dz_l2 -f \
     python tools/run_kernel.py dz 16384 32768 1024 3 > gpurun_out/r2_ncu_dz_l2.log 2>&1
+# (4) the stored-exponentials variant: launch list + full set of its kernels (FWD_E, dz_from_exp, the two whole-panel GEMMs)
+ONEPROT_KEEP_EXP=1 $BENCH > gpurun_out/r2_keep_plain.log 2>&1 && {
+ONEPROT_KEEP_EXP=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2_keep_launches.csv $BENCH \
+    > gpurun_out/r2_ncu_keep_launches.log 2>&1
+ONEPROT_KEEP_EXP=1 ncu --set full --clock-control none --import-source on -k regex:'clip_s_kernel|gemm_kernel|dz_from_exp' -s 24 -c 8 \
+    -o gpurun_out/r2_prof_keep -f $BENCH > gpurun_out/r2_ncu_keep_full.log 2>&1
+echo "keep_exp captures exit $?"; }
 ls -la gpurun_out/r2_*
 echo done

@@ -462,9 +462,13 @@ def run_ours(args):
     if int(pipe_ok.item()):
         e2e_ms = measure(step_e2e_pipelined)
         if rank == 0:
-            line["e2e"].update(value=GLOBAL_N / (e2e_ms * 1e-3), ms_per_step=e2e_ms,
-                               mode=("pipelined: PinnedPairPrefetcher copies the next step's pair on a copy stream inside "
-                                     "each timed step (one full H2D per step), the loss is read back to pinned host memory"))
+            line["e2e"]["pipelined_ms_per_step"] = e2e_ms
+            if e2e_ms <= e2e_serial_ms:
+                line["e2e"].update(value=GLOBAL_N / (e2e_ms * 1e-3), ms_per_step=e2e_ms,
+                                   mode=("pipelined: PinnedPairPrefetcher copies the next step's pair on a copy stream inside "
+                                         "each timed step (one full H2D per step), the loss is read back to pinned host memory"))
+            else:     # both legs are end-to-end measurements of the same metric: the faster host pattern is the figure
+                line["e2e"]["mode"] += "; the pipelined leg was measured too and was slower (pipelined_ms_per_step)"
     elif rank == 0:
         line["e2e"]["mode"] += f"; pipelined leg failed: {pipe_err or 'on another rank'}"
     watchdog.cancel()

@@ -35,8 +35,8 @@ def test_gpu_arm_control_flow_prints_one_line(mode):
     e = ln["e2e"]
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "mode", "serial_value"} <= set(e)
     assert e["h2d_bytes_per_step"] == 2 * 256 * 64 * 2 and e["d2h_bytes_per_step"] == 4
-    if mode == "pipelined":
-        assert e["mode"].startswith("pipelined")
+    if mode == "pipelined":      # the leg ran; it is the headline only if it beat the serial leg (CPU timing here is noise)
+        assert "pipelined_ms_per_step" in e and (e["mode"].startswith("pipelined") or "was slower" in e["mode"])
     else:
         assert e["mode"].startswith("serial") and "pipelined leg failed" in e["mode"]
 
@@ -50,7 +50,7 @@ def test_gpu_arm_over_the_emulated_library():
     lines = _json_lines(p.stdout)
     assert len(lines) == 1, p.stdout
     ln = lines[0]
-    assert KEYS <= set(ln) and ln["gpu_launches"] == 30 and ln["e2e"]["mode"].startswith("pipelined")
+    assert KEYS <= set(ln) and ln["gpu_launches"] == 30 and "pipelined_ms_per_step" in ln["e2e"]
     assert len(ln["roofline"]["kernels"]) == 4 and abs(ln["roofline"]["step"]["executed_over_algorithmic"] - 4 / 3) < 1e-9
     assert 3.0 < ln["config"]["loss"] < 6.0
 
@@ -66,7 +66,7 @@ def test_two_rank_control_flow_over_gloo():
     ln = lines[0]
     assert ln["n_gpus"] == 2 and ln["config"]["rows_per_gpu"] == 128 and ln["config"]["warmup_steps_run"] == 6 and ln["warmup"] == 3
     assert "cpu_baseline" not in ln                      # rank 0 at N = 1 only
-    assert ln["e2e"]["mode"].startswith("pipelined") and ln["e2e"]["h2d_bytes_per_step"] == 2 * 128 * 64 * 2
+    assert "pipelined_ms_per_step" in ln["e2e"] and ln["e2e"]["h2d_bytes_per_step"] == 2 * 128 * 64 * 2
 
 
 def test_reference_arm_prints_one_line():

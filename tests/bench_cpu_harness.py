@@ -109,5 +109,5 @@ world = int(os.environ.get("WORLD_SIZE", 1))
 if world > 1:      # launched by torch.distributed.run: NCCL -> gloo
     _init = dist.init_process_group
     dist.init_process_group = lambda backend=None, device_id=None, **k: _init("gloo", **k)
-sys.argv = ["bench.py", "--gpus", str(world), "--steps", "3", "--warmup", "3"]
+sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2" if "ONEPROT_LIB" in os.environ else "3", "--warmup", "3"]
 bench.main()

@@ -172,6 +172,8 @@ def _worker(rank, world, port, results, provider="fake"):
                 B = b.clone().requires_grad_(True)
                 ls = torch.tensor(float(g["scale"]), requires_grad=scale_grad)
                 for robust in ("off", "always", "keep"):       # "keep": stored-exponentials backward (falls back where it must)
+                    if provider == "emu" and scale_grad and robust != "off":
+                        continue                                # the emulated kernels are slow: variants once per convention
                     A = a.clone().requires_grad_(True)
                     B = b.clone().requires_grad_(True)
                     ls = torch.tensor(float(g["scale"]), requires_grad=scale_grad)
@@ -212,6 +214,8 @@ def test_two_rank_gloo_conventions_vs_reference_golden(provider, port):
             for gwg in (0, 1):
                 ref = f"ll{ll}_gwg{gwg}"
                 for sg, rob in ((0, ""), (1, ""), (0, "_rob"), (1, "_rob"), (0, "_keep"), (1, "_keep")):
+                    if provider == "emu" and sg and rob:
+                        continue
                     got = rec[f"{ref}_sg{sg}{rob}"]
                     assert rel_err(got["loss"], g[f"r{r}_loss_{ref}"]) < 1e-5, (r, ref)
                     # bf16 gradients: direction AND magnitude (the W-factor conventions of SURVEY.md 8a)

@@ -420,6 +420,9 @@ class _ClipLossFunction(torch.autograd.Function):
             # recompute.  A second backward over the same graph (retain_graph) finds E consumed and recomputes.
             ctx.E = None
             Wz = E
+            if cfg.get("keep_overlap") and cfg.get("keep_panels", 0) > 1:     # explicit panel count for the overlapped rescale
+                rows_k = max(128, -(-(-(-n // cfg["keep_panels"])) // 128) * 128)
+                panels = [(r0, min(rows_k, n - r0)) for r0 in range(0, n, rows_k)]
             if cfg.get("keep_overlap") and len(panels) > 1 and passes[0][2]:
                 # keep the panel split for the dB GEMM (a split of its K dimension: no tile is lost): the HBM-bound
                 # rescale of panel q + 1 runs on its own stream under the tensor-bound dB GEMM of panel q (the
@@ -599,8 +602,9 @@ class ClipLoss(nn.Module):
       keep_exp     stored-exponentials backward (opt-in, also ONEPROT_KEEP_EXP=1): the forward keeps the n x N
                    exponentials as a bf16 panel (<= keep_bytes, default 8 GiB) and the backward rescales it in
                    place instead of recomputing the logits - 3 GEMM units per step instead of 4.
-      keep_overlap with keep_exp (opt-in, also ONEPROT_KEEP_OVERLAP=1): keep the panel_bytes split and rescale
-                   panel q + 1 on a second stream under the GEMMs of panel q.
+      keep_overlap with keep_exp (opt-in, also ONEPROT_KEEP_OVERLAP=1): rescale panel q + 1 on a second stream under
+                   the dB GEMM of panel q; panels = the panel_bytes split, or keep_panels (ONEPROT_KEEP_PANELS) equal
+                   row panels when that is given.
       robust       "off": one common reference, validated window, device flag;
                    "always": per-row / per-column references for arbitrary inputs (2.25x the work);
                    "auto": run the normal path, read the device flag (one host sync per forward)
@@ -615,7 +619,7 @@ class ClipLoss(nn.Module):
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
                  panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
                  robust: Optional[str] = None, graph: bool = False, keep_exp: Optional[bool] = None,
-                 keep_bytes: int = DEFAULT_KEEP_BYTES, keep_overlap: Optional[bool] = None):
+                 keep_bytes: int = DEFAULT_KEEP_BYTES, keep_overlap: Optional[bool] = None, keep_panels: Optional[int] = None):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -637,6 +641,7 @@ class ClipLoss(nn.Module):
         self.keep_bytes = int(keep_bytes)
         self.keep_overlap = ((os.environ.get("ONEPROT_KEEP_OVERLAP") == "1") if keep_overlap is None
                              else bool(keep_overlap))
+        self.keep_panels = int(os.environ.get("ONEPROT_KEEP_PANELS", 0)) if keep_panels is None else int(keep_panels)
         self._graphs = {}            # (shape, dtype, gradient pattern, scale kind) -> GraphedStep
         # cache state (same attributes as the reference, loss.py:68-70)
         self.prev_num_logits = 0
@@ -709,7 +714,7 @@ class ClipLoss(nn.Module):
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
                    panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer, keep_exp=self.keep_exp,
-                   keep_bytes=self.keep_bytes, keep_overlap=self.keep_overlap)
+                   keep_bytes=self.keep_bytes, keep_overlap=self.keep_overlap, keep_panels=self.keep_panels)
         if self.robust is None:     # training: never sync; evaluation: fall back to the two-reference path when flagged
             cfg["robust"] = "off" if (torch.is_grad_enabled() or self.graph) else "auto"
         else:

@@ -150,6 +150,13 @@ def test_overlapped_rescale_gives_the_same_gradients(prov, monkeypatch):
         assert cosine(res[-1][0], ref.dA) > 0.9999 and cosine(res[-1][1], ref.dB) > 0.9999
     assert np.array_equal(res[0][0], res[1][0])                      # dA rows are independent of the split
     assert cosine(res[0][1], res[1][1]) > 0.999999
+    # explicit panel count (keep_panels), independent of panel_bytes; panels are whole 128-row blocks
+    A = a.clone().requires_grad_(True)
+    B = b.clone().requires_grad_(True)
+    del K.CALLS[:]
+    cl.ClipLoss(loss_dtype=torch.float32, keep_exp=True, keep_overlap=True, keep_panels=5)(A, B).backward()
+    assert K.CALLS.count("dz_from_exp") == 3 and K.CALLS.count("gemm") == 4        # ceil128(300 / 5) = 128 -> 3 panels
+    assert np.array_equal(A.grad.float().numpy(), res[0][0]) and cosine(B.grad.float().numpy(), res[0][1]) > 0.999999
 
 
 @pytest.mark.parametrize("n,N,d,off", [(25, 25, 64, 0), (130, 700, 72, 400), (256, 512, 128, 256)])

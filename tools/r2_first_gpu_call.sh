@@ -15,8 +15,8 @@ run bench_default python bench.py --steps 10 --warmup 3
 ONEPROT_SEQ=1 run bench_seq python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 ONEPROT_KEEP_EXP=1 run bench_keep_exp python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 run bench_keep_overlap2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 ONEPROT_PANEL_BYTES=$((640<<20)) run bench_keep_overlap4 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 ONEPROT_PANEL_BYTES=$((320<<20)) run bench_keep_overlap8 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 ONEPROT_KEEP_PANELS=4 run bench_keep_overlap4 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+ONEPROT_KEEP_EXP=1 ONEPROT_KEEP_OVERLAP=1 ONEPROT_KEEP_PANELS=8 run bench_keep_overlap8 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run dz_default    python tools/run_kernel.py dz 16384 32768 1024 10
 run k_fwd         python tools/run_kernel.py fwd 32768 32768 1024 10
 run k_fwd_e       python tools/run_kernel.py fwd_e 32768 32768 1024 10

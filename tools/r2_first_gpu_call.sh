@@ -30,3 +30,4 @@ run eager_bar     python tests/perf_eager_bar.py --sizes 8192,32768 --reps 5
 run heads_bench   python tools/bench_heads.py
 grep -h '"metric"' gpurun_out/bench_default.log gpurun_out/bench_seq.log gpurun_out/bench_keep_exp.log gpurun_out/bench_keep_overlap2.log gpurun_out/bench_keep_overlap4.log gpurun_out/bench_keep_overlap8.log > gpurun_out/r2_bench_lines.json
 echo done
+echo "python tools/show_bench.py -v gpurun_out/r2_bench_lines.json   # side-by-side view of the A/B lines"

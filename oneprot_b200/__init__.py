@@ -1,7 +1,9 @@
 """oneprot_b200 - B200-native (sm_100a) implementation of OneProt's ClipLoss hot path.
 
-Public surface mirrors the reference (klemens-floege/oneprot, src/models/components/loss.py and
-base_encoder.py): ``ClipLoss``, ``gather_features``, ``Normalize``, ``LearnableLogitScaling``.
+Public surface mirrors the reference (klemens-floege/oneprot): ``ClipLoss``, ``gather_features``, ``SigLipLoss``
+(src/models/components/loss.py), ``Normalize``, ``LearnableLogitScaling``, ``BaseEncoder`` and its layers
+(base_encoder.py), ``RetrievalMetric`` (retrieval_metric.py), ``ModalitySteps`` / ``mean_abs`` (the step logic and L1
+term of oneprot_module.py); plus ``NormalizeAndScale`` (fused epilogue) and ``PinnedPairPrefetcher`` (H2D staging).
 """
 __version__ = "0.1.0"
 

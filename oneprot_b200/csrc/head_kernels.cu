@@ -713,7 +713,7 @@ static int abs_blocks(size_t total8) {
   return static_cast<int>(std::min<size_t>(std::min<size_t>((total8 + 255) / 256, static_cast<size_t>(oneprot_num_sms()) * 16), oph::ABS_MAX_BLOCKS));
 }
 
-size_t oneprot_abs_mean_scratch_bytes(size_t count) { return sizeof(float) * static_cast<size_t>(oph::ABS_MAX_BLOCKS); (void)count; }
+size_t oneprot_abs_mean_scratch_bytes(size_t /*count*/) { return sizeof(float) * static_cast<size_t>(oph::ABS_MAX_BLOCKS); }   // one partial per block, at most
 
 int oneprot_abs_mean_fwd(const void* x, size_t count, size_t true_count, int is_fp32, float* out, void* scratch, size_t scratch_bytes,
                          void* stream) {

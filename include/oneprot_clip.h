@@ -197,7 +197,11 @@ int oneprot_clip_bwd_weights(const float* inv_rowsum, const float* inv_colsum, i
  * Wz (bf16, row-major, leading dimension ldw >= N, multiple of 8) - the bounded dL/dZ panel.
  * A_rows points at row r0 of A; wr/dg point at element r0.  grow0 = row_offset + r0 (global row
  * of the first panel row, for the diagonal).  Replaces the autograd backward of
- * F.cross_entropy (loss.py:109-112). */
+ * F.cross_entropy (loss.py:109-112).
+ * PADDING CONTRACT (every bf16 panel written through a TMA store: Wz here, E / S of the *_keep entry points):
+ * rows beyond `rows` are never touched; the padding columns [N, ldw) of the written rows are SCRATCH - when N is not
+ * a multiple of 8 elements the hardware store does not clip the last 16-byte chunk per element (measured on B200,
+ * round 1) - and no entry point of this library reads them (every consumer's tensor map has inner extent N). */
 int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N, int d, int grow0,
                           const float* scale_dev, const float* stats, const float* wr, const float* wc,
                           const float* dg, void* Wz, int ldw, void* stream);

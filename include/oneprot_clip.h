@@ -239,20 +239,6 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
                          const float* acc_in, float* acc_out, void* out_bf16, int ldc, const float* row_scale,
                          const void* dot_mat, int ld_dot, float* rowdot_part, void* stream);
 
-/* Fused GEMM + reduce-scatter push (single NVSwitch node): C = A^T-layout GEMM as in the dB call
- * (a_mn = b_mn = 1), M = owners * rows_per_owner.  Instead of a local C every finished
- * 128 x 256 tile (value = row_scale[m] * (acc + acc_in[m*ld_acc + n]), bf16) is TMA-stored into
- * owner_dst[m / rows_per_owner] (row-major rows_per_owner x Nc, leading dimension ld_dst; peer
- * memory of a symmetric allocation).  The owner then adds its slots (oneprot_sum_slots_bf16)
- * after a barrier.  Rank r starts with the rows of owner r+1 so that no owner is the target of
- * two ranks at once.  Replaces the reduce-scatter SUM in the backward of
- * torch.distributed.nn.all_gather (loss.py:32-33) overlapped with the dB contraction. */
-int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
-                           const float* acc_in, int ld_acc, const float* row_scale, void* const* owner_dst, int owners,
-                           int my_rank, int rows_per_owner, int ld_dst, void* stream);
-/* out[i] = bf16(sum_w slots[w*count + i]), fp32 accumulation in slot order (deterministic). */
-int oneprot_sum_slots_bf16(const void* slots, int W, size_t count, void* out, void* stream);
-
 /* out[i] = <x_i, y_i> over d bf16 elements (leading dimensions ldx, ldy; multiples of 8). */
 int oneprot_rowdot_bf16(const void* x, int ldx, const void* y, int ldy, int rows, int d, float* out, void* stream);
 /* out[0] = sum of v[0..count) in a fixed order (deterministic). */

@@ -68,8 +68,6 @@ SIGNATURES = {
     "oneprot_gemm_bf16": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _vp]),
     "oneprot_gemm_rowdot_scratch_bytes": (_sz, [_i, _i]),
     "oneprot_gemm_bf16_ex": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _vp, _i, _fp, _vp, _i, _fp, _vp]),
-    "oneprot_gemm_bf16_push": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _fp, _i, _fp, C.POINTER(C.c_void_p), _i, _i, _i, _i, _vp]),
-    "oneprot_sum_slots_bf16": (_i, [_vp, _i, _sz, _vp, _vp]),
     "oneprot_rowdot_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _fp, _vp]),
     "oneprot_sum_f32": (_i, [_fp, _i, _fp, _vp]),
     "oneprot_l2norm_scale_fwd": (_i, [_vp, _vp, _fp, _i, _i, _i, _fp, _f, _vp]),

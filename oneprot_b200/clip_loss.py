@@ -45,20 +45,12 @@ except ImportError:  # pragma: no cover
 _KERNELS = _cuda_kernels
 
 # bound of the bf16 dL/dZ panel workspace: 1.25 GiB lets N = 32768 run as two wave-aligned panels
-DEFAULT_PANEL_BYTES = int(os.environ.get("ONEPROT_PANEL_BYTES", 5 << 28))
+DEFAULT_PANEL_BYTES = 5 << 28
 
 # bound of the stored-exponentials panel (keep_exp=True): n x N bf16 per rank, 2 GiB at N = 32768 on one GPU
-DEFAULT_KEEP_BYTES = int(os.environ.get("ONEPROT_KEEP_BYTES", 8 << 30))
+DEFAULT_KEEP_BYTES = 8 << 30
 
 _SCALE_CACHE = {}               # (device, python float) -> 1-element fp32 device tensor
-_RESCALE_STREAMS = {}           # device -> stream of the overlapped rescale (keep_overlap)
-
-
-def _rescale_stream(device):
-    s = _RESCALE_STREAMS.get(str(device))
-    if s is None:
-        s = _RESCALE_STREAMS[str(device)] = torch.cuda.Stream(device=device)
-    return s
 
 
 def _float_scale_on(device, value: float) -> torch.Tensor:
@@ -186,11 +178,10 @@ class _GemmChain:
     """Sum of several GEMM terms into one output: fp32 accumulator chained through acc_in /
     acc_out, the last term applies the row scale and writes the final dtype."""
 
-    def __init__(self, M, Nc, out: torch.Tensor, row_scale, n_terms: int, push=None):
+    def __init__(self, M, Nc, out: torch.Tensor, row_scale, n_terms: int):
         self.M, self.Nc, self.out, self.row_scale, self.n_terms = M, Nc, out, row_scale, n_terms
         self.done = 0
         self.acc = None
-        self.push = push          # (owner addresses, rows per owner): last term pushes tiles to their owners
         if n_terms > 1 and out.dtype != torch.float32:
             self.acc = torch.empty(M, out.stride(0), dtype=torch.float32, device=out.device)[:, :Nc]
 
@@ -200,12 +191,6 @@ class _GemmChain:
         f32_out = self.out.dtype == torch.float32
         acc = self.out if f32_out else self.acc
         kw = dict(dot_mat=dot_mat, rowdot_part=rowdot_part)
-        if last and self.push is not None:
-            addrs, my_rank, rows_per_owner = self.push
-            Kn.gemm_bf16_push(A, B, self.M, self.Nc, K, addrs, my_rank, rows_per_owner, self.Nc,
-                              acc_in=None if first else acc, row_scale=self.row_scale)
-            self.done += 1
-            return
         if last:
             kw["row_scale"] = self.row_scale
             if f32_out:
@@ -286,7 +271,7 @@ class _ClipLossFunction(torch.autograd.Function):
         scale_dev = scale_t.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         loss_dtype = cfg["loss_dtype"] or ops.in_dtype
 
-        # Stored-exponentials backward (opt-in): the forward keeps e_ij as a bf16 n x N panel and the backward
+        # Stored-exponentials backward: the forward keeps e_ij as a bf16 n x N panel and the backward
         # rescales it in place instead of recomputing the logits (3 GEMM units per step instead of 4).  Needs the
         # one-pass gradient conventions, bf16 operands, the single-reference path and the panel to fit keep_bytes.
         local_mode = W > 1 and cfg["local_loss"]
@@ -344,6 +329,8 @@ class _ClipLossFunction(torch.autograd.Function):
             st = dict(st, token=None)
 
         ctx.cfg, ctx.ops, ctx.mode, ctx.comm, ctx.token = cfg, ops, mode, comm, st["token"]
+        needs_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or scale_t.requires_grad
+        ctx.bhold = comm.hold_for_backward(B_all) if (needs_bwd and st["token"] is not None) else None
         ctx.B_all, ctx.scale_dev, ctx.stats, ctx.inv_rs, ctx.inv_cs = B_all, scale_dev, stats, inv_rs, inv_cs
         ctx.scale_needs_grad = scale_t.requires_grad
         ctx.scale_meta = (scale_t.dtype, scale_t.device, scale_t.shape)
@@ -366,7 +353,7 @@ class _ClipLossFunction(torch.autograd.Function):
         N, off = W * n, rank * n
         dev = ops.A.device
         comm = ctx.comm
-        B_all = comm.b_all_for_backward(ops, ctx.B_all, ctx.token, rank, W)
+        B_all = comm.b_all_for_backward(ops, ctx.B_all, ctx.token, rank, W, hold=getattr(ctx, "bhold", None))
         need_a, need_b, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.scale_needs_grad
 
         g32 = (torch.zeros(1, dtype=torch.float32, device=dev) if g_loss is None
@@ -414,23 +401,14 @@ class _ClipLossFunction(torch.autograd.Function):
                 rows_cap = min(rows_cap, -(-target // 128) * 128)
         panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
         E = getattr(ctx, "E", None)
-        ev_rescaled, rs_stream = None, None
         if E is not None and len(passes) == 1:
             # stored exponentials: the whole n x N panel exists already; one in-place rescale replaces the dL/dZ
             # recompute.  A second backward over the same graph (retain_graph) finds E consumed and recomputes.
+            # (Rescaling panel by panel on a second stream under the GEMMs was measured in round 2: 6.20 - 6.68 ms
+            # per step against 6.14 ms for the single pass at N = 32768 - removed.)
             ctx.E = None
             Wz = E
-            if cfg.get("keep_overlap") and cfg.get("keep_panels", 0) > 1:     # explicit panel count for the overlapped rescale
-                rows_k = max(128, -(-(-(-n // cfg["keep_panels"])) // 128) * 128)
-                panels = [(r0, min(rows_k, n - r0)) for r0 in range(0, n, rows_k)]
-            if cfg.get("keep_overlap") and len(panels) > 1 and passes[0][2]:
-                # keep the panel split for the dB GEMM (a split of its K dimension: no tile is lost): the HBM-bound
-                # rescale of panel q + 1 runs on its own stream under the tensor-bound dB GEMM of panel q (the
-                # 128-register GEMM launch leaves room for it on every SM); dA is ONE GEMM over all rows at the end
-                rs_stream = _rescale_stream(dev)
-                ev_rescaled = [None] * len(panels)
-            else:
-                panels = [(0, n)]
+            panels = [(0, n)]
         else:
             E = None
             Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
@@ -454,9 +432,8 @@ class _ClipLossFunction(torch.autograd.Function):
                 K.bwd_weights(ctx.inv_rs, ctx.inv_cs, n, off, mode, gwg, part, W, rank, gvec, ctx.scale_dev,
                               wr, wc, dg, sA, sB)
             dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
-            push = comm.db_push_targets(n, d, grad_dtype, rank, W) if (want_b and exchange_b) else None
             dBp = comm.db_buffer(N, d, grad_dtype, dev) if want_b else None
-            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp, push=(push, rank, n) if push else None) if want_b else None
+            chain_b = _GemmChain(N, d, dBp, sB, len(panels) * n_bp) if want_b else None
             rd_global = need_s and not local         # rowdot of the unscaled dA rows inside the GEMM epilogue
             last_pass = pi == len(passes) - 1
             ev_rs, dB_async = None, None
@@ -476,11 +453,7 @@ class _ClipLossFunction(torch.autograd.Function):
 
             for qi, (r0, rows) in enumerate(panels):
                 A_rows = ops.A[r0:r0 + rows]
-                if E is not None and rs_stream is not None:
-                    if qi == 0:
-                        _enqueue_rescale(K, rs_stream, ev_rescaled, 0, panels, E, N, off, wr, wc, dg)
-                    torch.cuda.current_stream().wait_event(ev_rescaled[qi])
-                elif E is not None:
+                if E is not None:
                     K.dz_from_exp(E, n, N, off, wr, wc, dg)
                 elif ctx.dz_ops is not None:     # two-reference path: augmented operands of this direction
                     A_aug, B_aug = ctx.dz_ops[part]
@@ -495,21 +468,15 @@ class _ClipLossFunction(torch.autograd.Function):
                 if want_b:                        # dB first: its exchange then hides under the dA GEMM
                     for Ap in ops.a_pieces(A_rows):
                         chain_b.add(Wp, True, Ap, True, rows)
-                    if exchange_b and side is not None and push is None and qi == len(panels) - 1:
+                    if exchange_b and side is not None and qi == len(panels) - 1:
                         evb = main.record_event()
                         with torch.cuda.stream(side), K.stream_scope():
                             side.wait_event(evb)
                             dB_async = comm.reduce_scatter_db(dBp, rank, W, last_pass=last_pass)
                             ev_rs = side.record_event()
-                if rs_stream is not None and qi + 1 < len(panels):    # next panel's rescale, under this panel's dB GEMM
-                    _enqueue_rescale(K, rs_stream, ev_rescaled, qi + 1, panels, E, N, off, wr, wc, dg)
-                if want_a and rs_stream is None:
+                if want_a:
                     run_dA(r0, rows, Wp, A_rows)
-            if want_a and rs_stream is not None:          # overlapped rescale: every panel is rescaled by now
-                run_dA(0, n, E[:n], ops.A)
-            if want_b and exchange_b and push is not None:
-                dBp = comm.finish_pushed_db(n, d, rank, W, last_pass=last_pass)
-            elif want_b and exchange_b:
+            if want_b and exchange_b:
                 if dB_async is not None:
                     main.wait_event(ev_rs)
                     dB_async.record_stream(main)
@@ -544,17 +511,6 @@ class _ClipLossFunction(torch.autograd.Function):
             sdt, sdev, sshape = ctx.scale_meta
             grad_s = grad_s.reshape(sshape).to(device=sdev, dtype=sdt)
         return grad_a, grad_b, grad_s, None
-
-
-def _enqueue_rescale(K, rs_stream, events, qi, panels, E, N, off, wr, wc, dg):
-    """dz_from_exp of panel qi on the rescale stream, after everything the compute stream has enqueued so far
-    (the panel weights; for qi > 0 only the order matters); events[qi] marks its end."""
-    r0, rows = panels[qi]
-    ev = torch.cuda.current_stream().record_event()
-    with torch.cuda.stream(rs_stream), K.stream_scope():
-        rs_stream.wait_event(ev)
-        K.dz_from_exp(E[r0:], rows, N, off + r0, wr[r0:r0 + rows], wc, dg[r0:r0 + rows])
-        events[qi] = rs_stream.record_event()
 
 
 def _valid_rowdot(part_buf, rows, d):
@@ -599,12 +555,15 @@ class ClipLoss(nn.Module):
                    ONEPROT_SEQ=1) instead of kernel by kernel from Python.
       graph        replay the forward / backward launch sequences as CUDA graphs (world_size == 1);
                    removes the ~0.4 ms of host enqueue per step that dominates at OneProt's batch sizes.
-      keep_exp     stored-exponentials backward (opt-in, also ONEPROT_KEEP_EXP=1): the forward keeps the n x N
-                   exponentials as a bf16 panel (<= keep_bytes, default 8 GiB) and the backward rescales it in
-                   place instead of recomputing the logits - 3 GEMM units per step instead of 4.
-      keep_overlap with keep_exp (opt-in, also ONEPROT_KEEP_OVERLAP=1): rescale panel q + 1 on a second stream under
-                   the dB GEMM of panel q; panels = the panel_bytes split, or keep_panels (ONEPROT_KEEP_PANELS) equal
-                   row panels when that is given.
+      keep_exp     stored-exponentials backward (default True): the forward keeps the n x N exponentials as a
+                   bf16 panel (<= keep_bytes, default 8 GiB; 2 GiB at N = 32768 on one GPU) and the backward rescales
+                   it in place instead of recomputing the logits - 3 GEMM units per step instead of 4 (measured on
+                   B200, N = 32768: 6.14 vs 7.07 ms per step).  False, a panel above keep_bytes, fp32 features, the
+                   two-reference path and the two-pass gradient conventions use the recompute backward.
+      check_rows   "first" (default): the first call with a new (n, d, dtype) gathers n, d of every rank (one host
+                   sync, cached per shape) and raises ValueError when the ranks disagree - the reference leaves that
+                   to a collective error or hang (oneprot_datamodule.py:72 drop_last=False makes it possible);
+                   "always": every call; "never": skip.
       robust       "off": one common reference, validated window, device flag;
                    "always": per-row / per-column references for arbitrary inputs (2.25x the work);
                    "auto": run the normal path, read the device flag (one host sync per forward)
@@ -618,8 +577,8 @@ class ClipLoss(nn.Module):
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
                  panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
-                 robust: Optional[str] = None, graph: bool = False, keep_exp: Optional[bool] = None,
-                 keep_bytes: int = DEFAULT_KEEP_BYTES, keep_overlap: Optional[bool] = None, keep_panels: Optional[int] = None):
+                 robust: Optional[str] = None, graph: bool = False, keep_exp: bool = True,
+                 keep_bytes: int = DEFAULT_KEEP_BYTES, check_rows: str = "first"):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -637,11 +596,12 @@ class ClipLoss(nn.Module):
         if graph and (world_size != 1 or robust == "auto"):
             raise ValueError("graph=True needs world_size == 1 and a robust mode that is decided on the host side up front")
         self.graph = bool(graph)
-        self.keep_exp = (os.environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
+        self.keep_exp = bool(keep_exp)
         self.keep_bytes = int(keep_bytes)
-        self.keep_overlap = ((os.environ.get("ONEPROT_KEEP_OVERLAP") == "1") if keep_overlap is None
-                             else bool(keep_overlap))
-        self.keep_panels = int(os.environ.get("ONEPROT_KEEP_PANELS", 0)) if keep_panels is None else int(keep_panels)
+        if check_rows not in ("first", "always", "never"):
+            raise ValueError("check_rows must be 'first', 'always' or 'never'")
+        self.check_rows = check_rows
+        self._rows_checked = set()   # (n, d, dtype) already compared across ranks
         self._graphs = {}            # (shape, dtype, gradient pattern, scale kind) -> GraphedStep
         # cache state (same attributes as the reference, loss.py:68-70)
         self.prev_num_logits = 0
@@ -705,6 +665,7 @@ class ClipLoss(nn.Module):
                 raise RuntimeError("ClipLoss(world_size > 1) needs an initialised torch.distributed process group")
             if dist.get_world_size(self.group) != self.world_size:
                 raise RuntimeError("ClipLoss world_size does not match the process group")
+            self._check_equal_rows(A)
         if torch.is_tensor(logit_scale):
             if logit_scale.numel() != 1:
                 raise ValueError("logit_scale must be a scalar")
@@ -714,7 +675,7 @@ class ClipLoss(nn.Module):
         cfg = dict(world_size=self.world_size, rank=self.rank, group=self.group, local_loss=bool(self.local_loss),
                    gather_with_grad=bool(self.gather_with_grad), loss_dtype=self.loss_dtype,
                    panel_bytes=self.panel_bytes, host_sequencer=self.host_sequencer, keep_exp=self.keep_exp,
-                   keep_bytes=self.keep_bytes, keep_overlap=self.keep_overlap, keep_panels=self.keep_panels)
+                   keep_bytes=self.keep_bytes)
         if self.robust is None:     # training: never sync; evaluation: fall back to the two-reference path when flagged
             cfg["robust"] = "off" if (torch.is_grad_enabled() or self.graph) else "auto"
         else:
@@ -732,6 +693,22 @@ class ClipLoss(nn.Module):
             total_loss, loss32, flag = _ClipLossFunction.apply(A, B, scale_t, cfg)
         self.last_loss_fp32, self.last_hazard_flag = loss32, flag
         return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+    def _check_equal_rows(self, A):
+        """Every rank must hold the same (n, d): the row sharding, the symmetric-memory layout and the collectives
+        all assume it.  Compared once per new shape (all ranks meet a new shape in the same call when the sampler
+        pads ranks to equal length, as DistributedSampler does), on every rank, so all of them raise together."""
+        key = (int(A.shape[0]), int(A.shape[1]), A.dtype)
+        if self.check_rows == "never" or (self.check_rows == "first" and key in self._rows_checked):
+            return
+        mine = torch.tensor([key[0], key[1]], dtype=torch.int64, device=A.device)
+        every = torch.empty(self.world_size * 2, dtype=torch.int64, device=A.device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
+        every = every.view(self.world_size, 2).cpu()
+        if not bool((every == every[0]).all()):
+            raise ValueError("ClipLoss: every rank must pass the same (n, d); the ranks hold "
+                             f"{[tuple(int(v) for v in r) for r in every]} (drop the ragged last batch or pad it)")
+        self._rows_checked.add(key)
 
     def check_last_call(self):
         """Host-side check (synchronises) that the last forward stayed inside the validated fp32

@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import os
 import warnings
+import weakref
 
 import torch
 
@@ -75,8 +76,11 @@ class LocalComm:
     def gather_grad_outputs(self, g32, rank, world, token=None):
         return g32
 
-    def b_all_for_backward(self, ops, B_all, token, rank, world):
+    def b_all_for_backward(self, ops, B_all, token, rank, world, hold=None):
         return B_all
+
+    def hold_for_backward(self, B_all):
+        return None
 
     def db_buffer(self, N, d, dtype, dev):
         return torch.empty(N, d, dtype=dtype, device=dev)
@@ -91,9 +95,6 @@ class LocalComm:
         """Stream on which exchanges may overlap with compute (None: exchanges are synchronous)."""
         return None
 
-    def db_push_targets(self, n, d, dtype, rank, world):
-        """Per-owner destination addresses for the fused GEMM + reduce-scatter push, or None."""
-        return None
 
 
 class DistComm(LocalComm):
@@ -140,7 +141,13 @@ class NvlsComm(DistComm):
         dBp       N x d x 4                    partial dB (bf16 or fp32), reduced by its owner
     Double buffering + the barriers of the following call make reuse safe without extra
     synchronisation: a rank can only write buffer p of call t+2 after every rank entered call t+1,
-    i.e. finished reading buffer p of call t (everything is stream-ordered).
+    i.e. finished reading buffer p of call t (everything is stream-ordered).  That argument covers the
+    BACKWARD of call t (it reads Bg[p] again: dL/dZ recompute and the dA GEMM) only when it is enqueued
+    before forward t+1 - the reference's pattern (oneprot_module.py:100-105: one loss, its backward, the
+    next modality).  For any other order (several forwards, then their backwards) begin_forward first
+    snapshots the gathered operand of every forward that still waits for its backward
+    (``hold_for_backward`` / ``_snapshot_pending``): at that point no peer can have overwritten it yet
+    (it would have to be past forward t+1's barrier, which this rank has not entered).
     """
     name = "nvls"
     G_AT, STATS_AT, SUMS_AT = 0, 16, 32      # float offsets inside a small buffer: [g | maxima | sums]
@@ -155,6 +162,7 @@ class NvlsComm(DistComm):
         self.gen = [0, 0]        # generation of the data held in Bg[p]
         self.chan = 0
         self._side = None
+        self._pending = weakref.WeakSet()    # holders of forwards whose backward has not been enqueued yet
 
     # ---- workspace ----------------------------------------------------------------------
     @staticmethod
@@ -189,8 +197,6 @@ class NvlsComm(DistComm):
         self.chan = (self.chan + 1) % 8
 
     def side_stream(self, dev):
-        if os.environ.get("ONEPROT_NO_OVERLAP"):
-            return None
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
         return self._side
@@ -214,12 +220,29 @@ class NvlsComm(DistComm):
     def _off_ctl(self):
         return 2 * self.bg_bytes + 2 * self.small_bytes + self.db_bytes
 
+    # ---- gathered operand of forwards that still wait for their backward -----------------
+    class _Hold:
+        """Owned by the autograd ctx of one forward (dies with it); view = the rows of Bg[p] it used."""
+        __slots__ = ("view", "snap", "__weakref__")
+
+    def hold_for_backward(self, B_all):
+        h = NvlsComm._Hold()
+        h.view, h.snap = B_all, None
+        self._pending.add(h)
+        return h
+
+    def _snapshot_pending(self):
+        for h in list(self._pending):
+            if h.snap is None:
+                h.snap = h.view.clone()       # stream-ordered before this call's exchanges
+
     # ---- forward -------------------------------------------------------------------------
     def begin_forward(self, ops, rank, world):
         K = self.K
         n, dk = ops.n, ops.dk
         N = world * n
         self._ensure(n, dk, ops.d)
+        self._snapshot_pending()
         p = self.calls & 1
         self.calls += 1
         self.gen[p] = self.calls
@@ -229,7 +252,7 @@ class NvlsComm(DistComm):
         st = dict(B_all=Bg, sums=small[self.SUMS_AT:self.SUMS_AT + 3 * N], stats=small[self.STATS_AT:self.STATS_AT + 4],
                   stats_rows=ops.B, stats_off=0, token=(p, self.calls), p=p, N=N, ag=None)
         chunks = next((c for c in (8, 4, 2, 1) if n % (c * 256) == 0), 0)
-        if chunks and not os.environ.get("ONEPROT_NO_FUSED_AG"):
+        if chunks:
             # the gather is fused into the forward kernel: nothing to launch here
             base = int(self.hdl.buffer_ptrs[rank]) + self._off_ctl()
             mcb = self.mc + self._off_ctl()
@@ -264,7 +287,7 @@ class NvlsComm(DistComm):
     def seq_ready(self, n, dev):
         """The sequencer covers the fused-gather forward and the side-stream backward only."""
         chunks = next((c for c in (8, 4, 2, 1) if n % (c * 256) == 0), 0)
-        return bool(chunks) and not os.environ.get("ONEPROT_NO_FUSED_AG") and self.side_stream(dev) is not None
+        return bool(chunks) and self.side_stream(dev) is not None
 
     def _base(self):
         return int(self.hdl.buffer_ptrs[self.rank])
@@ -275,6 +298,7 @@ class NvlsComm(DistComm):
         n, dk = ops.n, ops.dk
         N = world * n
         self._ensure(n, dk, ops.d)
+        self._snapshot_pending()
         p = self.calls & 1
         self.calls += 1
         self.gen[p] = self.calls
@@ -284,7 +308,8 @@ class NvlsComm(DistComm):
         # field order of oneprot_ag_t
         ag = (ops.B.data_ptr(), self.mc + self._off_bg(p) + rank * n * dk * 2, ctl + 2048, mcb, ctl, mcb + 1024, ctl + 1024,
               stats_out_addr, self.calls & 0x7fffffff, rank, world, chunks, n)
-        return dict(B_all=base + self._off_bg(p), stats=base + small + self.STATS_AT * 4, zero_ptr=base + small,
+        return dict(B_all=base + self._off_bg(p), B_view=self._view(self._off_bg(p), (N, dk), torch.bfloat16),
+                    stats=base + small + self.STATS_AT * 4, zero_ptr=base + small,
                     zero_bytes=(self.SUMS_AT + 3 * N) * 4, sums=base + small + self.SUMS_AT * 4,
                     sums_mc=self.mc + small + self.SUMS_AT * 4, ag=ag, token=(p, self.calls))
 
@@ -316,34 +341,20 @@ class NvlsComm(DistComm):
         self.K.mc_allreduce_f32(self.mc + off, out, W4, 0)   # one-hot contributions: the sum is the gather
         return out[0:world]
 
-    def b_all_for_backward(self, ops, B_all, token, rank, world):
+    def b_all_for_backward(self, ops, B_all, token, rank, world, hold=None):
+        """The gathered operand for the backward of the forward `token`: the symmetric buffer when that backward
+        directly follows its forward, else the snapshot begin_forward took (see the class docstring)."""
+        if hold is not None:
+            self._pending.discard(hold)
+            if hold.snap is not None:
+                return hold.snap
         p, gen = token
-        if self.gen[p] != gen:       # overwritten by two later forwards: gather again (rare)
+        if self.gen[p] != gen:       # no holder (workspace regrown, or a caller without one): gather again
             return _all_gather_rows(ops.B, world, self.group)
         return B_all
 
     def db_buffer(self, N, d, dtype, dev):
         return self._view(self._off_db(), (N, d), dtype)
-
-    def db_push_targets(self, n, d, dtype, rank, world):
-        # Measured on 8 x B200 (N = 32768): the pull-reduce on a side stream under the dA GEMM gives a
-        # shorter step (0.98 ms) than pushing tiles from the dB GEMM epilogue (1.08 ms), so the push
-        # variant is opt-in.
-        if dtype != torch.bfloat16 or n % 128 or not os.environ.get("ONEPROT_PUSH"):
-            return None
-        # owner o keeps one (n x d) slot per source rank inside its dBp region: slot[src] at src*n*d
-        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
-        return [ptrs[o] + self._off_db() + rank * n * d * 2 for o in range(world)]
-
-    def finish_pushed_db(self, n, d, rank, world, last_pass=True):
-        """All ranks have pushed their tiles: add this rank's W slots (fixed order)."""
-        self._barrier()
-        slots = self._view(self._off_db(), (world * n, d), torch.bfloat16)
-        out = torch.empty(n, d, dtype=torch.bfloat16, device=self.dev)
-        self.K.sum_slots_bf16(slots, world, n * d, out)
-        if not last_pass:
-            self._barrier()
-        return out
 
     def reduce_scatter_db(self, dbp, rank, world, last_pass=True):
         K = self.K

@@ -12,9 +12,7 @@
 //   clip_s_kernel<FWD_E> the same + the exponentials kept as a bf16 panel (stored-exponentials backward, opt-in)
 //   clip_s_kernel<MAX>  exact maximum logit (robust tier, early-exits when the norm bound suffices)
 //   clip_s_kernel<DZ>   dL/dZ panel, bf16, staged through swizzled smem and written by TMA stores
-//   gemm_kernel         dA = Wz.B / dB = Wz^T.A with row-scale, row-dot, fp32 accumulate, and a PUSH
-//                       variant that TMA-stores finished tiles into the owner GPU's memory
-//   gemm2_kernel        the same GEMM on CTA pairs (tcgen05.mma cta_group::2), opt-in
+//   gemm_kernel         dA = Wz.B / dB = Wz^T.A with row-scale, row-dot, fp32 accumulate
 // plus the HBM-bound vector kernels and the multimem (NVLS) exchange kernels at the end.
 // ONEPROT_KERNEL_EMULATION (tests/emu): the kernel bodies of this file are also compiled for the CPU, with
 // ptx_emu.h supplying functional stand-ins for the TMA / mbarrier / tcgen05 / TMEM primitives of ptx.cuh.
@@ -288,19 +286,20 @@ __device__ __forceinline__ void load_c_and_G(const SParams& p, float& c, float& 
 
 enum { EPI_FWD = 0, EPI_DZ = 1, EPI_MAX = 2, EPI_RCMAX = 3, EPI_RANK = 4,    // RCMAX: row/col maxima; RANK: retrieval ranks
        EPI_SFWD = 5, EPI_SDZ = 6,     // SigLIP: row sums of softplus(z) / dL/dZ panel sigma(z) wr_i - [i == j] dg_i
-       EPI_DZ_L2 = 7,                 // EPI_DZ with L2 hints: panel stores evict-first, operand loads evict-last (A/B experiment)
        EPI_FWD_E = 8,                 // EPI_FWD that also keeps the exponentials e_ij as a bf16 panel: the backward then
                                       // rescales them in place (dz_from_exp_kernel) instead of recomputing the logits
-       EPI_FWD_E_L2 = 9,              // EPI_FWD_E with the L2 hints of EPI_DZ_L2 (same A/B experiment)
        EPI_SFWD_K = 10 };             // EPI_SFWD that also keeps sigma(z_ij) - [i == j] as a bf16 panel: dL/dz up to the constant
                                       // g / n, so the SigLIP backward needs neither a recompute nor a rescale pass
 
 template <int EPI>
 struct SCfg {
   static constexpr int NS = 4;                                             // operand ring depth
-  static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ || EPI == EPI_DZ_L2);   // writes a bf16 dL/dZ panel by TMA stores
-  static constexpr bool L2_HINTS = (EPI == EPI_DZ_L2 || EPI == EPI_FWD_E_L2);
-  static constexpr bool KEEP_E = (EPI == EPI_FWD_E || EPI == EPI_FWD_E_L2);
+  static constexpr bool PANEL = (EPI == EPI_DZ || EPI == EPI_SDZ);   // writes a bf16 dL/dZ panel by TMA stores
+  // L2 hints of the two panel writers of the ClipLoss step: panel stores evict-first (written once, read once later),
+  // operand loads evict-last (re-read by every CTA sweeping the same blocks).  Measured on B200 in round 2, kernels
+  // alone at N = 32768: DZ 0.852 vs 0.865 ms per 16384 rows, FWD_E 1.912 vs 1.935 ms; results bit-identical.
+  static constexpr bool L2_HINTS = (EPI == EPI_DZ || EPI == EPI_FWD_E);
+  static constexpr bool KEEP_E = (EPI == EPI_FWD_E);
   static constexpr bool SUMS = (EPI == EPI_FWD || KEEP_E);                    // row / column exp-sums (+ the fused all-gather)
   static constexpr bool KEEP_S = (EPI == EPI_SFWD_K);
   static constexpr int STAGING = (PANEL || KEEP_E || KEEP_S) ? STORE_STAGING_BYTES : 0;   // FWD / MAX / RCMAX / RANK / SFWD need none
@@ -483,7 +482,7 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 128; ++k) colacc[k] = (EPI == EPI_RCMAX) ? -INFINITY : 0.f;
       }
-      if (EPI == EPI_DZ || EPI == EPI_DZ_L2 || EPI == EPI_RANK) {
+      if (EPI == EPI_DZ || EPI == EPI_RANK) {
         // stage the per-column weights of this item's 256 columns
         named_bar_sync(1, EPI_THREADS);
         const int t = threadIdx.x - EPI_WARP0 * 32;
@@ -710,7 +709,6 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]);
 
 constexpr int GEMM_NS = 4;
 constexpr int GEMM_SMEM = smem_bytes(GEMM_NS, 0);
-constexpr int GEMM_PUSH_SMEM = smem_bytes(GEMM_NS, 2 * 16384);
 
 struct GParams {
   int M, Nc, nK;
@@ -723,23 +721,17 @@ struct GParams {
   const __nv_bfloat16* dot_mat;  // optional: rowdot_part[(nb*2+h)*ldd + m] = <unscaled value row, dot_mat row>
   float* rowdot_part;
   int ld_dot, ldd;
-  int rows_per_owner;            // PUSH: rows of C owned by each GPU (multiple of 128)
-  int mb_rot;                    // PUSH: row-block rotation so that ranks push to different owners at any time
 };
 
-// PUSH: the epilogue does not write a local C but pushes each finished 128-row tile, as bf16,
-// into the memory of the GPU that owns those rows (TMA store over NVLink into a symmetric-memory
-// slot) - the reduce-scatter of the partial dB fused into the GEMM, tile by tile.
-struct OwnerMaps {
-  CUtensorMap m[8];
-};
-
-template <int A_MN, int B_MN, bool PUSH>
+// (A variant whose epilogue TMA-stored every finished dB tile into its owner GPU - the reduce-scatter fused into
+// the GEMM - and a CTA-pair variant (tcgen05.mma cta_group::2, 256 x 256 tiles) were built and measured: 1.08 vs
+// 0.98 ms per step at 8 GPUs against the side-stream pull-reduce, resp. 7.13 vs 7.07 ms per step on one GPU in
+// the sustained regime; both were removed in round 2, see DESIGN.md.)
+template <int A_MN, int B_MN>
 __global__ void __maxnreg__(128)   // 384 x 128 registers: leaves 16 K registers per SM for a co-resident exchange kernel
-gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-            const __grid_constant__ OwnerMaps om, const GParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
   OP_DYNAMIC_SMEM(smem_raw);
-  const Smem s = carve_smem<GEMM_NS, PUSH ? STORE_STAGING_BYTES : 0>(smem_raw);
+  const Smem s = carve_smem<GEMM_NS, 0>(smem_raw);
   const uint32_t tmem_base = kernel_prologue(s, &mapA, &mapB);
   const int warp = threadIdx.x >> 5;
   const int tiles = p.nMb * p.nNb;
@@ -749,7 +741,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     if (lane_id() == 0) {
       PipeState<GEMM_NS> ps;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int mb = (t / p.nNb + p.mb_rot) % p.nMb, nb = t % p.nNb;
+        const int mb = t / p.nNb, nb = t % p.nNb;
         for (int kb = 0; kb < p.nK; ++kb) {
           mbar_wait(&s.tail->empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = s.stages + ps.stage * STAGE_BYTES;
@@ -790,10 +782,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int lane = lane_id();
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t stage_s = PUSH ? smem_u32(s.staging) + h * 16384 : 0u;
-    const bool store_issuer = (q == 0) && (lane == 0);
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int mb = (t / p.nNb + p.mb_rot) % p.nMb, nb = t % p.nNb;
+      const int mb = t / p.nNb, nb = t % p.nNb;
       const int m = mb * BM + q * 32 + lane;
       const int n0 = nb * BN + h * 128;
       const float rs = (p.row_scale && m < p.M) ? __ldg(p.row_scale + m) : 1.f;
@@ -813,41 +803,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         float (&v)[32] = vall[cc];
-        if (PUSH) {
-          if ((cc & 1) == 0) {
-            if (store_issuer) bulk_wait_read<0>();     // previous TMA store finished reading the staging box
-            named_bar_sync(2 + h, 128);
-          }
-          const int r = q * 32 + lane;
-          const uint32_t line = stage_s + r * 128;
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            float x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = v[v8 * 8 + u];
-            const int n = n0 + cc * 32 + v8 * 8;
-            if (p.acc_in && m < p.M && n < p.Nc) {
-              const size_t base = static_cast<size_t>(m) * p.ldc + n;
-              const float4 a0 = *reinterpret_cast<const float4*>(p.acc_in + base);
-              const float4 a1 = *reinterpret_cast<const float4*>(p.acc_in + base + 4);
-              x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
-              x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
-            }
-            const uint32_t slot = static_cast<uint32_t>(((cc & 1) * 4 + v8) ^ (r & 7));
-            st_shared_v4(line + slot * 16, pack_bf16x2(x[0] * rs, x[1] * rs), pack_bf16x2(x[2] * rs, x[3] * rs),
-                         pack_bf16x2(x[4] * rs, x[5] * rs), pack_bf16x2(x[6] * rs, x[7] * rs));
-          }
-          if (cc & 1) {
-            fence_proxy_async();
-            named_bar_sync(2 + h, 128);
-            if (store_issuer) {
-              const int owner = (mb * BM) / p.rows_per_owner;
-              tma_store_2d(&om.m[owner], s.staging + h * 16384, n0 + (cc >> 1) * 64, mb * BM - owner * p.rows_per_owner);
-              bulk_commit();
-            }
-          }
-          continue;
-        }
         if (m < p.M) {
           const size_t base = static_cast<size_t>(m) * p.ldc + n0 + cc * 32;
 #pragma unroll
@@ -887,190 +842,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       if (p.rowdot_part && m < p.M) p.rowdot_part[static_cast<size_t>(nb * 2 + h) * p.ldd + m] = rdot;
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (PUSH && store_issuer) bulk_wait<0>();   // all pushed tiles have left before the CTA retires
   }
   kernel_epilogue_dealloc(tmem_base);
 }
-
-#ifndef ONEPROT_KERNEL_EMULATION   // CTA pairs and the multimem exchanges below are not emulated
-// ------------------------------------------------------------------------------------------
-// CTA-pair GEMM (cta_group::2): two CTAs of a cluster own one 256 x 256 tile.  Each loads its own
-// 128 rows of A and HALF of the B tile (the tensor cores of both SMs share the halves), so the
-// operand traffic from L2 and out of shared memory drops by a third per flop; six 32-KiB stages.
-// ------------------------------------------------------------------------------------------
-constexpr int P_STAGE_BYTES = 32768;   // per CTA: A 128 x 64 + B-half 128 x 64, bf16
-constexpr int P_NS = 6;
-constexpr int GEMM2_SMEM = P_NS * P_STAGE_BYTES + 1024 + static_cast<int>(sizeof(SmemTail));
-
-template <int A_MN, int B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
-gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GParams p) {
-  OP_DYNAMIC_SMEM(smem_raw);
-  const uintptr_t base = (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023);
-  uint8_t* stages = reinterpret_cast<uint8_t*>(base);
-  SmemTail* tail = reinterpret_cast<SmemTail*>(base + P_NS * P_STAGE_BYTES);
-  const int warp = threadIdx.x >> 5;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-
-  if (warp == 0 && lane_id() == 0) {
-    prefetch_tmap(&mapA);
-    prefetch_tmap(&mapB);
-  }
-  if (warp == 1 && lane_id() == 0) {
-    for (int i = 0; i < P_NS; ++i) {
-      mbar_init(&tail->full[i], 1);      // leader: its producer's arrive.expect_tx; bytes come from both CTAs
-      mbar_init(&tail->empty[i], 1);     // the leader's multicast commit
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tail->tfull[i], 1);
-      mbar_init(&tail->tempty[i], 2 * EPI_THREADS / 32);   // epilogue warps of BOTH CTAs (leader's copy is used)
-    }
-    fence_mbar_init();
-  }
-  cluster_sync();                          // both CTAs' barriers exist before any remote signal
-  if (warp == 2) {
-    tmem_alloc_pair(&tail->tmem_base, TMEM_COLS);
-    tmem_relinquish_pair();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tail->tmem_base;
-
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int nMb2 = (p.M + 255) / 256;
-  const int tiles = nMb2 * p.nNb;
-
-  if (warp == 0) {
-    reg_dealloc<40>();
-    if (lane_id() == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = pair; t < tiles; t += npairs) {
-        const int m0 = (t / p.nNb) * 256 + static_cast<int>(rank) * 128;
-        const int nh0 = (t % p.nNb) * BN + static_cast<int>(rank) * 128;
-        for (int kb = 0; kb < p.nK; ++kb) {
-          mbar_wait(&tail->empty[stage], phase ^ 1);
-          uint64_t* fb = &tail->full[stage];
-          if (leader) mbar_arrive_expect_tx(fb, 2 * P_STAGE_BYTES);
-          uint8_t* sa = stages + stage * P_STAGE_BYTES;
-          uint8_t* sb = sa + 16384;
-          const int k0 = kb * BK;
-          if (A_MN == 0) {
-            tma_load_2d_pair(sa, &mapA, fb, k0, m0);
-          } else {
-            tma_load_2d_pair(sa, &mapA, fb, m0, k0);
-            tma_load_2d_pair(sa + 8192, &mapA, fb, m0 + 64, k0);
-          }
-          if (B_MN == 0) {
-            tma_load_2d_pair(sb, &mapB, fb, k0, nh0);
-          } else {
-            tma_load_2d_pair(sb, &mapB, fb, nh0, k0);
-            tma_load_2d_pair(sb + 8192, &mapB, fb, nh0 + 64, k0);
-          }
-          if (++stage == P_NS) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    reg_dealloc<40>();
-    if (leader && lane_id() == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN, B_MN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = pair; t < tiles; t += npairs) {
-        mbar_wait(&tail->tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.nK; ++kb) {
-          mbar_wait(&tail->full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stages + stage * P_STAGE_BYTES);
-          const uint32_t sb = sa + 16384;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16_pair(tmem_d, da, db, idesc, (kb == 0 && k == 0) ? 0u : 1u);
-          }
-          umma_commit_pair(&tail->empty[stage], 3);     // frees the stage in both CTAs
-          if (++stage == P_NS) { stage = 0; phase ^= 1; }
-        }
-        umma_commit_pair(&tail->tfull[acc], 3);          // accumulator ready in both CTAs
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp < EPI_WARP0) {
-    reg_dealloc<40>();
-  } else {
-    reg_alloc<168>();
-    const int ew = warp - EPI_WARP0;
-    const int q = ew & 3, h = ew >> 2;
-    const int lane = lane_id();
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = pair; t < tiles; t += npairs) {
-      const int nb = t % p.nNb;
-      const int m = (t / p.nNb) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
-      const int n0 = nb * BN + h * 128;
-      const float rs = (p.row_scale && m < p.M) ? __ldg(p.row_scale + m) : 1.f;
-      mbar_wait(&tail->tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 128;
-      float vall[4][32];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(taddr + cc * 32, vall[cc]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tempty[acc]), 0));   // the leader's barrier
-      if (m < p.M) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const size_t rowbase = static_cast<size_t>(m) * p.ldc + n0 + cc * 32;
-#pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            const int n = n0 + cc * 32 + v8 * 8;
-            if (n < p.Nc) {
-              float x[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) x[u] = vall[cc][v8 * 8 + u];
-              if (p.acc_in) {
-                const float4 a0 = *reinterpret_cast<const float4*>(p.acc_in + rowbase + v8 * 8);
-                const float4 a1 = *reinterpret_cast<const float4*>(p.acc_in + rowbase + v8 * 8 + 4);
-                x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
-                x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) x[u] *= rs;
-              if (p.acc_out) {
-                *reinterpret_cast<float4*>(p.acc_out + rowbase + v8 * 8) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(p.acc_out + rowbase + v8 * 8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
-              }
-              if (p.out) {
-                *reinterpret_cast<uint4*>(p.out + rowbase + v8 * 8) =
-                    make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                               pack_bf16x2(x[6], x[7]));
-              }
-            }
-          }
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();                          // no CTA frees TMEM while its partner may still use the pair
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, TMEM_COLS);
-  }
-}
-#endif  // ONEPROT_KERNEL_EMULATION
 
 #include "vector_kernels.cuh"   // the non-tensor-core kernels (also compiled for the CPU emulation of the tests)
 
@@ -1133,7 +907,6 @@ __global__ void mc_reduce_bf16_kernel(const uint4* src_mc, uint4* __restrict__ d
 namespace {
 
 thread_local std::string g_err;
-op::OwnerMaps g_no_owner_maps{};   // placeholder kernel argument of the non-push GEMM instantiations
 std::atomic<long long> g_launches{0};   // process-wide: backward runs on autograd's thread
 
 int fail(int code, const std::string& msg) {
@@ -1225,10 +998,6 @@ void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
       best_cost = cost;
       best_ci = ci;
     }
-  }
-  if (const char* e = getenv("ONEPROT_CI")) {   // experiment knob
-    const int v = atoi(e);
-    if (v > 0) best_ci = std::min(v, p.nI);
   }
   p.CI = std::max(1, best_ci);
   p.nChunks = cdiv(p.nI, p.CI);
@@ -1360,14 +1129,8 @@ int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, i
   }
   if (E) {
     constexpr int smem_e = op::SCfg<op::EPI_FWD_E>::SMEM;
-    static const bool l2_hints = getenv("ONEPROT_DZ_L2_HINTS") != nullptr;    // experiment knob, as in oneprot_clip_dz_panel
-    if (l2_hints) {
-      if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E_L2>, smem_e))) return rc;
-      op::clip_s_kernel<op::EPI_FWD_E_L2><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
-    } else {
-      if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E>, smem_e))) return rc;
-      op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
-    }
+    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E>, smem_e))) return rc;
+    op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
   } else {
     op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   }
@@ -1526,14 +1289,8 @@ int oneprot_clip_dz_panel(const void* A_rows, const void* B_all, int rows, int N
   if ((rc = make_map(&mapW, Wz, N, rows, ldw, op::BM))) return rc;
   constexpr int smem = op::SCfg<op::EPI_DZ>::SMEM;
   const int grid = std::min(num_sms(), p.nJ * p.nChunks);
-  static const bool l2_hints = getenv("ONEPROT_DZ_L2_HINTS") != nullptr;    // experiment knob
-  if (l2_hints) {
-    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ_L2>, smem))) return rc;
-    op::clip_s_kernel<op::EPI_DZ_L2><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
-  } else {
-    if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
-    op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
-  }
+  if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_DZ>, smem))) return rc;
+  op::clip_s_kernel<op::EPI_DZ><<<grid, op::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, mapW, p);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;
@@ -1718,90 +1475,17 @@ int oneprot_gemm_bf16_ex(const void* A, int lda, int a_mn, const void* B, int ld
   if (b_mn) rc = make_map(&mapB, B, Nc, K, ldb, 64); else rc = make_map(&mapB, B, K, Nc, ldb, op::BN);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#ifndef ONEPROT_KERNEL_EMULATION   // CTA pairs are not emulated
-  static const bool use_pairs = getenv("ONEPROT_CG2") != nullptr;
-  if (use_pairs && !dot_mat && (num_sms() % 2 == 0)) {
-    // CTA-pair variant: per-CTA boxes are 128 rows for both operands
-    if (a_mn) rc = make_map(&mapA, A, M, K, lda, 64); else rc = make_map(&mapA, A, K, M, lda, 128);
-    if (rc) return rc;
-    if (b_mn) rc = make_map(&mapB, B, Nc, K, ldb, 64); else rc = make_map(&mapB, B, K, Nc, ldb, 128);
-    if (rc) return rc;
-    const int tiles2 = cdiv(M, 256) * p.nNb;
-    const int grid2 = 2 * std::min(num_sms() / 2, tiles2);
-#define LAUNCH_GEMM2(AM, BMJ)                                                                      \
-  do {                                                                                             \
-    if ((rc = prep_kernel(op::gemm2_kernel<AM, BMJ>, op::GEMM2_SMEM))) return rc;                  \
-    op::gemm2_kernel<AM, BMJ><<<grid2, op::NUM_THREADS, op::GEMM2_SMEM, st>>>(mapA, mapB, p);      \
-  } while (0)
-    if (!a_mn && !b_mn) LAUNCH_GEMM2(0, 0);
-    else if (!a_mn && b_mn) LAUNCH_GEMM2(0, 1);
-    else if (a_mn && !b_mn) LAUNCH_GEMM2(1, 0);
-    else LAUNCH_GEMM2(1, 1);
-#undef LAUNCH_GEMM2
-    ++g_launches;
-    OP_CUDA(cudaGetLastError());
-    return ONEPROT_OK;
-  }
-#endif
   const int grid = std::min(num_sms(), p.nMb * p.nNb);
 #define LAUNCH_GEMM(AM, BMJ)                                                                       \
   do {                                                                                             \
-    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ, false>, op::GEMM_SMEM))) return rc;             \
-    op::gemm_kernel<AM, BMJ, false><<<grid, op::NUM_THREADS, op::GEMM_SMEM, st>>>(mapA, mapB, g_no_owner_maps, p); \
+    if ((rc = prep_kernel(op::gemm_kernel<AM, BMJ>, op::GEMM_SMEM))) return rc;                    \
+    op::gemm_kernel<AM, BMJ><<<grid, op::NUM_THREADS, op::GEMM_SMEM, st>>>(mapA, mapB, p);          \
   } while (0)
   if (!a_mn && !b_mn) LAUNCH_GEMM(0, 0);
   else if (!a_mn && b_mn) LAUNCH_GEMM(0, 1);
   else if (a_mn && !b_mn) LAUNCH_GEMM(1, 0);
   else LAUNCH_GEMM(1, 1);
 #undef LAUNCH_GEMM
-  ++g_launches;
-  OP_CUDA(cudaGetLastError());
-  return ONEPROT_OK;
-}
-
-int oneprot_gemm_bf16_push(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int Nc, int K,
-                           const float* acc_in, int ld_acc, const float* row_scale, void* const* owner_dst, int owners,
-                           int my_rank, int rows_per_owner, int ld_dst, void* stream) {
-  if (!A || !B || !owner_dst) return fail(ONEPROT_ERR_ARG, "gemm_push: null pointer");
-  if (my_rank < 0 || my_rank >= owners) return fail(ONEPROT_ERR_ARG, "gemm_push: my_rank out of range");
-  if (!a_mn || !b_mn) return fail(ONEPROT_ERR_ARG, "gemm_push: only the dB layout (a_mn = b_mn = 1) is instantiated");
-  if (owners <= 0 || owners > 8 || rows_per_owner <= 0 || rows_per_owner % op::BM || M != owners * rows_per_owner)
-    return fail(ONEPROT_ERR_ARG, "gemm_push: need <= 8 owners and rows_per_owner a multiple of 128 with M = owners * rows_per_owner");
-  if (Nc <= 0 || K <= 0 || Nc % 8 || ld_dst < Nc || ld_dst % 8 || (acc_in && (ld_acc < Nc || ld_acc % 8)))
-    return fail(ONEPROT_ERR_ARG, "gemm_push: bad sizes");
-  if (lda < M || ldb < Nc) return fail(ONEPROT_ERR_ARG, "gemm_push: leading dimension too small");
-  if (optrace::recording())
-    optrace::add("gemm_push A=%p lda=%d B=%p ldb=%d M=%d Nc=%d K=%d acc_in=%p ld_acc=%d row_scale=%p owners=%d my_rank=%d rows_per_owner=%d ld_dst=%d st=%p",
-                 A, lda, B, ldb, M, Nc, K, (const void*)acc_in, ld_acc, (const void*)row_scale, owners, my_rank, rows_per_owner, ld_dst, stream);
-  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
-  op::GParams p{};
-  p.M = M; p.Nc = Nc; p.nK = cdiv(K, op::BK);
-  p.nMb = cdiv(M, op::BM); p.nNb = cdiv(Nc, op::BN);
-  p.acc_in = acc_in; p.ldc = ld_acc; p.row_scale = row_scale; p.rows_per_owner = rows_per_owner;
-  p.mb_rot = ((my_rank + 1) % owners) * (rows_per_owner / op::BM);   // start with the next rank's rows
-  CUtensorMap mapA, mapB;
-  op::OwnerMaps om{};
-  int rc;
-  if ((rc = make_map(&mapA, A, M, K, lda, 64))) return rc;
-  if ((rc = make_map(&mapB, B, Nc, K, ldb, 64))) return rc;
-  for (int o = 0; o < owners; ++o)
-    if ((rc = make_map(&om.m[o], owner_dst[o], Nc, rows_per_owner, ld_dst, op::BM))) return rc;
-  const int grid = std::min(num_sms(), p.nMb * p.nNb);
-  if ((rc = prep_kernel(op::gemm_kernel<1, 1, true>, op::GEMM_PUSH_SMEM))) return rc;
-  op::gemm_kernel<1, 1, true><<<grid, op::NUM_THREADS, op::GEMM_PUSH_SMEM, static_cast<cudaStream_t>(stream)>>>(mapA, mapB, om, p);
-  ++g_launches;
-  OP_CUDA(cudaGetLastError());
-  return ONEPROT_OK;
-}
-
-int oneprot_sum_slots_bf16(const void* slots, int W, size_t count, void* out, void* stream) {
-  if (!slots || !out || W <= 0 || count == 0 || count % 8 || (reinterpret_cast<uintptr_t>(slots) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
-    return fail(ONEPROT_ERR_ARG, "sum_slots_bf16: count must be a multiple of 8, pointers 16-byte aligned");
-  if (optrace::recording()) optrace::add("sum_slots_bf16 slots=%p W=%d count=%zu out=%p st=%p", slots, W, count, out, stream);
-  if (optrace::dry()) { ++g_launches; return ONEPROT_OK; }
-  const size_t n16 = count / 8;
-  const int blocks = static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(num_sms()) * 8));
-  op::sum_slots_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(slots), W, n16, static_cast<uint4*>(out));
   ++g_launches;
   OP_CUDA(cudaGetLastError());
   return ONEPROT_OK;

@@ -468,22 +468,6 @@ __global__ void rowdot_dense_kernel(const void* __restrict__ x, const void* __re
   }
 }
 
-// out[i] = bf16( sum_w slots[w][i] ) with fp32 accumulation in slot order (deterministic); 8 per thread
-__global__ void sum_slots_bf16_kernel(const uint4* __restrict__ slots, int W, size_t n16, uint4* __restrict__ out) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int w = 0; w < W; ++w) {
-      float f[8];
-      bf16x8_to_float(slots[static_cast<size_t>(w) * n16 + i], f);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] += f[u];
-    }
-    out[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                        pack_bf16x2(acc[6], acc[7]));
-  }
-}
-
 // fp32 -> bf16 limbs: x = h + m + l (each bf16).  side 0 (left operand):  [h h m | h m l]
 //                                                   side 1 (right operand): [h m h | l m h]
 // terms = 3 keeps the first three limb products (h.h + h.m + m.h), terms = 6 all six of order <= 2.

@@ -498,22 +498,6 @@ def mc_reduce_bf16(src_mc_addr: int, dst, nbytes: int):
           "oneprot_mc_reduce_bf16")
 
 
-def gemm_bf16_push(A, B, M: int, Nc: int, K: int, owner_dst_addrs, my_rank: int, rows_per_owner: int, ld_dst: int, *,
-                   acc_in=None, row_scale=None):
-    """dB-layout GEMM (a_mn = b_mn = 1) whose tiles are pushed to their owners; see oneprot_gemm_bf16_push."""
-    _need_cuda(A, B, acc_in, row_scale)
-    arr = (C.c_void_p * len(owner_dst_addrs))(*[C.c_void_p(a) for a in owner_dst_addrs])
-    check(_lib.load().oneprot_gemm_bf16_push(ptr(A), A.stride(0), 1, ptr(B), B.stride(0), 1, M, Nc, K, ptr(acc_in),
-                                             acc_in.stride(0) if acc_in is not None else 0, ptr(row_scale), arr,
-                                             len(owner_dst_addrs), my_rank, rows_per_owner, ld_dst, _stream()),
-          "oneprot_gemm_bf16_push")
-
-
-def sum_slots_bf16(slots, W: int, count: int, out):
-    _need_cuda(slots, out)
-    check(_lib.load().oneprot_sum_slots_bf16(ptr(slots), W, count, ptr(out), _stream()), "oneprot_sum_slots_bf16")
-
-
 def retrieval_ranks(S, M, label_dot, rank_s2m, rank_m2s, scratch=None):
     """rank_s2m[i] = #{j != i: <s_i, m_j> > label_dot[i]}, rank_m2s[j] = #{i != j: <s_i, m_j> > label_dot[j]}."""
     _need_cuda(S, M, label_dot, rank_s2m, rank_m2s)

@@ -45,7 +45,7 @@ def eligible(cfg, ops, comm, scale_requires_grad: bool) -> bool:
 
 class _State:
     """What the backward needs from the forward (kept on ctx)."""
-    __slots__ = ("saved", "B_all_ptr", "B_keep", "token", "mode", "scale_dev", "E")
+    __slots__ = ("saved", "B_all_ptr", "B_keep", "token", "mode", "scale_dev", "E", "hold")
 
 
 def forward(ctx, ops, scale_dev, cfg, comm, K, keep=None):
@@ -74,7 +74,7 @@ def forward(ctx, ops, scale_dev, cfg, comm, K, keep=None):
         f.stats_rows_n, f.stats_off = N, 0
         f.stats = sp + 4 * STATS_AT
         check(lib.oneprot_seq_fwd(C.byref(f)), "oneprot_seq_fwd")
-        st.B_all_ptr, st.B_keep, st.token = ops.B.data_ptr(), ops.B, None
+        st.B_all_ptr, st.B_keep, st.token, st.hold = ops.B.data_ptr(), ops.B, None, None
     else:
         x = comm.seq_forward_desc(ops, rank, W, sp + 4 * STATS_AT)
         ag = _lib.AgDesc(*x["ag"])
@@ -88,6 +88,7 @@ def forward(ctx, ops, scale_dev, cfg, comm, K, keep=None):
         comm._barrier()                       # every rank's partial sums are in place
         check(lib.oneprot_seq_fwd_end(C.byref(f)), "oneprot_seq_fwd_end")
         st.B_all_ptr, st.B_keep, st.token = x["B_all"], None, x["token"]
+        st.hold = comm.hold_for_backward(x["B_view"]) if any(ctx.needs_input_grad[:2]) else None
     ctx.seq = st
     return saved[0:1], saved[FLAG_AT:FLAG_AT + 1].view(torch.int32)
 
@@ -126,7 +127,7 @@ def backward(ctx, g_loss, cfg, ops, comm, K):
         q.dB = dB.data_ptr() if want_b else None
         check(lib.oneprot_seq_bwd_main(C.byref(q)), "oneprot_seq_bwd_main")
         return dA, dB
-    B_keep = comm.b_all_for_backward(ops, None, st.token, rank, W)   # None: the gathered operand is still in place
+    B_keep = comm.b_all_for_backward(ops, None, st.token, rank, W, hold=st.hold)   # None: the gathered operand is still in place
     q.B_all = B_keep.data_ptr() if B_keep is not None else st.B_all_ptr
     side = comm.side_stream(dev)
     dB_out = torch.empty(n, d, dtype=torch.bfloat16, device=dev)

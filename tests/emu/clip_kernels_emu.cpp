@@ -88,7 +88,8 @@ void emu_dz_panel(const void* A_rows, const void* B, int rows, int N, int d, int
   make_map(&mA, A_rows, d, rows, d, op::BM);
   make_map(&mB, B, d, N, d, op::BN);
   make_map(&mW, Wz, N, rows, ldw, op::BM);
-  if (l2_hints) run_s<op::EPI_DZ_L2>(mA, mB, mW, p); else run_s<op::EPI_DZ>(mA, mB, mW, p);
+  (void)l2_hints;
+  run_s<op::EPI_DZ>(mA, mB, mW, p);
 }
 
 void emu_rowcol_max(const void* A, const void* B, int n, int N, int d, const float* scale, float* rowmax, float* colmax, float* scratch) {
@@ -169,13 +170,12 @@ void emu_gemm(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn
   CUtensorMap mA, mB;
   if (a_mn) make_map(&mA, A, M, K, lda, 64); else make_map(&mA, A, K, M, lda, op::BM);
   if (b_mn) make_map(&mB, B, Nc, K, ldb, 64); else make_map(&mB, B, K, Nc, ldb, op::BN);
-  op::OwnerMaps om{};
   const int grid = std::min(g_sms, p.nMb * p.nNb);
   emu::launch(dim3(grid), dim3(op::NUM_THREADS), [&] {
-    if (!a_mn && !b_mn) op::gemm_kernel<0, 0, false>(mA, mB, om, p);
-    else if (!a_mn && b_mn) op::gemm_kernel<0, 1, false>(mA, mB, om, p);
-    else if (a_mn && !b_mn) op::gemm_kernel<1, 0, false>(mA, mB, om, p);
-    else op::gemm_kernel<1, 1, false>(mA, mB, om, p);
+    if (!a_mn && !b_mn) op::gemm_kernel<0, 0>(mA, mB, p);
+    else if (!a_mn && b_mn) op::gemm_kernel<0, 1>(mA, mB, p);
+    else if (a_mn && !b_mn) op::gemm_kernel<1, 0>(mA, mB, p);
+    else op::gemm_kernel<1, 1>(mA, mB, p);
   });
 }
 

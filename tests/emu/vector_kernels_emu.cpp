@@ -89,12 +89,6 @@ void emu_rowdot(const void* x, const void* y, int rows, int d, int fp32, float* 
     if (fp32) op::rowdot_dense_kernel<true>(x, y, rows, d, out); else op::rowdot_dense_kernel<false>(x, y, rows, d, out);
   });
 }
-void emu_sum_slots_bf16(const void* slots, int W, size_t count, void* out) {
-  const size_t n16 = count / 8;
-  emu::launch(dim3(static_cast<unsigned>(std::min<size_t>((n16 + 255) / 256, SMS * 8))), dim3(256), [&] {
-    op::sum_slots_bf16_kernel(static_cast<const uint4*>(slots), W, n16, static_cast<uint4*>(out));
-  });
-}
 void emu_split_fp32(const float* x, void* out, int rows, int d, int side, int terms) {
   const size_t total = static_cast<size_t>(rows) * d;
   emu::launch(dim3(static_cast<unsigned>(std::min<size_t>((total + 255) / 256, SMS * 16))), dim3(256), [&] {

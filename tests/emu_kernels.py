@@ -153,7 +153,7 @@ def dz_panel(A_rows, B_all, grow0, scale_dev, stats, wr, wc, dg, Wz):
     CALLS.append("dz_panel")
     rows, d = A_rows.shape
     _tc().emu_dz_panel(_p(A_rows), _p(B_all), rows, B_all.shape[0], d, grow0, _p(scale_dev), _p(stats), _p(wr), _p(wc), _p(dg), _p(Wz),
-                       Wz.stride(0), int(bool(os.environ.get("ONEPROT_DZ_L2_HINTS"))))
+                       Wz.stride(0), 0)
 
 
 def gemm_rowdot_scratch_floats(M, Nc):

@@ -30,14 +30,15 @@ def _loss_mod(**kw):
     return ClipLoss(**kw)
 
 
+@pytest.mark.parametrize("keep_exp", [True, False])     # stored-exponentials backward (default) / recompute backward
 @pytest.mark.parametrize("name", SINGLE)
-def test_golden_single_rank(name):
+def test_golden_single_rank(name, keep_exp):
     g = load_golden(name)
     A = bf16_from_bits(g["A_bf16"]).cuda().requires_grad_(True)
     B = bf16_from_bits(g["B_bf16"]).cuda().requires_grad_(True)
     is_t = bool(g["scale_is_tensor"])
     ls = torch.tensor(float(g["scale"]), device="cuda", requires_grad=True) if is_t else float(g["scale"])
-    m = _loss_mod(loss_dtype=torch.float32)
+    m = _loss_mod(loss_dtype=torch.float32, keep_exp=keep_exp)
     loss = m(A, B, ls)
     loss.backward()
     torch.cuda.synchronize()
@@ -58,14 +59,15 @@ def test_golden_single_rank(name):
 
 @pytest.mark.parametrize("n,d,corr,t_in_b", [(64, 1024, True, True), (1000, 1024, True, True), (2048, 1024, False, True),
                                              (96, 512, True, False), (3000, 256, True, True)])
-def test_synthetic_vs_closed_form(n, d, corr, t_in_b):
+@pytest.mark.parametrize("keep_exp", [True, False])
+def test_synthetic_vs_closed_form(n, d, corr, t_in_b, keep_exp):
     a, b = oc.synthetic_pair(n, d, seed=1234, pair_id=1, rank=0, correlated=corr, temperature_into_b=t_in_b)
     s = 1.0 if t_in_b else 1.0 / 0.07
     ref = oc.clip_loss_closed_form(a.double().numpy(), b.double().numpy(), s)
     A = a.cuda().requires_grad_(True)
     B = b.cuda().requires_grad_(True)
     ls = torch.tensor(s, device="cuda", requires_grad=True)
-    m = _loss_mod(loss_dtype=torch.float32)
+    m = _loss_mod(loss_dtype=torch.float32, keep_exp=keep_exp)
     loss = m(A, B, ls)
     loss.backward()
     assert rel_err(loss.item(), ref.loss) < BF16_LOSS_RTOL
@@ -81,7 +83,7 @@ def test_multi_panel_backward_equals_single_panel():
     for pb in (1 << 30, 256 * 1536 * 2):
         A = a.cuda().requires_grad_(True)
         B = b.cuda().requires_grad_(True)
-        _loss_mod(loss_dtype=torch.float32, panel_bytes=pb)(A, B).backward()
+        _loss_mod(loss_dtype=torch.float32, panel_bytes=pb, keep_exp=False)(A, B).backward()
         outs.append((A.grad.float().cpu().numpy(), B.grad.float().cpu().numpy()))
     assert np.array_equal(outs[0][0], outs[1][0])          # dA rows are panel-independent: bit-exact
     assert cosine(outs[0][1], outs[1][1]) > 0.99999         # dB: fp32 accumulation across panels

@@ -35,11 +35,13 @@ def _worker(rank, world, port, n, d, results):
     rec["a"], rec["b"] = a.float().numpy(), b.float().numpy()
     for ll in (False, True):
         for gwg in (False, True):
+            keep_exp = n != 1024            # n = 1024 runs the recompute backward over several dL/dZ panels
             A = a.cuda().requires_grad_(True)
             B = b.cuda().requires_grad_(True)
             ls = torch.tensor(s, device="cuda", requires_grad=True)
             m = ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world,
-                         loss_dtype=torch.float32, panel_bytes=(1 << 30) if n != 1024 else 512 * 2048 * 2)
+                         loss_dtype=torch.float32, panel_bytes=(1 << 30) if n != 1024 else 512 * 2048 * 2,
+                         keep_exp=keep_exp)
             loss = m(A, B, ls)
             (loss * gout).backward()
             m.check_last_call()

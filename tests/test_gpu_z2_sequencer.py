@@ -36,6 +36,7 @@ def test_single_gpu_bit_identical_to_python_host(n, d, panel_rows, need):
     kw = {}
     if panel_rows:
         kw["panel_bytes"] = 2 * ((n + 63) // 64 * 64) * panel_rows
+        kw["keep_exp"] = False                       # several dL/dZ panels: the recompute backward
     l0, ga0, gb0, k0 = _step(a, b, need=need, **kw)
     l1, ga1, gb1, k1 = _step(a, b, need=need, host_sequencer=True, **kw)
     assert l0.item() == l1.item()
@@ -87,7 +88,7 @@ def _worker(rank, world, port, n, d, results):
                 B = b.cuda().requires_grad_(True)
                 m = ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world,
                              loss_dtype=torch.float32, host_sequencer=seq,
-                             panel_bytes=(5 << 28) if n != 1024 else 2 * (world * n) * 384)
+                             panel_bytes=(5 << 28) if n != 1024 else 2 * (world * n) * 384, keep_exp=n != 1024)
                 loss = m(A, B)
                 (loss * (1.0 + 0.25 * rank)).backward()
                 torch.cuda.synchronize()

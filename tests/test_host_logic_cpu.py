@@ -56,7 +56,7 @@ def test_single_rank_host_path_vs_golden(fake, name, panel_bytes):
     B = bf16_from_bits(g["B_bf16"]).requires_grad_(True)
     is_t = bool(g["scale_is_tensor"])
     ls = torch.tensor(float(g["scale"]), requires_grad=True) if is_t else float(g["scale"])
-    m = fake.ClipLoss(loss_dtype=torch.float32, panel_bytes=panel_bytes)
+    m = fake.ClipLoss(loss_dtype=torch.float32, panel_bytes=panel_bytes, keep_exp=False)
     out = m(A, B, ls, output_dict=True)
     assert set(out) == {"contrastive_loss"}
     loss = out["contrastive_loss"]
@@ -122,7 +122,7 @@ def test_two_reference_path_handles_arbitrary_inputs(fake, mode):
     A = a.clone().requires_grad_(True)
     B = b.clone().requires_grad_(True)
     ls = torch.tensor(1.0, requires_grad=True)
-    m = fake.ClipLoss(loss_dtype=torch.float32, robust=mode, panel_bytes=128 * 128 * 2)
+    m = fake.ClipLoss(loss_dtype=torch.float32, robust=mode, panel_bytes=128 * 128 * 2, keep_exp=False)
     loss = m(A, B, ls)
     loss.backward()
     m.check_last_call()
@@ -188,6 +188,14 @@ def _worker(rank, world, port, results, provider="fake"):
     # gather_features keeps the reference contract
     am, asq = clip_loss.gather_features(a.float().requires_grad_(True), b.float(), False, True, rank, world)
     rec["gather_shape"] = tuple(am.shape)
+    # ranks that disagree on n must all get a ValueError before any exchange of the loss itself
+    m = clip_loss.ClipLoss(rank=rank, world_size=world)
+    ragged = torch.zeros(6 + rank, 32, dtype=torch.bfloat16)
+    try:
+        m(ragged, ragged)
+        rec["ragged"] = "no error"
+    except ValueError as e:
+        rec["ragged"] = str(e)
     results[rank] = rec
     dist.barrier()
     dist.destroy_process_group()
@@ -210,6 +218,7 @@ def test_two_rank_gloo_conventions_vs_reference_golden(provider, port):
     for r in range(world):
         rec = results[r]
         assert rec["gather_shape"] == (24, 32)
+        assert "same (n, d)" in rec["ragged"] and "(6, 32), (7, 32)" in rec["ragged"]
         for ll in (0, 1):
             for gwg in (0, 1):
                 ref = f"ll{ll}_gwg{gwg}"

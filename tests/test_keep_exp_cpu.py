@@ -113,52 +113,6 @@ def test_dz_from_exp_kernel_source_matches_float64(n, N, grow0):
     assert torch.equal(E[:n, :N], want[:n, :N])                                      # bf16 round-to-nearest of the same fp32 value
 
 
-def test_overlapped_rescale_gives_the_same_gradients(prov, monkeypatch):
-    """keep_overlap rescales panel by panel on a second stream (tests/test_sequencer_cpu.py checks the stream / event
-    order) and splits only the dB GEMM along its K dimension; per element it is the same arithmetic, so dA is
-    bit-equal and dB equal up to the fp32 accumulation order of its panel terms."""
-    import contextlib
-    cl, K = prov
-
-    class _Ev:
-        pass
-
-    class _St:
-        cuda_stream = 0
-
-        def record_event(self):
-            return _Ev()
-
-        def wait_event(self, ev):
-            assert isinstance(ev, _Ev)
-
-    st = _St()
-    monkeypatch.setattr(cl, "_rescale_stream", lambda dev: st)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: st)
-    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
-    a, b = oc.synthetic_pair(300, 64, seed=12)
-    ref = oc.clip_loss_closed_form(a.double().numpy(), b.double().numpy(), 1.0)
-    res = []
-    for overlap in (False, True):
-        A = a.clone().requires_grad_(True)
-        B = b.clone().requires_grad_(True)
-        m = cl.ClipLoss(loss_dtype=torch.float32, keep_exp=True, keep_overlap=overlap, panel_bytes=320 * 128 * 2)
-        del K.CALLS[:]
-        m(A, B).backward()
-        assert K.CALLS.count("dz_from_exp") == (3 if overlap else 1) and K.CALLS.count("gemm") == (4 if overlap else 2)    # overlap: dB per panel (K split), dA once
-        res.append((A.grad.float().numpy(), B.grad.float().numpy()))
-        assert cosine(res[-1][0], ref.dA) > 0.9999 and cosine(res[-1][1], ref.dB) > 0.9999
-    assert np.array_equal(res[0][0], res[1][0])                      # dA rows are independent of the split
-    assert cosine(res[0][1], res[1][1]) > 0.999999
-    # explicit panel count (keep_panels), independent of panel_bytes; panels are whole 128-row blocks
-    A = a.clone().requires_grad_(True)
-    B = b.clone().requires_grad_(True)
-    del K.CALLS[:]
-    cl.ClipLoss(loss_dtype=torch.float32, keep_exp=True, keep_overlap=True, keep_panels=5)(A, B).backward()
-    assert K.CALLS.count("dz_from_exp") == 3 and K.CALLS.count("gemm") == 4        # ceil128(300 / 5) = 128 -> 3 panels
-    assert np.array_equal(A.grad.float().numpy(), res[0][0]) and cosine(B.grad.float().numpy(), res[0][1]) > 0.999999
-
-
 @pytest.mark.parametrize("n,N,d,off", [(25, 25, 64, 0), (130, 700, 72, 400), (256, 512, 128, 256)])
 def test_siglip_keeping_forward_kernel_source_matches_float64(n, N, d, off):
     """clip_s_kernel<SFWD_K> (CPU emulation): softplus row sums as SFWD, S = sigma(z) - [i == j] as a bf16 panel clipped to

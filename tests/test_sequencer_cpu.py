@@ -403,75 +403,3 @@ def test_sequencer_workspace_regions_do_not_overlap(streams, n, d, panel_rows):
         assert a0 + sz <= b0, (na, nb)
     assert regs[-1][1] + regs[-1][2] <= endb
     assert all(_addr(a["Wz"]) == _addr(dz[0]["Wz"]) for a in dz) and all(int(a["ldw"]) == ldw for a in dz)
-
-
-# ---------------------------------------------------------------------------------------------
-# keep_exp + keep_overlap: stream / event order of the overlapped rescale (Python host)
-# ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("world", [1, 2])
-@pytest.mark.parametrize("need", [(True, True), (True, False), (False, True)])
-def test_overlapped_rescale_order(streams, monkeypatch, need, world):
-    """Panel q + 1 is rescaled on its own stream, enqueued behind the dB GEMM of panel q; no GEMM reads a panel before
-    the compute stream has waited for that panel's rescale; dA is one GEMM over all rows after the last wait.  Without
-    a dB to hide under (need = (True, False)) the variant falls back to one rescale + one GEMM."""
-    RS = 0x3000
-    rs = FakeStream(RS)
-    monkeypatch.setattr(cl, "_rescale_stream", lambda dev: rs)
-    n, d, rows_cap = (1000 if world == 1 else 1024), 64, 384
-    A, B, scale = _pair(n, d)
-    ldw = (world * n + 63) // 64 * 64
-    cfg = dict(_cfg(world, 0, False, True, 2 * ldw * rows_cap, False, True), keep_overlap=True)
-    comm = comm_mod.LocalComm(K) if world == 1 else FakeNvlsComm(world, 0, streams)
-    lines, _ = _run(streams, A, B, scale, cfg, comm, need)
-    bwd = lines[lines.index("---- backward") + 1:]
-    kinds = [ln.split()[0] for ln in bwd]
-    if world > 1:
-        # the exchange of the partial dB (side stream) is enqueued behind the LAST dB GEMM and before the dA GEMM
-        last_db = max(i for i, ln in enumerate(bwd) if ln.startswith("gemm") and "a_mn=1" in ln)
-        red = kinds.index("mc_reduce_bf16")
-        assert last_db < red and bwd[red].endswith(f"st={SIDE:#x}")
-        if need[0]:
-            assert red < max(i for i, ln in enumerate(bwd) if ln.startswith("gemm") and "a_mn=0" in ln)
-    if not need[1] and world == 1:
-        assert kinds.count("dz_from_exp") == 1 and kinds.count("gemm") == 1 and not any(ln.endswith(f"st={RS:#x}") for ln in bwd)
-        return
-    n_panels = -(-n // rows_cap)
-    assert kinds.count("dz_from_exp") == n_panels and kinds.count("dz_panel") == 0
-    assert kinds.count("gemm") == n_panels + int(need[0])
-    e_base = int(re.search(r"keep E=(0x[0-9a-f]+)", next(ln for ln in lines if ln.split()[0] == "keep")).group(1), 16)
-    done_ev, waited, rescaled_rows, gemms = {}, set(), [], []
-    pending = None
-    for ln in bwd:
-        k = ln.split()[0]
-        if k == "dz_from_exp":
-            assert ln.endswith(f"st={RS:#x}")                                   # on the rescale stream
-            ptr = int(re.search(r"E=(0x[0-9a-f]+)", ln).group(1), 16)
-            r0 = (ptr - e_base) // (2 * ldw)
-            assert int(re.search(r"grow0=(\d+)", ln).group(1)) == r0
-            pending = r0
-            rescaled_rows.append((r0, int(re.search(r"rows=(\d+)", ln).group(1))))
-        elif k == "record" and ln.endswith(f"st={RS:#x}"):
-            done_ev[re.search(r"ev=(\d+)", ln).group(1)] = pending
-        elif k == "wait" and ln.endswith(f"st={MAIN:#x}"):
-            ev = re.search(r"ev=(\d+)", ln).group(1)
-            if ev in done_ev:
-                waited.add(done_ev[ev])
-        elif k == "gemm":
-            assert ln.endswith(f"st={MAIN:#x}")
-            ptr = int(re.search(r" A=(0x[0-9a-f]+)", ln).group(1), 16)
-            r0 = (ptr - e_base) // (2 * ldw)
-            a_mn = int(re.search(r"a_mn=(\d)", ln).group(1))
-            gemms.append((a_mn, r0, int(re.search(r" K=(\d+)", ln).group(1)), int(re.search(r" M=(\d+)", ln).group(1))))
-            if a_mn:      # dB term of one panel: needs that panel
-                assert r0 in waited, "dB GEMM reads a panel whose rescale the compute stream has not waited for"
-            else:         # dA over all rows: needs every panel
-                assert waited == {r for r, _ in rescaled_rows} and len(waited) == n_panels
-    panels = [(r0, min(rows_cap, n - r0)) for r0 in range(0, n, rows_cap)]
-    assert rescaled_rows == panels
-    assert [(g[1], g[2]) for g in gemms if g[0]] == panels                        # dB: K split by panel
-    if need[0]:
-        assert gemms[-1][0] == 0 and gemms[-1][1] == 0 and gemms[-1][3] == n     # dA: one GEMM, all rows, last
-    # overlap: the rescale of panel 1 is enqueued right behind the dB GEMM of panel 0
-    first_gemm = kinds.index("gemm")
-    second_rescale = [i for i, k in enumerate(kinds) if k == "dz_from_exp"][1]
-    assert first_gemm < second_rescale < [i for i, k in enumerate(kinds) if k == "gemm"][1]

@@ -37,6 +37,9 @@ os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 GLOBAL_N = int(os.environ.get("ONEPROT_BENCH_N", 32768))
 DIM = int(os.environ.get("ONEPROT_BENCH_D", 1024))
 METRIC = "cliploss_fwd_bwd_samples_per_s"
+# fp32 global loss of the synthetic pair (tools.synthetic.synthetic_global_rows, seed 1234) measured on 1 x B200; every
+# world size must reproduce it to 1e-6 relative (the row-sharded path computes the same global function)
+EXPECTED_LOSS = {}
 UNIT = "samples/s"
 
 
@@ -191,19 +194,19 @@ def cpu_panel_step(A, B, m):
     return float(loss.detach())
 
 
-def cpu_reference(steps, warmup, budget_s_per_step):
-    """The only place of bench.py that executes oracle/ code (cpu_baseline / --impl reference leg)."""
+CPU_PANEL_ROWS = 8192     # fixed sample of the CPU legs: rows [0, 8192) of both logit matrices = 1/4 of a full step
+
+
+def cpu_reference(steps, warmup):
+    """The baseline legs (cpu_baseline / --impl reference / eager_b200) are the only places of bench.py that execute
+    oracle/ code.  Same fixed sample in every leg (round 1 sized it by a time budget: 128 vs 8192 rows gave a 2.4x
+    spread on the same host from the sample size alone)."""
     import torch
-    from tools.synthetic import synthetic_pair
+    from tools.synthetic import synthetic_global_rows
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    a, b = synthetic_pair(GLOBAL_N, DIM, seed=1234, dtype="fp32")
-    # probe to size the panel
-    t0 = time.perf_counter(); cpu_panel_step(a, b, 128); cpu_panel_step(a, b, 128)
-    t_probe = (time.perf_counter() - t0) / 2
-    m = 128
-    while m * 2 <= GLOBAL_N and t_probe * (m * 2 / 128) <= budget_s_per_step:
-        m *= 2
+    a, b = synthetic_global_rows(0, GLOBAL_N, DIM, seed=1234, dtype="fp32")
+    m = min(CPU_PANEL_ROWS, GLOBAL_N)
     for _ in range(warmup):
         cpu_panel_step(a, b, m)
     times = []
@@ -229,14 +232,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 3))
-    budget = max(0.25, min(2.0, 120.0 / (steps + warmup)))   # whole run within a few minutes
-    cb = cpu_reference(steps, warmup, budget)
+    # ~1.7 s per sampled step on a 16-core host: the default driver call (--steps 20 --warmup 5) takes under a minute;
+    # very long requests are capped so that the arm always ends within a few minutes (the count run is reported)
+    steps, warmup = max(1, min(args.steps, 60)), max(0, min(args.warmup, 10))
+    cb = cpu_reference(steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step_full_equiv"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": f"ClipLoss fwd+bwd, global batch {GLOBAL_N} x {DIM}, reference CPU path (W=1)",
-                       "global_batch": GLOBAL_N, "dim": DIM},
+                       "global_batch": GLOBAL_N, "dim": DIM, "sample_rows": min(CPU_PANEL_ROWS, GLOBAL_N),
+                       "requested": {"steps": args.steps, "warmup": args.warmup}},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -250,7 +255,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from oneprot_b200 import ClipLoss, kernels
-    from tools.synthetic import synthetic_pair   # input generator (not the oracle)
+    from tools.synthetic import synthetic_global_rows   # input generator (not the oracle)
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -273,8 +278,10 @@ def run_ours(args):
     warmup_req = warmup
     warmup = warmup * world
 
-    a, b = synthetic_pair(n, DIM, seed=1234, pair_id=0, rank=rank, correlated=True, temperature_into_b=True,
-                          dtype="bf16")
+    # rows [rank n, (rank + 1) n) of ONE global pair that does not depend on the sharding: the global loss is the
+    # same number at 1, 2, 4 and 8 GPUs (checked below against EXPECTED_LOSS)
+    a, b = synthetic_global_rows(rank * n, n, DIM, seed=1234, pair_id=0, correlated=True, temperature_into_b=True,
+                                 dtype="bf16")
     a_pin, b_pin = a.pin_memory(), b.pin_memory()
     A = a.to(dev).requires_grad_(True)
     B = b.to(dev).requires_grad_(True)
@@ -338,6 +345,21 @@ def run_ours(args):
     ms_per_step = float(total_ms.item()) / steps
     loss_val = float(loss_mod.last_loss_fp32.item())
     loss_mod.check_last_call()
+    expected = EXPECTED_LOSS.get((GLOBAL_N, DIM))
+    if expected is not None and abs(loss_val - expected) > 1e-6 * abs(expected):
+        raise SystemExit(f"bench: global loss {loss_val!r} at {world} GPU(s) differs from the 1-GPU value {expected!r} "
+                         f"by more than 1e-6 relative - the sharded path does not compute the same function")
+
+    # ---- sustained leg: >= 3 s of back-to-back steps (power-capped regime; differences under ~8 % between short
+    # runs are power state, not code - VERDICT r1), same timing method, max over ranks
+    sus_steps = max(steps, int(3000.0 / max(ms_per_step, 1e-3)) + 1)
+    barrier()
+    ms_sus = timed(step_device, sus_steps)
+    barrier()
+    sus = torch.tensor([sum(ms_sus), sum(ms_sus[-10:])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sus, op=dist.ReduceOp.MAX)
+    sus_ms, sus_last10_ms = float(sus[0].item()) / sus_steps, float(sus[1].item()) / min(10, sus_steps)
 
     # ---- e2e: pinned host inputs -> H2D -> fwd+bwd -> D2H loss
     # (1) serial: every step copies its own pair on the compute stream, then computes;
@@ -360,7 +382,8 @@ def run_ours(args):
     e2e_serial_ms = measure(lambda: step_e2e(host_loss))
 
     # ---- roofline: the four tensor-core kernels timed alone (rank-local panel), CUDA events
-    roof = kernel_roofline(torch, kernels, A.detach(), B.detach(), n, GLOBAL_N, world, rank, dev, flush) if rank == 0 else None
+    roof = (kernel_roofline(torch, kernels, A.detach(), B.detach(), n, GLOBAL_N, world, rank, dev, flush, loss_mod.keep_exp)
+            if rank == 0 else None)
     if world > 1:
         dist.barrier()
 
@@ -369,7 +392,9 @@ def run_ours(args):
         peaks = _peaks()
         flops = 6.0 * GLOBAL_N * GLOBAL_N * DIM
         step_tflops = flops / world / (ms_per_step * 1e-3) / 1e12        # per GPU, algorithmic
-        dom = max((k for k in roof["kernels"] if "tflops" in roof["kernels"][k]), key=lambda k: roof["kernels"][k]["ms"])
+        # the per-step dominant tensor-core kernel: time alone x launches per step
+        dom = max((k for k in roof["kernels"] if "tflops" in roof["kernels"][k]),
+                  key=lambda k: roof["kernels"][k]["ms"] * roof["kernels"][k]["launches_per_step"])
         dk = roof["kernels"][dom]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -387,7 +412,12 @@ def run_ours(args):
                                    f"gather_with_grad=True, {GLOBAL_N // world} rows per GPU",
                        "global_batch": GLOBAL_N, "dim": DIM, "rows_per_gpu": n, "warmup_steps_run": warmup,
                        "l2": "256 MiB buffer written between timed steps (L2 flush); inputs 128 MiB",
-                       "loss": loss_val, "ms_steps_rank0": ms_steps_rank0,
+                       "loss": loss_val, "loss_expected": expected, "ms_steps_rank0": ms_steps_rank0,
+                       "last10_ms_per_step": sum(ms[-10:]) / len(ms[-10:]),
+                       "sustained": {"steps": sus_steps, "seconds": sus_ms * sus_steps * 1e-3, "ms_per_step": sus_ms,
+                                     "last10_ms_per_step": sus_last10_ms, "value": GLOBAL_N / (sus_ms * 1e-3),
+                                     "frac_of_burst_peak": 6.0 * GLOBAL_N * GLOBAL_N * DIM / world / (sus_ms * 1e-3) / 1e12 / _peaks()["bf16_tflops"]},
+                       "backward": "stored exponentials (keep_exp)" if loss_mod.keep_exp else "recompute",
                        "host": "C step sequencer (ONEPROT_SEQ=1)" if os.environ.get("ONEPROT_SEQ") == "1" else "python",
                        "knobs": {k: v for k, v in os.environ.items() if k.startswith("ONEPROT_") and k not in ("ONEPROT_BENCH_N", "ONEPROT_BENCH_D")}},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": dk["tflops"], "peak": peaks["bf16_tflops"],
@@ -398,16 +428,20 @@ def run_ours(args):
                                   "frac_of_burst_peak": step_tflops / peaks["bf16_tflops"],
                                   "frac_of_sustained_peak": (step_tflops / peaks["bf16_tflops_sustained"]
                                                              if peaks["bf16_tflops_sustained"] else None),
-                                  "executed_over_algorithmic": 1.0 if os.environ.get("ONEPROT_KEEP_EXP") == "1" else 8.0 / 6.0}},
+                                  "executed_over_algorithmic": 1.0 if loss_mod.keep_exp else 8.0 / 6.0}},
             "e2e": {"value": GLOBAL_N / (e2e_serial_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_serial_ms,
                     "h2d_bytes_per_step": 2 * n * DIM * 2, "d2h_bytes_per_step": 4,
-                    "mode": "serial (copy, then compute, on one stream)",
+                    "mode": "serial (copy, then compute, on one stream); dA / dB stay on the device (they feed the encoder backward there), only the loss is read back",
                     "serial_value": GLOBAL_N / (e2e_serial_ms * 1e-3), "serial_ms_per_step": e2e_serial_ms},
             "gpu_launches": launches,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference(steps=2, warmup=1, budget_s_per_step=6.0)
+            try:
+                line["eager_b200"] = eager_b200(torch, a, b, dev, flush, ms_per_step)
+            except Exception as e:      # a baseline that cannot run must not take the measurement down with it
+                line["eager_b200"] = {"unavailable": repr(e)}
+            cb = cpu_reference(steps=3, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if world > 1:
         dist.barrier()      # rank 0 may have spent a while in the roofline / CPU legs
@@ -478,7 +512,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, reps=5):
+def eager_b200(torch, a, b, dev, flush, ours_ms):
+    """The reference's own op sequence (unmodified ClipLoss from oracle/_ref when present, else the oracle port) run
+    eagerly by PyTorch on this GPU, same inputs: the bar SURVEY.md 8(d) names besides the CPU baseline.  Baseline leg
+    (N = 1, rank 0) - checker code, never the product path."""
+    from oracle.eager_bar import time_eager
+    out = {"unit": UNIT, "ours_ms_per_step": ours_ms}
+    for tag, dtype, tf32 in (("bf16", torch.bfloat16, False), ("fp32_tf32", torch.float32, True)):
+        r = time_eager(a, b, dtype, tf32, dev, flush, reps=3, warm=2)
+        out[tag] = {"ms_per_step": r["ms"], "value": (GLOBAL_N / (r["ms"] * 1e-3)) if r["ms"] else None,
+                    "peak_gib": r["peak_gib"], "loss": r["loss"]}
+        out["impl"] = r["kind"]
+    if out["bf16"]["ms_per_step"]:
+        out["speedup_vs_bf16"] = out["bf16"]["ms_per_step"] / ours_ms
+    return out
+
+
+def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, keep, reps=5):
     """Times each tensor-core kernel of one rank's panel alone (CUDA events on the launch stream)."""
     d = A.shape[1]
     off = rank * n
@@ -491,7 +541,6 @@ def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, reps=5):
     K.rowstats(A, B_all, off, diag, stats)
     scratch = K.fwd_sums(A, B_all, scale, stats, rowsum, colsum)
     ldw = (N + 63) // 64 * 64
-    keep = os.environ.get("ONEPROT_KEEP_EXP") == "1"       # stored-exponentials backward: one whole-panel pass per kernel
     rows = n if keep else min(n, max(128, ((1 << 30) // (2 * ldw)) // 128 * 128))
     Wz = torch.empty((rows + 127) // 128 * 128, ldw, dtype=torch.bfloat16, device=dev)
     wr = torch.full((n,), 1e-6, dtype=torch.float32, device=dev)
@@ -523,10 +572,12 @@ def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, reps=5):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         t = sum(ts) / len(ts)
+        per_step = 1 if ("FWD" in name or "dz_from_exp" in name) else -(-n // rows)     # panel kernels run once per panel
         if fl == 0.0:      # HBM-bound vector kernel: 2 bytes read + 2 written per logit
-            out[name] = {"ms": t, "bytes": 4.0 * n * N, "gbps": 4.0 * n * N / (t * 1e-3) / 1e9, "rows": n}
+            out[name] = {"ms": t, "bytes": 4.0 * n * N, "gbps": 4.0 * n * N / (t * 1e-3) / 1e9, "rows": n, "launches_per_step": per_step}
         else:
-            out[name] = {"ms": t, "flops": fl, "tflops": fl / (t * 1e-3) / 1e12, "rows": rows if "FWD" not in name else n}
+            out[name] = {"ms": t, "flops": fl, "tflops": fl / (t * 1e-3) / 1e12, "rows": rows if "FWD" not in name else n,
+                         "launches_per_step": per_step}
     return {"kernels": out}
 
 

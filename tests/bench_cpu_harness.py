@@ -20,6 +20,7 @@ os.environ.setdefault("ONEPROT_BENCH_N", "128" if len(sys.argv) > 1 and sys.argv
 os.environ.setdefault("ONEPROT_BENCH_D", "64")
 
 import torch  # noqa: E402
+import torch.distributed.nn  # noqa: E402,F401  (imported by the reference's loss.py; must precede the torch.device stand-in)
 
 from tests import fake_kernels  # noqa: E402
 
@@ -90,7 +91,7 @@ if mode.startswith("lib"):
     mode = mode[len("lib-"):] or "fallback"
 else:
     clip_loss._KERNELS = fake_kernels
-    for name in ("rowstats", "fwd_sums", "dz_panel", "gemm_bf16", "loss_finalize", "bwd_weights"):
+    for name in ("rowstats", "fwd_sums", "dz_panel", "dz_from_exp", "gemm_bf16", "loss_finalize", "bwd_weights"):
         setattr(kernels, name, getattr(fake_kernels, name))
 
 if mode == "pipelined":

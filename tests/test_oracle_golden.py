@@ -113,3 +113,49 @@ def test_retrieval_metric_oracle_matches_reference_golden():
         assert set(got) == set(want)
         for k in want:
             assert float(got[k]) == want[k], (tag, k)
+
+
+# ---- oracle/_ref: the unmodified reference classes (vendored by oracle/make_ref.py), when present ---------------
+def _ref_or_skip():
+    from oracle.make_ref import import_reference
+    ref = import_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (python oracle/make_ref.py needs /root/reference)")
+    return ref
+
+
+@pytest.mark.parametrize("n,d,scale", [(256, 512, 1.0 / 0.07), (100, 72, 1.0), (33, 40, 5.0)])
+def test_port_and_closed_form_match_the_vendored_reference(n, d, scale):
+    """The port bench.py times and the closed form the GPU tests use, against the reference's own ClipLoss run here."""
+    import torch
+    loss_mod, _ = _ref_or_skip()
+    g = torch.Generator().manual_seed(n)
+    a = torch.nn.functional.normalize(torch.randn(n, d, generator=g, dtype=torch.float64), dim=-1)
+    b = torch.nn.functional.normalize(a + 0.5 * torch.randn(n, d, generator=g, dtype=torch.float64), dim=-1)
+    A, B = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    s = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+    want = loss_mod.ClipLoss()(A, B, s)
+    want.backward()
+    A2, B2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    got = oc.clip_loss_port(A2, B2, scale)
+    got.backward()
+    assert abs(got.item() - want.item()) < 1e-12 and torch.allclose(A2.grad, A.grad, atol=1e-14) and torch.allclose(B2.grad, B.grad, atol=1e-14)
+    cf = oc.clip_loss_closed_form(a.numpy(), b.numpy(), scale)
+    assert abs(cf.loss - want.item()) < 1e-12 and abs(cf.dscale - s.grad.item()) < 1e-12
+    assert np.allclose(cf.dA, A.grad.numpy(), atol=1e-13) and np.allclose(cf.dB, B.grad.numpy(), atol=1e-13)
+    # the row-panel sample of the CPU baseline is the reference's own rows: mean over the first m rows of both matrices
+    m = n // 2
+    za, zb = (scale * a) @ b.T, (scale * b) @ a.T
+    lab = torch.arange(m)
+    panel = (torch.nn.functional.cross_entropy(za[:m], lab) + torch.nn.functional.cross_entropy(zb[:m], lab)) / 2
+    assert abs(oc.clip_loss_port_panel(a, b, m, scale).item() - panel.item()) < 1e-12
+
+
+def test_epilogue_closed_forms_match_the_vendored_reference():
+    import torch
+    _, be = _ref_or_skip()
+    x = torch.randn(17, 24, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    assert np.allclose(oc.normalize_closed_form(x.numpy()), be.Normalize(dim=-1)(x).numpy(), atol=1e-15)
+    sc = be.LearnableLogitScaling(learnable=True)
+    y, s = oc.logit_scaling_closed_form(x.numpy(), float(sc.log_logit_scale))
+    assert np.allclose(y, sc(x).detach().numpy(), rtol=1e-6)

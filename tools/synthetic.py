@@ -21,3 +21,21 @@ def synthetic_pair(n: int, d: int, *, seed: int = 1234, pair_id: int = 0, rank: 
         b = b * (1.0 / 0.07)
     td = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[dtype]
     return a.to(td), b.to(td)
+
+
+GLOBAL_BLOCK = 1024      # rows per independently seeded block of a global pair
+
+
+def synthetic_global_rows(row0: int, rows: int, d: int, *, seed: int = 1234, pair_id: int = 0, correlated: bool = True,
+                          temperature_into_b: bool = True, dtype: str = "bf16"):
+    """Rows [row0, row0 + rows) of ONE global synthetic pair that does not depend on how it is sharded: the pair is
+    drawn in blocks of GLOBAL_BLOCK rows, block k with its own generator (seed, pair_id, k), each block exactly like
+    ``synthetic_pair``.  Rank r of W holds rows [r n, (r + 1) n), so the global loss of ClipLoss(local_loss=False) is
+    the same number at every world size (bench.py asserts it)."""
+    import torch
+
+    k0, k1 = row0 // GLOBAL_BLOCK, -(-(row0 + rows) // GLOBAL_BLOCK)
+    parts = [synthetic_pair(GLOBAL_BLOCK, d, seed=seed + 7919 * (1 + k), pair_id=pair_id, rank=0, correlated=correlated,
+                            temperature_into_b=temperature_into_b, dtype=dtype) for k in range(k0, k1)]
+    lo = row0 - k0 * GLOBAL_BLOCK
+    return (torch.cat([p[0] for p in parts])[lo:lo + rows].contiguous(), torch.cat([p[1] for p in parts])[lo:lo + rows].contiguous())

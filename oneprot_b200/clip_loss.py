@@ -625,31 +625,35 @@ class ClipLoss(nn.Module):
         return labels
 
     def get_logits(self, modality_features, sequence_features, logit_scale):
-        """Materialised logits as in loss.py:85-101 - DEBUG ONLY (the loss path never forms
-        them).  Contraction on the tcgen05 GEMM kernel, fp32 accumulators, scale applied in fp32."""
+        """Materialised logits as in loss.py:85-101 - DEBUG / API parity only (the loss path never forms them).
+        Like the reference, the scale is multiplied into the LEFT operand and rounded to the feature dtype before the
+        contraction (loss.py:92-99); the contraction runs on the tcgen05 GEMM kernel with fp32
+        accumulators and the result is rounded to the feature dtype (bf16 in -> bf16 out, as torch's matmul).
+        The three cases of the reference: world 1 -> (s A) B^T and (s B) A^T; sharded global -> Z and Z.T on the
+        gathered operands; sharded local -> this rank's rows against the gathered other side."""
         K = _KERNELS
         A, B = modality_features, sequence_features
         if self.world_size > 1:
             A_all, B_all = gather_features(A, B, self.local_loss, self.gather_with_grad, self.rank, self.world_size,
                                            self.use_horovod)
-        else:
-            A_all, B_all = A, B
 
         def mm(x, y):
-            xo, _, _ = _prep_side(x, 0)
+            xs = (logit_scale * x).to(x.dtype)           # scale-then-round, the reference's operator precedence
+            xo, _, _ = _prep_side(xs, 0)
             yo, _, _ = _prep_side(y, 1)
             M, Nc, Kd = xo.shape[0], yo.shape[0], xo.shape[1]
             ld = (Nc + 7) // 8 * 8
             out = torch.empty(M, ld, dtype=torch.float32, device=x.device)[:, :Nc]
             K.gemm_bf16(xo, False, yo, False, M, Nc, Kd, acc_out=out)
-            sc = logit_scale.to(device=x.device, dtype=torch.float32) if torch.is_tensor(logit_scale) else float(logit_scale)
-            return (out * sc).to(x.dtype)
+            return out.to(x.dtype)
 
         with torch.no_grad():
             if self.world_size > 1 and self.local_loss:
                 return mm(A, B_all), mm(B, A_all)
-            z = mm(A_all, B_all)
-            return z, z.T
+            if self.world_size > 1:
+                z = mm(A_all, B_all)
+                return z, z.T
+            return mm(A, B), mm(B, A)
 
     def forward(self, modality_features, sequence_features, logit_scale=1.0, output_dict=False):
         A, B = modality_features, sequence_features

@@ -282,3 +282,56 @@ def siglip_closed_form(A_all: np.ndarray, B_all: np.ndarray, scale: float, bias:
     dZ = dZ * np.repeat(g, n)[:, None]
     return SigLipResult(loss=float(lossmat[rows].sum() / n), dA=scale * (dZ[rows] @ B_all), dB=scale * (dZ[:, rows].T @ A_all),
                         dscale=float((dZ[rows] * (A_all[rows] @ B_all.T)).sum()), dbias=float(dZ[rows].sum()))
+
+
+# ----------------------------------------------------------------------------------------------
+# all ranks at once (torch float64, any device): the same closed form as clip_loss_closed_form, arranged so that the
+# N x N matrices are formed once for all W ranks - for the multi-GPU parity tests at sizes where W x 4 numpy passes
+# over N x N doubles would take minutes (N = 16384: the 8-rank fused-gather shape).  Pinned against
+# clip_loss_closed_form rank by rank in tests/test_oracle_golden.py.
+# ----------------------------------------------------------------------------------------------
+def clip_all_ranks_closed_form(A_all, B_all, scale: float, *, world_size: int, local_loss: bool, gather_with_grad: bool,
+                               grad_outputs=None, device="cpu"):
+    """-> dict(loss[W], dA[N, d], dB[N, d], dscale[W]) in float64 torch tensors (rows of rank r: [r n, (r + 1) n)).
+    Conventions: see clip_loss_closed_form (loss.py:19-46, 85-114)."""
+    import torch
+    A = torch.as_tensor(A_all).to(device=device, dtype=torch.float64)
+    B = torch.as_tensor(B_all).to(device=device, dtype=torch.float64)
+    N, W = A.shape[0], int(world_size)
+    n = N // W
+    g = torch.ones(W, dtype=torch.float64, device=device) if grad_outputs is None else torch.as_tensor(grad_outputs).to(device=device, dtype=torch.float64)
+    s = float(scale)
+    dot = A @ B.T
+    Z = s * dot
+    rl = torch.logsumexp(Z, dim=1)
+    cl = torch.logsumexp(Z, dim=0)
+    diag = torch.diagonal(Z).clone()
+    P = torch.exp(Z - rl[:, None])
+    Q = torch.exp(Z - cl[None, :])
+    idx = torch.arange(N, device=device)
+    P[idx, idx] -= 1.0                        # P - I
+    Q[idx, idx] -= 1.0                        # Q - I
+    go = g.repeat_interleave(n)               # upstream gradient of the rank owning each row / column
+    if W == 1 or not local_loss:
+        Lg = 0.5 * ((rl - diag).mean() + (cl - diag).mean())
+        loss = Lg.repeat(W)
+        dZ = (P + Q) / (2 * N)                                   # dL_g / dZ
+        unit_ds = (dZ * dot).sum()
+        dA_u, dB_u = s * (dZ @ B), s * (dZ.T @ A)
+        w = g.sum().repeat(N) if (W > 1 and gather_with_grad) else go
+        dA, dB = w[:, None] * dA_u, w[:, None] * dB_u
+        dscale = g * unit_ds
+    else:
+        per_row = 0.5 * ((rl - diag) + (cl - diag))
+        loss = per_row.view(W, n).mean(dim=1)
+        if gather_with_grad:
+            gz = (go[:, None] * P + go[None, :] * Q) / (2 * n)
+            dA, dB = s * (gz @ B), s * (gz.T @ A)
+        else:                                                      # query side only
+            dA = s * ((go[:, None] * P / (2 * n)) @ B)
+            dB = s * ((go[None, :] * Q / (2 * n)).T @ A)
+        # d value_r / d scale: rows of rank r through P, columns of rank r through Q
+        rows_p = (P * dot).sum(dim=1).view(W, n).sum(dim=1)
+        cols_q = (Q * dot).sum(dim=0).view(W, n).sum(dim=1)
+        dscale = g * (rows_p + cols_q) / (2 * n)
+    return dict(loss=loss, dA=dA, dB=dB, dscale=dscale)

@@ -1,0 +1,371 @@
+"""GPU parity on the code paths that produce the headline numbers and on the BASELINE.json configurations that round 1
+never ran on hardware ("missing" 2, 3, 5, 6):
+
+  * single GPU, N = 32768 x 1024 (the metric's own size) against the reference op sequence run eagerly in fp32 on the
+    same GPU (the unmodified ClipLoss from oracle/_ref when present, else the oracle port);
+  * gather_features (loss.py:19-46, all three branches) and get_logits (loss.py:85-101) against the reference;
+  * all ranks of the box (8 on the driver's scaling box): the fused in-kernel all-gather with 8 row chunks
+    (n % 2048 == 0) + side-stream pull-reduce, every (local_loss, gather_with_grad) convention, unequal upstream
+    gradients, both parities of the double-buffered workspace, Python host and C step sequencer - against the
+    float64 closed form of all ranks (oracle.clip_oracle.clip_all_ranks_closed_form);
+  * BASELINE cfg 3: (A_m, B_m) pairs of 1024 rows per GPU x 1024, the shipped mode local_loss=True,
+    gather_with_grad=True (configs/model/oneprot.yaml:11-12), one after the other as training_step does
+    (oneprot_module.py:92-108);
+  * BASELINE cfg 4: N = 65536 x 1024 over 8 GPUs (n = 8192): loss against a chunked fp32 -> float64 log-sum-exp,
+    sampled gradient rows against the float64 closed form of those rows, and the checksum identity
+    sum_i <a_i, dA_i> = sum_j <b_j, dB_j> (both equal s * d logit_scale * W).
+
+The multi-rank cases share ONE spawn of the ranks (process start-up dominates their cost)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle as oc
+from tests.helpers import cosine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+BF16_LOSS_RTOL = 1e-3      # BASELINE.json north_star
+GRAD_COS = 0.9999
+CONV = ((False, False), (False, True), (True, False), (True, True))
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# single GPU
+# ------------------------------------------------------------------------------------------------------------
+def test_metric_size_single_gpu_against_eager_fp32_reference():
+    """N = 32768 x 1024 bf16-valued inputs: loss and both gradients of the fused path against the reference op
+    sequence in fp32 (TF32 off) with the 4 GiB logit matrices materialised, on the same GPU."""
+    from oneprot_b200 import ClipLoss
+    from oracle.eager_bar import reference_loss_fn
+    from tools.synthetic import synthetic_global_rows
+    N, d = 32768, 1024
+    a, b = synthetic_global_rows(0, N, d, seed=1234)
+    A = a.cuda().requires_grad_(True)
+    B = b.cuda().requires_grad_(True)
+    m = ClipLoss(loss_dtype=torch.float32)
+    loss = m(A, B)
+    loss.backward()
+    m.check_last_call()
+    got = (loss.item(), A.grad.float(), B.grad.float())
+    del A, B, loss
+    fn, _ = reference_loss_fn()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        A32 = a.cuda().float().requires_grad_(True)
+        B32 = b.cuda().float().requires_grad_(True)
+        ref = fn(A32, B32, 1.0)
+        ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert rel_err(got[0], ref.item()) < BF16_LOSS_RTOL
+    for g, r in ((got[1], A32.grad), (got[2], B32.grad)):
+        cos = float((g.double() * r.double()).sum() / (g.double().norm() * r.double().norm()))
+        assert cos >= GRAD_COS
+        assert abs(float(g.norm() / r.norm()) - 1) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_get_logits_single_gpu_matches_reference(dtype):
+    """loss.py:98-99: (s A) B^T and (s B) A^T, scale rounded into the left operand first, output in the input dtype."""
+    from oneprot_b200 import ClipLoss
+    from oracle.make_ref import import_reference
+    n, d, s = 300, 136, 1.0 / 0.07
+    a, b = oc.synthetic_pair(n, d, seed=3, temperature_into_b=False, dtype="bf16" if dtype == torch.bfloat16 else "fp32")
+    A, B = a.cuda(), b.cuda()
+    zab, zba = ClipLoss().get_logits(A, B, s)
+    assert zab.shape == (n, n) and zba.shape == (n, n) and zab.dtype == dtype
+    ref = import_reference()
+    if ref is not None:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            rab, rba = ref[0].ClipLoss().get_logits(A, B, s)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+    else:
+        rab, rba = (s * A) @ B.T, (s * B) @ A.T
+    # same rounded operands, fp32 accumulation in both: results differ by the summation order only (fp32: 2^-16 limb
+    # products) - at most one rounding step of the output dtype
+    tol = 2 ** -7 if dtype == torch.bfloat16 else 3e-5
+    for z, r in ((zab, rab), (zba, rba)):
+        assert float((z.double() - r.double()).abs().max()) <= tol * float(r.double().abs().max())
+
+
+# ------------------------------------------------------------------------------------------------------------
+# all ranks of the box, one spawn
+# ------------------------------------------------------------------------------------------------------------
+FUSED_N, FUSED_D = 2048, 64          # 8 row chunks per rank in the fused all-gather (n % 2048 == 0)
+CFG3_N, CFG3_D, CFG3_PAIRS = 1024, 1024, 3
+CFG4_N, CFG4_D = 8192, 1024
+SAMPLE = (0, 1, 127, 128, 4095, 4096, 8190, 8191)      # local rows whose gradients travel back for cfg 4
+
+
+def _worker(rank, world, port, results):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oneprot_b200 import ClipLoss, gather_features
+    from oneprot_b200.clip_loss import _get_comm
+    from oracle.make_ref import import_reference
+    from tools.synthetic import synthetic_global_rows
+    rec = {}
+    gout = 1.0 + 0.25 * rank
+
+    # ---- (1) fused all-gather, 8 chunks: every convention x {python host, C sequencer}, twice (both buffer parities)
+    a, b = oc.synthetic_pair(FUSED_N, FUSED_D, seed=77, rank=rank, temperature_into_b=False)
+    rec["fused_a"], rec["fused_b"] = a.float().numpy(), b.float().numpy()
+    for ll, gwg in CONV:
+        for seq in (False, True):
+            for rep in range(2):
+                A = a.cuda().requires_grad_(True)
+                B = b.cuda().requires_grad_(True)
+                ls = torch.tensor(1.0 / 0.07, device="cuda", requires_grad=not seq)      # the sequencer takes no d scale
+                m = ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world,
+                             loss_dtype=torch.float32, host_sequencer=seq)
+                loss = m(A, B, ls)
+                (loss * gout).backward()
+                torch.cuda.synchronize()
+                m.check_last_call()
+            rec[("fused", ll, gwg, seq)] = dict(loss=loss.item(), dA=A.grad.float().cpu().numpy(), dB=B.grad.float().cpu().numpy(),
+                                               ds=None if seq else ls.grad.item())
+    comm = _get_comm(world, rank, None, torch.device("cuda", rank))
+    rec["provider"] = comm.name
+    rec["fused_chunks"] = next((c for c in (8, 4, 2, 1) if FUSED_N % (c * 256) == 0), 0) if comm.name == "nvls" else 0
+
+    # ---- (2) several forwards before their backwards (the gathered operand of a pending forward is
+    # snapshotted before a later forward may let a peer overwrite it)
+    mods, losses, leaves = [], [], []
+    for k in range(3):
+        ak, bk = oc.synthetic_pair(FUSED_N, FUSED_D, seed=500 + k, rank=rank, temperature_into_b=False)
+        A = ak.cuda().requires_grad_(True)
+        B = bk.cuda().requires_grad_(True)
+        m = ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world, loss_dtype=torch.float32)
+        losses.append(m(A, B, 1.0 / 0.07))
+        leaves.append((A, B))
+        mods.append(m)
+        rec[("pending_in", k)] = (ak.float().numpy(), bk.float().numpy())
+    for k in (2, 0, 1):
+        losses[k].backward()
+    torch.cuda.synchronize()
+    for k in range(3):
+        rec[("pending", k)] = dict(loss=losses[k].item(), dA=leaves[k][0].grad.float().cpu().numpy(), dB=leaves[k][1].grad.float().cpu().numpy())
+
+    # ---- (3) gather_features / get_logits against the reference classes (fp32: exact copies, sums of few terms)
+    ref = import_reference()
+    x = torch.randn(96, 40, generator=torch.Generator().manual_seed(10 + rank)).cuda()
+    y = torch.randn(96, 40, generator=torch.Generator().manual_seed(20 + rank)).cuda()
+    wgt = torch.randn(world * 96, 40, generator=torch.Generator().manual_seed(30 + rank)).cuda()
+    gf = {}
+    for ll, gwg in ((False, True), (False, False), (True, False)):
+        out = []
+        for fn in ([gather_features] + ([ref[0].gather_features] if ref is not None else [])):
+            xm = x.clone().requires_grad_(True)
+            ys = y.clone().requires_grad_(True)
+            am, asq = fn(xm, ys, ll, gwg, rank, world)
+            if am.requires_grad:
+                ((am * wgt).sum() + 2.0 * (asq * wgt).sum()).backward()
+            out.append((am.detach().cpu(), asq.detach().cpu(), None if xm.grad is None else xm.grad.cpu(),
+                        None if ys.grad is None else ys.grad.cpu(), am.requires_grad))
+        gf[(ll, gwg)] = out
+    rec["gather"] = gf
+    rec["gather_x"], rec["gather_w"] = x.cpu(), wgt.cpu()
+    if ref is not None:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        gl = {}
+        for ll in (False, True):
+            ours = ClipLoss(local_loss=ll, gather_with_grad=False, rank=rank, world_size=world).get_logits(x, y, 3.0)
+            theirs = ref[0].ClipLoss(local_loss=ll, gather_with_grad=False, rank=rank, world_size=world).get_logits(x, y, 3.0)
+            gl[ll] = [float((o.double() - t.double()).abs().max() / t.double().abs().max()) for o, t in zip(ours, theirs)] + \
+                     [tuple(o.shape) == tuple(t.shape) for o, t in zip(ours, theirs)]
+        rec["get_logits"] = gl
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+    # ---- (4) BASELINE cfg 3: independent pairs, n = 1024 rows per GPU, shipped mode; one by one and grouped
+    pairs = [synthetic_global_rows(rank * CFG3_N, CFG3_N, CFG3_D, seed=1234, pair_id=p) for p in range(CFG3_PAIRS)]
+    one = []
+    for p, (ap, bp) in enumerate(pairs):
+        A = ap.cuda().requires_grad_(True)
+        B = bp.cuda().requires_grad_(True)
+        m = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world, loss_dtype=torch.float32)
+        loss = m(A, B)
+        loss.backward()
+        one.append(dict(loss=loss.item(), dA=A.grad.float().cpu().numpy() if p == 0 else None,
+                        dB=B.grad.float().cpu().numpy() if p == 0 else None,
+                        dA_sum=float(A.grad.double().sum()), dB_sum=float(B.grad.double().sum())))
+    rec["cfg3"] = one
+
+    # ---- (5) BASELINE cfg 4: N = 65536 (only when the box has 8 GPUs: n = 8192 rows per GPU)
+    if world == 8:
+        a4, b4 = synthetic_global_rows(rank * CFG4_N, CFG4_N, CFG4_D, seed=4321)
+        A = a4.cuda().requires_grad_(True)
+        B = b4.cuda().requires_grad_(True)
+        m = ClipLoss(local_loss=False, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world, loss_dtype=torch.float32)
+        loss = m(A, B)
+        loss.backward()
+        torch.cuda.synchronize()
+        m.check_last_call()
+        idx = torch.tensor(SAMPLE, device="cuda")
+        rec["cfg4"] = dict(loss=loss.item(), dA=A.grad[idx].float().cpu().numpy(), dB=B.grad[idx].float().cpu().numpy(),
+                           a_dA=float((A.detach().double() * A.grad.double()).sum()),
+                           b_dB=float((B.detach().double() * B.grad.double()).sum()))
+    results[rank] = rec
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def ranks():
+    if _ngpu() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = min(_ngpu(), 8)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, 29871, results), nprocs=world, join=True)
+    return world, {r: results[r] for r in range(world)}
+
+
+def _check(got, want_loss, want_dA, want_dB, tag):
+    assert rel_err(got["loss"], want_loss) < BF16_LOSS_RTOL, tag
+    assert cosine(got["dA"], want_dA) >= GRAD_COS and cosine(got["dB"], want_dB) >= GRAD_COS, tag
+    assert abs(np.linalg.norm(got["dA"]) / np.linalg.norm(want_dA) - 1) < 1e-2, tag
+    assert abs(np.linalg.norm(got["dB"]) / np.linalg.norm(want_dB) - 1) < 1e-2, tag
+
+
+def test_fused_all_gather_all_conventions_all_ranks(ranks):
+    world, res = ranks
+    n = FUSED_N
+    A_all = np.concatenate([res[r]["fused_a"] for r in range(world)])
+    B_all = np.concatenate([res[r]["fused_b"] for r in range(world)])
+    g = 1.0 + 0.25 * np.arange(world)
+    assert res[0]["provider"] == "nvls" and res[0]["fused_chunks"] == 8       # the path SCALE measures
+    for ll, gwg in CONV:
+        ref = oc.clip_all_ranks_closed_form(A_all, B_all, 1.0 / 0.07, world_size=world, local_loss=ll, gather_with_grad=gwg,
+                                            grad_outputs=g, device="cuda")
+        dA, dB = ref["dA"].cpu().numpy(), ref["dB"].cpu().numpy()
+        for r in range(world):
+            rows = slice(r * n, (r + 1) * n)
+            for seq in (False, True):
+                got = res[r][("fused", ll, gwg, seq)]
+                _check(got, ref["loss"][r].item(), dA[rows], dB[rows], (r, ll, gwg, seq))
+                if not seq:
+                    want = ref["dscale"][r].item()
+                    assert abs(got["ds"] - want) < 2e-2 * abs(want) + 1e-5, (r, ll, gwg)
+            # same kernels, same arguments, same order: the C sequencer reproduces the Python host bit for bit where it
+            # is eligible (it falls back to the Python host for local_loss without gather_with_grad)
+            assert res[r][("fused", ll, gwg, True)]["loss"] == res[r][("fused", ll, gwg, False)]["loss"]
+
+
+def test_backwards_in_any_order_after_several_forwards(ranks):
+    world, res = ranks
+    n = FUSED_N
+    for k in range(3):
+        A_all = np.concatenate([res[r][("pending_in", k)][0] for r in range(world)])
+        B_all = np.concatenate([res[r][("pending_in", k)][1] for r in range(world)])
+        ref = oc.clip_all_ranks_closed_form(A_all, B_all, 1.0 / 0.07, world_size=world, local_loss=False, gather_with_grad=True,
+                                            device="cuda")
+        dA, dB = ref["dA"].cpu().numpy(), ref["dB"].cpu().numpy()
+        for r in range(world):
+            _check(res[r][("pending", k)], ref["loss"][r].item(), dA[r * n:(r + 1) * n], dB[r * n:(r + 1) * n], (k, r))
+
+
+def test_gather_features_matches_reference_semantics(ranks):
+    world, res = ranks
+    X = torch.cat([res[r]["gather_x"] for r in range(world)])
+    for r in range(world):
+        gf = res[r]["gather"]
+        for (ll, gwg), outs in gf.items():
+            am, asq, gx, gy, req = outs[0]
+            assert torch.equal(am, X)                                             # values: concatenation in rank order
+            rows = slice(r * 96, (r + 1) * 96)
+            if gwg:        # backward = reduce-scatter SUM of every rank's upstream gradient (loss.py:32-33)
+                want = sum(res[q]["gather_w"][rows] for q in range(world))
+                assert torch.allclose(gx, want, rtol=1e-5, atol=1e-5) and torch.allclose(gy, 2.0 * want, rtol=1e-5, atol=1e-5)
+            elif not ll:   # only the local slot carries the gradient (loss.py:39-42)
+                assert torch.equal(gx, res[r]["gather_w"][rows]) and torch.equal(gy, 2.0 * res[r]["gather_w"][rows])
+            else:          # local_loss without gather_with_grad: constants (loss.py:35-38)
+                assert gx is None and gy is None and not req
+            if len(outs) > 1:                                                    # the unmodified reference, same process
+                ram, ras, rgx, rgy, rreq = outs[1]
+                assert torch.equal(am, ram) and torch.equal(asq, ras) and req == rreq
+                assert (gx is None) == (rgx is None)
+                if gx is not None:
+                    assert torch.allclose(gx, rgx, rtol=1e-5, atol=1e-5) and torch.allclose(gy, rgy, rtol=1e-5, atol=1e-5)
+        if "get_logits" in res[r]:
+            for ll, v in res[r]["get_logits"].items():
+                assert v[0] < 3e-5 and v[1] < 3e-5 and v[2] and v[3], (r, ll, v)
+
+
+def test_cfg3_modalities_shipped_mode(ranks):
+    """1024 rows per GPU x 1024, local_loss=True, gather_with_grad=True; pair 0 in full against the closed form, the
+    other pairs by loss and by the sums of their gradients."""
+    from tools.synthetic import synthetic_global_rows
+    world, res = ranks
+    n = CFG3_N
+    for p in range(CFG3_PAIRS):
+        a, b = synthetic_global_rows(0, world * n, CFG3_D, seed=1234, pair_id=p)
+        ref = oc.clip_all_ranks_closed_form(a.double(), b.double(), 1.0, world_size=world, local_loss=True, gather_with_grad=True,
+                                            device="cuda")
+        dA, dB = ref["dA"].cpu().numpy(), ref["dB"].cpu().numpy()
+        for r in range(world):
+            got = res[r]["cfg3"][p]
+            assert rel_err(got["loss"], ref["loss"][r].item()) < BF16_LOSS_RTOL
+            assert abs(got["dA_sum"] - dA[r * n:(r + 1) * n].sum()) <= 2e-2 * np.abs(dA[r * n:(r + 1) * n]).sum() / np.sqrt(n)
+            assert abs(got["dB_sum"] - dB[r * n:(r + 1) * n].sum()) <= 2e-2 * np.abs(dB[r * n:(r + 1) * n]).sum() / np.sqrt(n)
+            if p == 0:
+                _check(got, ref["loss"][r].item(), dA[r * n:(r + 1) * n], dB[r * n:(r + 1) * n], ("cfg3", r))
+
+
+def test_cfg4_global_batch_65536_over_8_gpus(ranks):
+    from tools.synthetic import synthetic_global_rows
+    world, res = ranks
+    if world != 8:
+        pytest.skip("BASELINE cfg 4 is defined on 8 GPUs")
+    n, N, d, s = CFG4_N, 8 * CFG4_N, CFG4_D, 1.0
+    a, b = synthetic_global_rows(0, N, d, seed=4321)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        A, B = a.cuda().float(), b.cuda().float()
+        rl = torch.empty(N, dtype=torch.float64, device="cuda")
+        cl = torch.full((N,), -float("inf"), dtype=torch.float64, device="cuda")
+        diag = (A.double() * B.double()).sum(1) * s
+        for i0 in range(0, N, 4096):                                  # the logit matrix is never whole here either
+            Z = (s * (A[i0:i0 + 4096] @ B.T)).double()
+            rl[i0:i0 + 4096] = torch.logsumexp(Z, dim=1)
+            cl = torch.logaddexp(cl, torch.logsumexp(Z, dim=0))
+        want_loss = float(0.5 * ((rl - diag).mean() + (cl - diag).mean()))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    Ad, Bd = A.double(), B.double()
+    tot_a = tot_b = 0.0
+    for r in range(world):
+        got = res[r]["cfg4"]
+        assert rel_err(got["loss"], want_loss) < BF16_LOSS_RTOL
+        tot_a += got["a_dA"]
+        tot_b += got["b_dB"]
+        gi = torch.tensor([r * n + i for i in SAMPLE], device="cuda")
+        # rows: dA_i = W s sum_j dZ_ij b_j;  columns: dB_j = W s sum_i dZ_ij a_i;  dZ = (P + Q) / (2N) - I / N
+        zi = s * (Ad[gi] @ Bd.T)
+        dz = (torch.exp(zi - rl[gi][:, None]) + torch.exp(zi - cl[None, :])) / (2 * N)
+        dz[torch.arange(len(SAMPLE)), gi] -= 1.0 / N
+        want_dA = (world * s * (dz @ Bd)).cpu().numpy()
+        zj = s * (Ad @ Bd[gi].T)                                     # N x samples: column j of Z
+        dzc = (torch.exp(zj - rl[:, None]) + torch.exp(zj - cl[gi][None, :])) / (2 * N)
+        dzc[gi, torch.arange(len(SAMPLE))] -= 1.0 / N
+        want_dB = (world * s * (dzc.T @ Ad)).cpu().numpy()
+        assert cosine(got["dA"], want_dA) >= GRAD_COS and cosine(got["dB"], want_dB) >= GRAD_COS, r
+        assert abs(np.linalg.norm(got["dA"]) / np.linalg.norm(want_dA) - 1) < 1e-2
+        assert abs(np.linalg.norm(got["dB"]) / np.linalg.norm(want_dB) - 1) < 1e-2
+    assert abs(tot_a - tot_b) <= 2e-3 * abs(tot_a)                    # both are W * s * d L / d logit_scale

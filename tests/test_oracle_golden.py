@@ -159,3 +159,21 @@ def test_epilogue_closed_forms_match_the_vendored_reference():
     sc = be.LearnableLogitScaling(learnable=True)
     y, s = oc.logit_scaling_closed_form(x.numpy(), float(sc.log_logit_scale))
     assert np.allclose(y, sc(x).detach().numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_all_ranks_closed_form_equals_the_per_rank_closed_form(world):
+    rng = np.random.default_rng(world)
+    N, d = 24, 16
+    A = rng.standard_normal((N, d)); A /= np.linalg.norm(A, axis=1, keepdims=True)
+    B = rng.standard_normal((N, d)); B /= np.linalg.norm(B, axis=1, keepdims=True)
+    g = 1.0 + 0.25 * np.arange(world)
+    n = N // world
+    for ll in (False, True):
+        for gwg in (False, True):
+            allr = oc.clip_all_ranks_closed_form(A, B, 7.0, world_size=world, local_loss=ll, gather_with_grad=gwg, grad_outputs=g)
+            for r in range(world):
+                ref = oc.clip_loss_closed_form(A, B, 7.0, rank=r, world_size=world, local_loss=ll, gather_with_grad=gwg, grad_outputs=g)
+                assert abs(allr["loss"][r].item() - ref.loss) < 1e-12 and abs(allr["dscale"][r].item() - ref.dscale) < 1e-12
+                assert np.allclose(allr["dA"][r * n:(r + 1) * n].numpy(), ref.dA, atol=1e-13)
+                assert np.allclose(allr["dB"][r * n:(r + 1) * n].numpy(), ref.dB, atol=1e-13)

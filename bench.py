@@ -39,7 +39,7 @@ DIM = int(os.environ.get("ONEPROT_BENCH_D", 1024))
 METRIC = "cliploss_fwd_bwd_samples_per_s"
 # fp32 global loss of the synthetic pair (tools.synthetic.synthetic_global_rows, seed 1234) measured on 1 x B200; every
 # world size must reproduce it to 1e-6 relative (the row-sharded path computes the same global function)
-EXPECTED_LOSS = {}
+EXPECTED_LOSS = {(32768, 1024): 9.602405548095703}
 UNIT = "samples/s"
 
 

@@ -642,10 +642,12 @@ class ClipLoss(nn.Module):
             xo, _, _ = _prep_side(xs, 0)
             yo, _, _ = _prep_side(y, 1)
             M, Nc, Kd = xo.shape[0], yo.shape[0], xo.shape[1]
-            ld = (Nc + 7) // 8 * 8
-            out = torch.empty(M, ld, dtype=torch.float32, device=x.device)[:, :Nc]
-            K.gemm_bf16(xo, False, yo, False, M, Nc, Kd, acc_out=out)
-            return out.to(x.dtype)
+            ld = (Nc + 7) // 8 * 8                   # the GEMM writes whole 8-column groups: zero rows of y pad the tail
+            if ld != Nc:
+                yo = torch.nn.functional.pad(yo, (0, 0, 0, ld - Nc))
+            out = torch.empty(M, ld, dtype=torch.float32, device=x.device)
+            K.gemm_bf16(xo, False, yo, False, M, ld, Kd, acc_out=out)
+            return out[:, :Nc].to(x.dtype)
 
         with torch.no_grad():
             if self.world_size > 1 and self.local_loss:

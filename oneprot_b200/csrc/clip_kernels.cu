@@ -36,6 +36,8 @@
 #include <atomic>
 #include <algorithm>
 
+#include "row_regs.cuh"
+
 namespace op {
 
 constexpr int BM = 128;            // accumulator rows  (TMEM lanes)
@@ -205,6 +207,7 @@ struct SParams {
   int nI, nJ;      // row blocks (128), column blocks (256)
   int CI;          // row blocks per work item
   int nChunks;     // ceil(nI / CI)
+  int SC;          // chunks per chunk group: consecutive items sweep all column blocks of SC row chunks (L2 locality)
   int grow0;       // global row index of row 0 (diagonal)
   const float* scale;   // device scalar
   const float* stats;   // [maxA2, maxB2]
@@ -248,6 +251,21 @@ __device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int ep
   } while (v != epoch);
 }
 #endif
+
+// Work item -> (logical column block, row chunk).  Items are dealt round-robin to one persistent CTA per SM, so the
+// ~#SM consecutive items in flight at a time should share operands through L2: they cover SC row chunks x
+// (#SM / SC) column blocks - a roughly square super-tile - and the row operand of a chunk group (SC * CI * 128 rows)
+// stays hot while all column blocks sweep past it.  SC = nChunks is the plain column-major order (one column block x
+// all row chunks at a time), which the fused all-gather needs (columns in arrival order).  Measured with ncu on B200,
+// N = 32768 (round 2): the plain order re-streams the whole row operand per wave - 0.97 GB of DRAM reads for 0.13 GB of
+// operands in FWD, 2.49 GB in FWD_E where the streamed panel evicts them, 73 % L2 hit rate, 73 % tensor-pipe activity.
+__device__ __forceinline__ void item_to_jc(const SParams& p, int item, int& jl, int& ch) {
+  const int per_group = p.nJ * p.SC;
+  const int cg = item / per_group, r = item - cg * per_group;
+  const int sc_here = min(p.SC, p.nChunks - cg * p.SC);
+  jl = r / sc_here;
+  ch = cg * p.SC + (r - jl * sc_here);
+}
 
 // logical column-block index -> actual column block: chunk-major (arrival order), own rank first
 __device__ __forceinline__ int map_jb(const SParams& p, int jl) {
@@ -356,7 +374,9 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       PipeState<NS> ps;
       const uint64_t pol_keep = SCfg<EPI>::L2_HINTS ? l2_policy_evict_last() : 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
+        int jl, ch;
+        item_to_jc(p, item, jl, ch);
+        const int jb = map_jb(p, jl);
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
         if (SCfg<EPI>::SUMS && p.ag_src) {
           // columns [256 jb, 256 jb + 256) belong to one chunk of one rank: wait until it has landed
@@ -390,7 +410,8 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int ch = item % p.nChunks;
+        int jl, ch;
+        item_to_jc(p, item, jl, ch);
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
         for (int ib = ch * p.CI; ib < ib1; ++ib) {
           mbar_wait(&s.tail->tempty[acc], acc_phase ^ 1);
@@ -475,7 +496,9 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const bool store_issuer = (q == 0) && (lane == 0);
     const uint64_t pol_stream = SCfg<EPI>::L2_HINTS ? l2_policy_evict_first() : 0;   // the panel is written once, read once later
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int jb = map_jb(p, item / p.nChunks), ch = item % p.nChunks;
+      int jl, ch;
+      item_to_jc(p, item, jl, ch);
+      const int jb = map_jb(p, jl);
       const int ib1 = min(p.nI, (ch + 1) * p.CI);
       const int j0 = jb * BN + h * 128;   // first column this thread sees
       if (SUMS || EPI == EPI_RCMAX || EPI == EPI_RANK) {
@@ -1001,6 +1024,13 @@ void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
   }
   p.CI = std::max(1, best_ci);
   p.nChunks = cdiv(p.nI, p.CI);
+  // chunk group: SC row chunks x (#SM / SC) column blocks in flight at a time, roughly square in operand bytes:
+  // SC * CI * 128 rows = (#SM / SC) * 256 columns
+  int sc = static_cast<int>(std::lround(std::sqrt(2.0 * sms / p.CI)));
+  if (const char* e = getenv("ONEPROT_SC")) {   // A/B knob of round 2 (removed once measured)
+    if (atoi(e) > 0) sc = atoi(e);
+  }
+  p.SC = std::max(1, std::min(sc, p.nChunks));
 }
 
 }  // namespace
@@ -1085,6 +1115,7 @@ int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, i
       return fail(ONEPROT_ERR_ARG, "fwd_sums_ag: null pointer in oneprot_ag_t");
     if (W <= 0 || W > 8 || ag->rank < 0 || ag->rank >= W || rows * W != N || CH <= 0 || rows % (CH * op::BN))
       return fail(ONEPROT_ERR_ARG, "fwd_sums_ag: need N = world * rows_per_rank and rows_per_rank a multiple of chunks * 256");
+    p.SC = p.nChunks;                // the fused all-gather consumes column blocks in arrival order: plain order
     p.ag_src = static_cast<const uint4*>(ag->src);
     p.ag_dst_mc = static_cast<uint4*>(ag->dst_mc);
     p.ag_counters = ag->counters;
@@ -1513,12 +1544,62 @@ int oneprot_sum_f32(const float* v, int count, float* out, void* stream) {
   return ONEPROT_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// one wave of persistent 256-thread blocks: resident blocks per SM from the occupancy API, cached per instantiation
+template <typename Kern>
+int row_grid(Kern kern, int& cache, int rows) {
+  if (!cache) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    cache = nb;
+  }
+  return std::max(1, std::min(cdiv(rows, 8), num_sms() * cache));
+}
+template <bool FP32, int C>
+void launch_l2norm_fwd(const void* x, void* y, float* inv_norm, int rows, int d, const float* scale_dev, float eps, cudaStream_t st) {
+  static int nb = 0;
+  const int blocks = row_grid(op::l2norm_fwd_rows_kernel<FP32, C>, nb, rows);
+  op::l2norm_fwd_rows_kernel<FP32, C><<<blocks, 256, 0, st>>>(x, y, inv_norm, rows, d, scale_dev, eps);
+}
+template <bool FP32, int C>
+void launch_l2norm_bwd(const void* x, const void* gy, const float* inv_norm, void* gx, float* dscale_partial, int rows, int d,
+                       const float* scale_dev, float eps, cudaStream_t st) {
+  static int nb = 0;
+  const int blocks = row_grid(op::l2norm_bwd_rows_kernel<FP32, C>, nb, rows);
+  op::l2norm_bwd_rows_kernel<FP32, C><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
+}
+#define ROW_SWITCH_C(cneed, CALL)                                           \
+  switch (cneed) {                                                          \
+    case 1: CALL(1); break;                                                 \
+    case 2: CALL(2); break;                                                 \
+    case 3: CALL(3); break;                                                 \
+    case 4: CALL(4); break;                                                 \
+    case 5: CALL(5); break;                                                 \
+    case 6: CALL(6); break;                                                 \
+    default: CALL(8); break;                                                \
+  }
+}  // namespace
+
+extern "C" {
+
 int oneprot_l2norm_scale_fwd(const void* x, void* y, float* inv_norm, int rows, int d, int is_fp32,
                              const float* scale_dev, float eps, void* stream) {
   if (!x || !y || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "l2norm_fwd: need d a positive multiple of 8");
   const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_fp32) op::l2norm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, y, inv_norm, rows, d, scale_dev, eps);
+  if (d <= 256 * oprow::MAXC) {        // the row fits the register-resident kernel
+    if (is_fp32) {
+#define ROW_CALL(CC) launch_l2norm_fwd<true, CC>(x, y, inv_norm, rows, d, scale_dev, eps, st)
+      ROW_SWITCH_C(cdiv(d, 256), ROW_CALL)
+#undef ROW_CALL
+    } else {
+#define ROW_CALL(CC) launch_l2norm_fwd<false, CC>(x, y, inv_norm, rows, d, scale_dev, eps, st)
+      ROW_SWITCH_C(cdiv(d, 256), ROW_CALL)
+#undef ROW_CALL
+    }
+  } else if (is_fp32) op::l2norm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, y, inv_norm, rows, d, scale_dev, eps);
   else op::l2norm_fwd_kernel<false><<<blocks, 256, 0, st>>>(x, y, inv_norm, rows, d, scale_dev, eps);
   ++g_launches;
   OP_CUDA(cudaGetLastError());
@@ -1530,7 +1611,17 @@ int oneprot_l2norm_scale_bwd(const void* x, const void* gy, const float* inv_nor
   if (!x || !gy || !inv_norm || !gx || rows <= 0 || d <= 0 || d % 8) return fail(ONEPROT_ERR_ARG, "l2norm_bwd: bad argument");
   const int blocks = std::min(cdiv(rows, 8), num_sms() * 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_fp32) op::l2norm_bwd_kernel<true><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
+  if (d <= 256 * oprow::MAXC) {
+    if (is_fp32) {
+#define ROW_CALL(CC) launch_l2norm_bwd<true, CC>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps, st)
+      ROW_SWITCH_C(cdiv(d, 256), ROW_CALL)
+#undef ROW_CALL
+    } else {
+#define ROW_CALL(CC) launch_l2norm_bwd<false, CC>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps, st)
+      ROW_SWITCH_C(cdiv(d, 256), ROW_CALL)
+#undef ROW_CALL
+    }
+  } else if (is_fp32) op::l2norm_bwd_kernel<true><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
   else op::l2norm_bwd_kernel<false><<<blocks, 256, 0, st>>>(x, gy, inv_norm, gx, dscale_partial, rows, d, scale_dev, eps);
   ++g_launches;
   OP_CUDA(cudaGetLastError());

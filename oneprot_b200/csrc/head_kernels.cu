@@ -23,6 +23,8 @@ void count_launch(int n);
 }  // namespace opint
 #endif
 
+#include "row_regs.cuh"
+
 namespace oph {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -66,93 +68,169 @@ __device__ __forceinline__ void store8(void* base, size_t idx, const float (&f)[
 
 constexpr int LN_MAXC = 8;   // 8 chunks x 32 lanes x 8 elements = rows of up to 2048 elements held in registers
 
-// ---- LayerNorm forward: y = (x - mean) * rstd * gamma + beta, one warp per row, one read of x ----
-template <bool FP32>
-__global__ void layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma, const void* __restrict__ beta,
-                                     void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows, int d,
-                                     float eps) {
+using oprow::Vec8;
+
+// ---- LayerNorm forward: y = (x - mean) * rstd * gamma + beta, one warp per row, one read of x.
+// C = row chunks of 256 elements held in registers (ceil(d / 256) <= C); the loads of a row are all issued first.
+template <bool FP32, int C>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
+                                                            const void* __restrict__ beta, void* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows, int d,
+                                                            float eps) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const float inv_d = 1.f / static_cast<float>(d);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
     const size_t base = static_cast<size_t>(row) * d;
-    float v[LN_MAXC][8];
+    Vec8<FP32> v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) v[c].load(x, base + k);
+    }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
-      const int k = lane * 8 + c * 256;
-      if (k < d) {
-        load8<FP32>(x, base + k, v[c]);
+    for (int c = 0; c < C; ++c) {
+      if (lane * 8 + c * 256 < d) {
+        float f[8];
+        v[c].unpack(f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += v[c][u];
+        for (int u = 0; u < 8; ++u) s += f[u];
       }
     }
     const float mu = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
-      const int k = lane * 8 + c * 256;
-      if (k < d) {
+    for (int c = 0; c < C; ++c) {
+      if (lane * 8 + c * 256 < d) {
+        float f[8];
+        v[c].unpack(f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const float t = v[c][u] - mu; q = fmaf(t, t, q); }
+        for (int u = 0; u < 8; ++u) { const float t = f[u] - mu; q = fmaf(t, t, q); }
       }
     }
     const float rs = rsqrtf(warp_sum(q) * inv_d + eps);     // biased variance, eps inside the root (torch.nn.LayerNorm)
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < C; ++c) {
       const int k = lane * 8 + c * 256;
       if (k < d) {
-        float g[8], b[8], o[8];
+        float f[8], g[8], b[8], o[8];
+        v[c].unpack(f);
         load8<FP32>(gamma, k, g);
         load8<FP32>(beta, k, b);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = fmaf((v[c][u] - mu) * rs, g[u], b[u]);
+        for (int u = 0; u < 8; ++u) o[u] = fmaf((f[u] - mu) * rs, g[u], b[u]);
         store8<FP32>(y, base + k, o);
       }
     }
   }
 }
 
-// ---- LayerNorm backward, row part: gx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = gy * gamma ----
-template <bool FP32>
-__global__ void layernorm_bwd_rows_kernel(const void* __restrict__ x, const void* __restrict__ gy, const void* __restrict__ gamma,
-                                          const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ gx,
-                                          int rows, int d) {
-  const int lane = threadIdx.x & 31;
+// ---- LayerNorm backward in ONE pass over x and gy (3 d bytes per row: read x, read gy, write gx):
+//   gx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = gy * gamma        (row part, one warp per row)
+//   d gamma = sum_rows gy * xhat, d beta = sum_rows gy                         (column part)
+// The column sums of the rows a warp handles live in that warp's PRIVATE slice of shared memory (no atomics: a lane
+// only ever touches its own addresses, rows are dealt to warps in a fixed order), the 8 warps of a block are added in
+// warp order into one partial slot per block, and sum_slots_f32_kernel adds the slots in block order - deterministic.
+// Dynamic shared memory: 8 warps x 2 x C x 256 floats.  gx may be null (only the column part) and so may dg_part.
+#ifdef ONEPROT_KERNEL_EMULATION
+#define HD_DYNAMIC_SMEM(name) static float name[8 * 2 * LN_MAXC * 256]
+#else
+#define HD_DYNAMIC_SMEM(name) extern __shared__ float name[]
+#endif
+template <bool FP32, int C>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ x, const void* __restrict__ gy,
+                                                            const void* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, void* __restrict__ gx,
+                                                            float* __restrict__ dg_part, float* __restrict__ db_part, int ld,
+                                                            int rows, int d) {
+  HD_DYNAMIC_SMEM(acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const float inv_d = 1.f / static_cast<float>(d);
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+  // warp-private accumulators, laid out so that the float4 accesses of a warp are conflict-free:
+  // [warp][dg | db][chunk][half 0 | 1][lane][4]
+  float* my = acc + static_cast<size_t>(warp) * (2 * C * 256);
+  if (dg_part) {
+#pragma unroll
+    for (int i = 0; i < 2 * C * 2; ++i) *reinterpret_cast<float4*>(my + (i * 32 + lane) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int row = blockIdx.x * wpb + warp; row < rows; row += gridDim.x * wpb) {
     const size_t base = static_cast<size_t>(row) * d;
+    Vec8<FP32> vx[C], vg[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) { vx[c].load(x, base + k); vg[c].load(gy, base + k); }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float xh[LN_MAXC][8], g[LN_MAXC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < C; ++c) {
       const int k = lane * 8 + c * 256;
       if (k < d) {
-        float gm[8];
-        load8<FP32>(x, base + k, xh[c]);
-        load8<FP32>(gy, base + k, g[c]);
+        float fx[8], fg[8], gm[8];
+        vx[c].unpack(fx);
+        vg[c].unpack(fg);
         load8<FP32>(gamma, k, gm);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          xh[c][u] = (xh[c][u] - mu) * rs;
-          g[c][u] *= gm[u];
-          s1 += g[c][u];
-          s2 = fmaf(g[c][u], xh[c][u], s2);
+          const float xh = (fx[u] - mu) * rs, g = fg[u] * gm[u];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+        }
+        if (dg_part) {
+          float* pg = my + ((c * 2) * 32 + lane) * 4;
+          float* pb = my + ((C * 2 + c * 2) * 32 + lane) * 4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 ag = *reinterpret_cast<float4*>(pg + h * 128), ab = *reinterpret_cast<float4*>(pb + h * 128);
+            ag.x = fmaf(fg[4 * h + 0], (fx[4 * h + 0] - mu) * rs, ag.x); ab.x += fg[4 * h + 0];
+            ag.y = fmaf(fg[4 * h + 1], (fx[4 * h + 1] - mu) * rs, ag.y); ab.y += fg[4 * h + 1];
+            ag.z = fmaf(fg[4 * h + 2], (fx[4 * h + 2] - mu) * rs, ag.z); ab.z += fg[4 * h + 2];
+            ag.w = fmaf(fg[4 * h + 3], (fx[4 * h + 3] - mu) * rs, ag.w); ab.w += fg[4 * h + 3];
+            *reinterpret_cast<float4*>(pg + h * 128) = ag;
+            *reinterpret_cast<float4*>(pb + h * 128) = ab;
+          }
         }
       }
     }
-    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+    if (gx) {
+      const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
-      const int k = lane * 8 + c * 256;
-      if (k < d) {
-        float o[8];
+      for (int c = 0; c < C; ++c) {
+        const int k = lane * 8 + c * 256;
+        if (k < d) {
+          float fx[8], fg[8], gm[8], o[8];
+          vx[c].unpack(fx);
+          vg[c].unpack(fg);
+          load8<FP32>(gamma, k, gm);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) o[u] = rs * (g[c][u] - c1 - xh[c][u] * c2);
-        store8<FP32>(gx, base + k, o);
+          for (int u = 0; u < 8; ++u) o[u] = rs * (fg[u] * gm[u] - c1 - (fx[u] - mu) * rs * c2);
+          store8<FP32>(gx, base + k, o);
+        }
+      }
+    }
+  }
+  if (dg_part) {
+    __syncthreads();
+    // thread t adds column t of every 256-column chunk over the 8 warps (warp order), one slot per block
+    const int t = threadIdx.x;
+    const int l = t >> 3, u = t & 7;                         // column t of a chunk = lane l, element u
+    const int off = ((u >> 2) * 32 + l) * 4 + (u & 3);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int col = c * 256 + t;
+      if (col < d) {
+        float sg = 0.f, sb = 0.f;
+        for (int w = 0; w < wpb; ++w) {
+          const float* base_w = acc + static_cast<size_t>(w) * (2 * C * 256);
+          sg += base_w[(c * 2) * 128 + off];
+          sb += base_w[(C * 2 + c * 2) * 128 + off];
+        }
+        dg_part[static_cast<size_t>(blockIdx.x) * ld + col] = sg;
+        db_part[static_cast<size_t>(blockIdx.x) * ld + col] = sb;
       }
     }
   }
@@ -342,22 +420,40 @@ __device__ __forceinline__ float gelu_grad_f(float v) {
   return fmaf(v, pdf, cdf);
 }
 
+// 4 independent 16-byte vectors per thread and step: all loads are issued before the first erf (bytes in flight)
 template <bool FP32, bool BWD>
-__global__ void gelu_kernel(const void* __restrict__ x, const void* __restrict__ gy, void* __restrict__ out, size_t total8) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float f[8], o[8];
-    load8<FP32>(x, i * 8, f);
-    if (BWD) {
-      float g[8];
-      load8<FP32>(gy, i * 8, g);
+__global__ void __launch_bounds__(256) gelu_kernel(const void* __restrict__ x, const void* __restrict__ gy, void* __restrict__ out,
+                                                   size_t total8) {
+  constexpr int U = 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i0 < total8; i0 += U * stride) {
+    Vec8<FP32> vx[U], vg[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) o[u] = g[u] * gelu_grad_f(f[u]);
-    } else {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) o[u] = gelu_f(f[u]);
+    for (int j = 0; j < U; ++j) {
+      const size_t i = i0 + j * stride;
+      if (i < total8) {
+        vx[j].load(x, i * 8);
+        if (BWD) vg[j].load(gy, i * 8);
+      }
     }
-    store8<FP32>(out, i * 8, o);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const size_t i = i0 + j * stride;
+      if (i < total8) {
+        float f[8], o[8];
+        vx[j].unpack(f);
+        if (BWD) {
+          float g[8];
+          vg[j].unpack(g);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[u] = g[u] * gelu_grad_f(f[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[u] = gelu_f(f[u]);
+        }
+        store8<FP32>(out, i * 8, o);
+      }
+    }
   }
 }
 
@@ -373,14 +469,27 @@ __global__ void meanpool_fwd_kernel(const void* __restrict__ x, const float* __r
   const int k = blockIdx.y * 256 + lane * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float cnt = 0.f;
-  for (int l = warp; l < L; l += 8) {
-    const float m = mask ? mask[static_cast<size_t>(b) * L + l] : 1.f;
-    cnt += m;
-    if (m != 0.f && k < D) {
-      float f[8];
-      load8<FP32>(x, (static_cast<size_t>(b) * L + l) * D + k, f);
+  // 8 tokens per warp and step: their loads are all issued before the first accumulation (bytes in flight; the tokens
+  // are still added in increasing order, so the result does not depend on the unrolling)
+  constexpr int U = 8;
+  for (int l0 = warp; l0 < L; l0 += 8 * U) {
+    Vec8<FP32> v[U];
+    float m[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = fmaf(m, f[u], acc[u]);
+    for (int j = 0; j < U; ++j) {
+      const int l = l0 + 8 * j;
+      m[j] = (l < L) ? (mask ? mask[static_cast<size_t>(b) * L + l] : 1.f) : 0.f;
+      if (m[j] != 0.f && k < D) v[j].load(x, (static_cast<size_t>(b) * L + l) * D + k);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      cnt += m[j];
+      if (m[j] != 0.f && k < D) {
+        float f[8];
+        v[j].unpack(f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = fmaf(m[j], f[u], acc[u]);
+      }
     }
   }
 #pragma unroll
@@ -533,6 +642,54 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
     if (_e != cudaSuccess) return opint::fail(ONEPROT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// Resident blocks per SM of a row kernel (occupancy API, cached per instantiation): the grid is ONE wave of persistent
+// blocks whose warps stride over the rows, so no tail wave runs at a fraction of the machine.
+template <typename Kern>
+int resident_blocks(Kern kern, int& cache, size_t smem) {
+  if (!cache) {
+    int nb = 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+    cache = nb;
+  }
+  return cache;
+}
+
+template <bool FP32, int C>
+void launch_ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int rows, int d, float eps,
+                   cudaStream_t st) {
+  static int nb = 0;
+  const int blocks = std::min(cdiv(rows, 8), oneprot_num_sms() * resident_blocks(oph::layernorm_fwd_kernel<FP32, C>, nb, 0));
+  oph::layernorm_fwd_kernel<FP32, C><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+}
+
+constexpr int LN_BWD_MAX_BLOCKS_PER_SM = 8;
+inline int ln_bwd_max_blocks(int rows) { return std::max(1, std::min(cdiv(rows, 8), oneprot_num_sms() * LN_BWD_MAX_BLOCKS_PER_SM)); }
+
+// -> number of partial slots written (= blocks) when dgamma is wanted
+template <bool FP32, int C>
+int launch_ln_bwd(const void* x, const void* gy, const void* gamma, const float* mean, const float* rstd, void* gx, float* pg, float* pb,
+                  int ld, int rows, int d, cudaStream_t st) {
+  static int nb = 0;
+  const size_t smem = pg ? sizeof(float) * 8 * 2 * C * 256 : 0;
+  static int nb_nosmem = 0;
+  const int per_sm = std::min(LN_BWD_MAX_BLOCKS_PER_SM, resident_blocks(oph::layernorm_bwd_kernel<FP32, C>, pg ? nb : nb_nosmem, smem));
+  const int blocks = std::max(1, std::min(cdiv(rows, 8), oneprot_num_sms() * per_sm));
+  oph::layernorm_bwd_kernel<FP32, C><<<blocks, 256, smem, st>>>(x, gy, gamma, mean, rstd, gx, pg, pb, ld, rows, d);
+  return blocks;
+}
+
+#define LN_SWITCH_C(cneed, CALL)                                            \
+  switch (cneed) {                                                          \
+    case 1: CALL(1); break;                                                 \
+    case 2: CALL(2); break;                                                 \
+    case 3: CALL(3); break;                                                 \
+    case 4: CALL(4); break;                                                 \
+    case 5: CALL(5); break;                                                 \
+    case 6: CALL(6); break;                                                 \
+    default: CALL(8); break;                                                \
+  }
+
 int ln_row_chunks(int rows, int d) {
   // enough (column tile, row chunk) blocks for ~2 per SM, at least 64 rows per chunk
   const int tiles = cdiv(d, 256);
@@ -556,8 +713,15 @@ int oneprot_layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
   if (d > 256 * oph::LN_MAXC) {       // row does not fit the register-resident kernel
     if (is_fp32) oph::layernorm_fwd_long_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
     else oph::layernorm_fwd_long_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
-  } else if (is_fp32) oph::layernorm_fwd_kernel<true><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
-  else oph::layernorm_fwd_kernel<false><<<blocks, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, d, eps);
+  } else if (is_fp32) {
+#define LN_CALL(CC) launch_ln_fwd<true, CC>(x, gamma, beta, y, mean, rstd, rows, d, eps, st)
+    LN_SWITCH_C(cdiv(d, 256), LN_CALL)
+#undef LN_CALL
+  } else {
+#define LN_CALL(CC) launch_ln_fwd<false, CC>(x, gamma, beta, y, mean, rstd, rows, d, eps, st)
+    LN_SWITCH_C(cdiv(d, 256), LN_CALL)
+#undef LN_CALL
+  }
   HD_CUDA(cudaGetLastError());
   return ONEPROT_OK;
 }
@@ -565,7 +729,8 @@ int oneprot_layernorm_fwd(const void* x, const void* gamma, const void* beta, vo
 size_t oneprot_layernorm_bwd_scratch_bytes(int rows, int d) {
   if (rows <= 0 || d <= 0) return 0;
   const size_t ld = static_cast<size_t>(cdiv(d, 256)) * 256;
-  return 2 * static_cast<size_t>(ln_row_chunks(rows, d)) * ld * sizeof(float);
+  const int slots = d > 256 * oph::LN_MAXC ? ln_row_chunks(rows, d) : ln_bwd_max_blocks(rows);     // one partial slot per block
+  return 2 * static_cast<size_t>(slots) * ld * sizeof(float);
 }
 
 int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, const float* mean, const float* rstd, void* gx,
@@ -579,22 +744,41 @@ int oneprot_layernorm_bwd(const void* x, const void* gy, const void* gamma, cons
     return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: scratch too small");
   if (!al16(x) || !al16(gy) || !al16(gamma) || (gx && !al16(gx))) return opint::fail(ONEPROT_ERR_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
   if (optrace::recording()) optrace::add("layernorm_bwd x=%p gy=%p gamma=%p mean=%p rstd=%p gx=%p dgamma=%p dbeta=%p scratch=%p rows=%d d=%d fp32=%d st=%p", x, gy, gamma, (const void*)mean, (const void*)rstd, gx, (void*)dgamma, (void*)dbeta, scratch, rows, d, is_fp32, stream);
-  opint::count_launch((gx ? 1 : 0) + (dgamma ? 3 : 0));
+  const bool fused = d <= 256 * oph::LN_MAXC;      // one pass over x and gy; longer rows: row kernel + column kernel
+  opint::count_launch(fused ? (dgamma ? 3 : 1) : ((gx ? 1 : 0) + (dgamma ? 3 : 0)));
   if (optrace::dry()) return ONEPROT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ld = cdiv(d, 256) * 256;
+  if (fused) {
+    float* pg = dgamma ? static_cast<float*>(scratch) : nullptr;
+    float* pb = dgamma ? pg + static_cast<size_t>(ln_bwd_max_blocks(rows)) * ld : nullptr;
+    int slots = 0;
+    if (is_fp32) {
+#define LN_CALL(CC) slots = launch_ln_bwd<true, CC>(x, gy, gamma, mean, rstd, gx, pg, pb, ld, rows, d, st)
+      LN_SWITCH_C(cdiv(d, 256), LN_CALL)
+#undef LN_CALL
+    } else {
+#define LN_CALL(CC) slots = launch_ln_bwd<false, CC>(x, gy, gamma, mean, rstd, gx, pg, pb, ld, rows, d, st)
+      LN_SWITCH_C(cdiv(d, 256), LN_CALL)
+#undef LN_CALL
+    }
+    HD_CUDA(cudaGetLastError());
+    if (dgamma) {
+      oph::sum_slots_f32_kernel<<<cdiv(d, 256), 256, 0, st>>>(pg, slots, ld, d, dgamma);
+      oph::sum_slots_f32_kernel<<<cdiv(d, 256), 256, 0, st>>>(pb, slots, ld, d, dbeta);
+      HD_CUDA(cudaGetLastError());
+    }
+    return ONEPROT_OK;
+  }
   if (gx) {
     const int blocks = std::min(cdiv(rows, 8), oneprot_num_sms() * 8);
-    if (d > 256 * oph::LN_MAXC) {
-      if (is_fp32) oph::layernorm_bwd_rows_long_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
-      else oph::layernorm_bwd_rows_long_kernel<false><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
-    } else if (is_fp32) oph::layernorm_bwd_rows_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
-    else oph::layernorm_bwd_rows_kernel<false><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+    if (is_fp32) oph::layernorm_bwd_rows_long_kernel<true><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
+    else oph::layernorm_bwd_rows_long_kernel<false><<<blocks, 256, 0, st>>>(x, gy, gamma, mean, rstd, gx, rows, d);
     HD_CUDA(cudaGetLastError());
   }
   if (dgamma) {
     const int chunks = ln_row_chunks(rows, d);
     const int rpc = cdiv(rows, chunks);
-    const int ld = cdiv(d, 256) * 256;
     float* pg = static_cast<float*>(scratch);
     float* pb = pg + static_cast<size_t>(chunks) * ld;
     const dim3 grid(cdiv(d, 256), chunks);

@@ -367,7 +367,101 @@ __device__ __forceinline__ void store8(void* base, size_t idx, const float (&f)[
   }
 }
 
-// one warp per row; the row is read once (kept in registers for d <= 2048) and written once
+// L2-normalise (+ logit scale), one warp per row.  Register-resident variant (d <= 2048): the row is loaded ONCE in its
+// storage format (oprow::Vec8; all loads of a row issued first) and written once - 2 d bytes per row forward,
+// 3 d backward, the algorithmic minimum.  C = row chunks of 256 elements, ceil(d / 256) <= C.
+template <bool FP32, int C>
+__global__ void __launch_bounds__(256) l2norm_fwd_rows_kernel(const void* __restrict__ x, void* __restrict__ y,
+                                                              float* __restrict__ inv_norm, int rows, int d,
+                                                              const float* __restrict__ scale, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float sc = scale ? *scale : 1.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    oprow::Vec8<FP32> v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) v[c].load(x, base + k);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (lane * 8 + c * 256 < d) {
+        float f[8];
+        v[c].unpack(f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ss = fmaf(f[u], f[u], ss);
+      }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+    const float m = inv * sc;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+        float f[8];
+        v[c].unpack(f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] *= m;
+        store8<FP32>(y, base + k, f);
+      }
+    }
+  }
+}
+
+template <bool FP32, int C>
+__global__ void __launch_bounds__(256) l2norm_bwd_rows_kernel(const void* __restrict__ x, const void* __restrict__ gy,
+                                                              const float* __restrict__ inv_norm, void* __restrict__ gx,
+                                                              float* __restrict__ dscale_partial, int rows, int d,
+                                                              const float* __restrict__ scale, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float sc = scale ? *scale : 1.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = static_cast<size_t>(row) * d;
+    oprow::Vec8<FP32> vx[C], vg[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) { vx[c].load(x, base + k); vg[c].load(gy, base + k); }
+    }
+    const float inv = inv_norm[row];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (lane * 8 + c * 256 < d) {
+        float fx[8], fg[8];
+        vx[c].unpack(fx);
+        vg[c].unpack(fg);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dot = fmaf(fx[u] * inv, fg[u], dot);
+      }
+    }
+    dot = warp_sum(dot);                      // <yhat, gy>
+    if (lane == 0 && dscale_partial) dscale_partial[row] = dot;
+    // below the eps clamp F.normalize is x / eps: the projection term vanishes
+    const bool clamped = inv >= 1.f / eps;
+    const float proj = clamped ? 0.f : dot;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int k = lane * 8 + c * 256;
+      if (k < d) {
+        float fx[8], fg[8], o[8];
+        vx[c].unpack(fx);
+        vg[c].unpack(fg);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = sc * inv * (fg[u] - fx[u] * inv * proj);
+        store8<FP32>(gx, base + k, o);
+      }
+    }
+  }
+}
+
+// rows longer than 2048 elements: same math, the row is re-read from L1 / L2 instead of being held in registers
 template <bool FP32>
 __global__ void l2norm_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, float* __restrict__ inv_norm,
                                   int rows, int d, const float* __restrict__ scale, float eps) {

@@ -45,7 +45,8 @@ if os.path.exists(rep):
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_active.avg",
-            "lts__t_bytes.sum", "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic"]
+            "lts__t_bytes.sum", "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct",
+            "smsp__cycles_elapsed.avg.per_second"]
     idx = [i for i, h in enumerate(hdr) if h in want]
     with open(os.path.join(out, f"{tag}_ncu_raw_summary.csv"), "w", newline="") as f:
         w = csv.writer(f)
@@ -57,6 +58,8 @@ if os.path.exists(rep):
     # per-launch DRAM traffic keyed the way bench.py names the kernels
     names = {"clip_s_kernel<0>": "clip_s_kernel<FWD> (logits + exp-sums)",
              "clip_s_kernel<1>": "clip_s_kernel<DZ> (logits recompute + dL/dZ panel)",
+             "clip_s_kernel<8>": "clip_s_kernel<FWD_E> (logits + exp-sums + kept exponentials)",
+             "dz_from_exp_kernel": "dz_from_exp_kernel (in-place rescale of the kept panel, HBM-bound)",
              "gemm_kernel<0, 1": "gemm_kernel<K,MN> (dA = Wz . B)",
              "gemm_kernel<1, 1": "gemm_kernel<MN,MN> (dB = Wz^T . A)"}
     ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")

@@ -1,6 +1,7 @@
 // Compiles the tensor-core kernels of oneprot_b200/csrc/clip_kernels.cu for the CPU (ptx_emu.h supplies
 // TMA / mbarrier / tcgen05 / TMEM stand-ins) and exposes C entry points that set the kernel parameters up
 // exactly like the CUDA host functions of that file do.  Test infrastructure only.
+#include <cmath>
 #define ONEPROT_KERNEL_EMULATION 1
 #include "../../oneprot_b200/csrc/clip_kernels.cu"
 
@@ -28,6 +29,8 @@ void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
   }
   p.CI = std::max(1, best_ci);
   p.nChunks = cdiv(p.nI, p.CI);
+  p.SC = std::max(1, std::min(static_cast<int>(std::lround(std::sqrt(2.0 * g_sms / p.CI))), p.nChunks));   // chunk groups, as the library
+  if (const char* e = getenv("ONEPROT_SC")) { if (atoi(e) > 0) p.SC = std::max(1, std::min(atoi(e), p.nChunks)); }
 }
 
 template <int EPI>

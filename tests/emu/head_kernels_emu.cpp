@@ -18,36 +18,70 @@ int ln_row_chunks(int rows, int d) {
 
 extern "C" {
 
+#define EMU_SWITCH_C(cneed, CALL)                                           \
+  switch (cneed) {                                                          \
+    case 1: CALL(1); break;                                                 \
+    case 2: CALL(2); break;                                                 \
+    case 3: CALL(3); break;                                                 \
+    case 4: CALL(4); break;                                                 \
+    case 5: CALL(5); break;                                                 \
+    case 6: CALL(6); break;                                                 \
+    default: CALL(8); break;                                                \
+  }
+
 void emu_layernorm_fwd(const void* x, const void* g, const void* b, void* y, float* mean, float* rstd, int rows, int d, int fp32, float eps) {
-  const int blocks = std::min(cdiv(rows, 8), SMS * 8);
+  const int blocks = std::min(cdiv(rows, 8), SMS * 2);
   const bool lng = d > 256 * oph::LN_MAXC;
   emu::launch(dim3(blocks), dim3(256), [&] {
     if (lng) { if (fp32) oph::layernorm_fwd_long_kernel<true>(x, g, b, y, mean, rstd, rows, d, eps); else oph::layernorm_fwd_long_kernel<false>(x, g, b, y, mean, rstd, rows, d, eps); }
-    else if (fp32) oph::layernorm_fwd_kernel<true>(x, g, b, y, mean, rstd, rows, d, eps);
-    else oph::layernorm_fwd_kernel<false>(x, g, b, y, mean, rstd, rows, d, eps);
+    else if (fp32) {
+#define EMU_CALL(CC) oph::layernorm_fwd_kernel<true, CC>(x, g, b, y, mean, rstd, rows, d, eps)
+      EMU_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+    } else {
+#define EMU_CALL(CC) oph::layernorm_fwd_kernel<false, CC>(x, g, b, y, mean, rstd, rows, d, eps)
+      EMU_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+    }
   });
 }
 
+int emu_ln_slots(int rows, int d) { return d > 256 * oph::LN_MAXC ? ln_row_chunks(rows, d) : std::max(1, std::min(cdiv(rows, 8), SMS * 2)); }
+
 void emu_layernorm_bwd(const void* x, const void* gy, const void* g, const float* mean, const float* rstd, void* gx, float* dgamma,
                        float* dbeta, float* scratch, int rows, int d, int fp32) {
-  const int blocks = std::min(cdiv(rows, 8), SMS * 8);
   const bool lng = d > 256 * oph::LN_MAXC;
-  emu::launch(dim3(blocks), dim3(256), [&] {
-    if (lng) { if (fp32) oph::layernorm_bwd_rows_long_kernel<true>(x, gy, g, mean, rstd, gx, rows, d); else oph::layernorm_bwd_rows_long_kernel<false>(x, gy, g, mean, rstd, gx, rows, d); }
-    else if (fp32) oph::layernorm_bwd_rows_kernel<true>(x, gy, g, mean, rstd, gx, rows, d);
-    else oph::layernorm_bwd_rows_kernel<false>(x, gy, g, mean, rstd, gx, rows, d);
-  });
-  const int chunks = ln_row_chunks(rows, d), rpc = cdiv(rows, chunks), ld = cdiv(d, 256) * 256;
+  const int ld = cdiv(d, 256) * 256;
+  const int slots = emu_ln_slots(rows, d);
   float* pg = scratch;
-  float* pb = pg + static_cast<size_t>(chunks) * ld;
-  emu::launch(dim3(cdiv(d, 256), chunks), dim3(256), [&] {
-    if (fp32) oph::layernorm_bwd_cols_kernel<true>(x, gy, mean, rstd, rows, d, rpc, pg, pb, ld);
-    else oph::layernorm_bwd_cols_kernel<false>(x, gy, mean, rstd, rows, d, rpc, pg, pb, ld);
-  });
-  emu::launch(dim3(cdiv(d, 256)), dim3(256), [&] { oph::sum_slots_f32_kernel(pg, chunks, ld, d, dgamma); });
-  emu::launch(dim3(cdiv(d, 256)), dim3(256), [&] { oph::sum_slots_f32_kernel(pb, chunks, ld, d, dbeta); });
+  float* pb = pg + static_cast<size_t>(slots) * ld;
+  if (!lng) {        // one fused pass: row part + warp-private column sums, one partial slot per block
+    emu::launch(dim3(slots), dim3(256), [&] {
+      if (fp32) {
+#define EMU_CALL(CC) oph::layernorm_bwd_kernel<true, CC>(x, gy, g, mean, rstd, gx, pg, pb, ld, rows, d)
+        EMU_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+      } else {
+#define EMU_CALL(CC) oph::layernorm_bwd_kernel<false, CC>(x, gy, g, mean, rstd, gx, pg, pb, ld, rows, d)
+        EMU_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+      }
+    });
+  } else {
+    const int blocks = std::min(cdiv(rows, 8), SMS * 8);
+    emu::launch(dim3(blocks), dim3(256), [&] {
+      if (fp32) oph::layernorm_bwd_rows_long_kernel<true>(x, gy, g, mean, rstd, gx, rows, d); else oph::layernorm_bwd_rows_long_kernel<false>(x, gy, g, mean, rstd, gx, rows, d);
+    });
+    const int rpc = cdiv(rows, slots);
+    emu::launch(dim3(cdiv(d, 256), slots), dim3(256), [&] {
+      if (fp32) oph::layernorm_bwd_cols_kernel<true>(x, gy, mean, rstd, rows, d, rpc, pg, pb, ld);
+      else oph::layernorm_bwd_cols_kernel<false>(x, gy, mean, rstd, rows, d, rpc, pg, pb, ld);
+    });
+  }
+  emu::launch(dim3(cdiv(d, 256)), dim3(256), [&] { oph::sum_slots_f32_kernel(pg, slots, ld, d, dgamma); });
+  emu::launch(dim3(cdiv(d, 256)), dim3(256), [&] { oph::sum_slots_f32_kernel(pb, slots, ld, d, dbeta); });
 }
-int emu_ln_scratch_floats(int rows, int d) { return 2 * ln_row_chunks(rows, d) * cdiv(d, 256) * 256; }
+int emu_ln_scratch_floats(int rows, int d) { return 2 * emu_ln_slots(rows, d) * cdiv(d, 256) * 256; }
 
 void emu_gelu(const void* x, const void* gy, void* out, size_t count, int fp32) {
   const size_t total8 = count / 8;

@@ -37,6 +37,7 @@ inline cudaError_t get_props(cudaDeviceProp* p, int) { std::memset(p, 0, sizeof(
 #define cudaGetLastError() cudaSuccess
 #define cudaGetErrorString(e) "emulated CUDA call"
 #define cudaFuncSetAttribute(k, a, v) emu::ok((void*)(k), (a), (v))
+#define cudaOccupancyMaxActiveBlocksPerMultiprocessor(p, k, t, s) (*(p) = 2, (void)(k), cudaSuccess)
 #define cudaGetDevice(p) emu::get_device(p)
 #define cudaDeviceGetAttribute(p, a, d) emu::get_attr((p), (a), (d))
 #define cudaGetDeviceProperties(p, d) emu::get_props((p), (d))

@@ -2,6 +2,7 @@
 // CPU through tests/emu/cuda_emu.h, with the launch shapes of the CUDA host code.  Test infrastructure only.
 #include "cuda_emu.h"
 #include "../../include/oneprot_clip.h"
+#include "../../oneprot_b200/csrc/row_regs.cuh"
 
 namespace op {
 constexpr float LOG2E = 1.4426950408889634f;
@@ -68,14 +69,44 @@ void emu_rowdot_bf16(const void* x, int ldx, const void* y, int ldy, int rows, i
 void emu_sum_f32(const float* v, int count, float* out) {
   emu::launch(dim3(1), dim3(1024), [&] { op::sum_kernel(v, count, out); });
 }
+#define EMU_ROW_SWITCH_C(cneed, CALL)                                       \
+  switch (cneed) {                                                          \
+    case 1: CALL(1); break;                                                 \
+    case 2: CALL(2); break;                                                 \
+    case 3: CALL(3); break;                                                 \
+    case 4: CALL(4); break;                                                 \
+    case 5: CALL(5); break;                                                 \
+    case 6: CALL(6); break;                                                 \
+    default: CALL(8); break;                                                \
+  }
 void emu_l2norm_fwd(const void* x, void* y, float* inv, int rows, int d, int fp32, const float* scale, float eps) {
-  emu::launch(dim3(std::min(cdiv(rows, 8), SMS * 16)), dim3(256), [&] {
-    if (fp32) op::l2norm_fwd_kernel<true>(x, y, inv, rows, d, scale, eps); else op::l2norm_fwd_kernel<false>(x, y, inv, rows, d, scale, eps);
+  const bool lng = d > 256 * oprow::MAXC;          // register-resident rows up to 2048 elements, as the library dispatches
+  emu::launch(dim3(std::min(cdiv(rows, 8), SMS * (lng ? 16 : 2))), dim3(256), [&] {
+    if (lng) { if (fp32) op::l2norm_fwd_kernel<true>(x, y, inv, rows, d, scale, eps); else op::l2norm_fwd_kernel<false>(x, y, inv, rows, d, scale, eps); }
+    else if (fp32) {
+#define EMU_CALL(CC) op::l2norm_fwd_rows_kernel<true, CC>(x, y, inv, rows, d, scale, eps)
+      EMU_ROW_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+    } else {
+#define EMU_CALL(CC) op::l2norm_fwd_rows_kernel<false, CC>(x, y, inv, rows, d, scale, eps)
+      EMU_ROW_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+    }
   });
 }
 void emu_l2norm_bwd(const void* x, const void* gy, const float* inv, void* gx, float* dsp, int rows, int d, int fp32, const float* scale, float eps) {
-  emu::launch(dim3(std::min(cdiv(rows, 8), SMS * 16)), dim3(256), [&] {
-    if (fp32) op::l2norm_bwd_kernel<true>(x, gy, inv, gx, dsp, rows, d, scale, eps); else op::l2norm_bwd_kernel<false>(x, gy, inv, gx, dsp, rows, d, scale, eps);
+  const bool lng = d > 256 * oprow::MAXC;
+  emu::launch(dim3(std::min(cdiv(rows, 8), SMS * (lng ? 16 : 2))), dim3(256), [&] {
+    if (lng) { if (fp32) op::l2norm_bwd_kernel<true>(x, gy, inv, gx, dsp, rows, d, scale, eps); else op::l2norm_bwd_kernel<false>(x, gy, inv, gx, dsp, rows, d, scale, eps); }
+    else if (fp32) {
+#define EMU_CALL(CC) op::l2norm_bwd_rows_kernel<true, CC>(x, gy, inv, gx, dsp, rows, d, scale, eps)
+      EMU_ROW_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+    } else {
+#define EMU_CALL(CC) op::l2norm_bwd_rows_kernel<false, CC>(x, gy, inv, gx, dsp, rows, d, scale, eps)
+      EMU_ROW_SWITCH_C(cdiv(d, 256), EMU_CALL)
+#undef EMU_CALL
+    }
   });
 }
 void emu_scale_rows(const void* x, void* y, int rows, int d, int fp32, const float* scale) {

@@ -259,9 +259,10 @@ def test_siglip_finalize(vec):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_l2norm_scale_and_split(vec, dtype):
+@pytest.mark.parametrize("d", [1024, 72, 1152, 1800, 2560])     # whole chunks, one ragged chunk, 5 / 8 chunks, long rows (re-read)
+def test_l2norm_scale_and_split(vec, dtype, d):
     rng = np.random.default_rng(6)
-    rows, d = 37, 1024
+    rows = 37
     x, xv = _t(3 * rng.standard_normal((rows, d)), dtype)
     x[5] = 0
     xv[5] = 0
@@ -317,10 +318,12 @@ def _unit(rng, n, d, scale=1.0):
 SHAPES = [(300, 300, 72, 0), (256, 512, 128, 256), (130, 700, 64, 400)]       # (n, N, d, row offset): ragged tiles, K tails, panels
 
 
-@pytest.mark.parametrize("n,N,d,off", SHAPES)
-@pytest.mark.parametrize("sms", [3, 1])
-def test_emulated_forward_sums(tc, n, N, d, off, sms):
+@pytest.mark.parametrize("n,N,d,off,sms,sc", [(*sh, sms, 0) for sh in SHAPES for sms in (3, 1)] +
+                         [(640, 512, 64, 0, 3, 2), (900, 300, 64, 0, 2, 3)])    # chunk groups: 2 of 3 (5) row chunks per group
+def test_emulated_forward_sums(tc, n, N, d, off, sms, sc, monkeypatch):
     tc.emu_set_sms(sms)
+    if sc:
+        monkeypatch.setenv("ONEPROT_SC", str(sc))
     rng = np.random.default_rng(n + N)
     A, Av = _unit(rng, n, d)
     B, Bv = _unit(rng, N, d, 1 / 0.07)
@@ -338,7 +341,7 @@ def test_emulated_forward_sums(tc, n, N, d, off, sms):
     scratch.zero_()
     tc.emu_fwd_sums(_p(A), _p(B), n, N, d, _p(scale), _p(stats), _p(rs2), _p(cs2), _p(scratch), _p(kept), ld)
     assert torch.equal(rs2, rowsum) and torch.equal(cs2, colsum)
-    assert torch.all(kept[n:] == 7.0) and torch.all(kept[:, N:] == 7.0)
+    assert torch.all(kept[n:] == 7.0) and torch.all(kept[:, (N + 7) // 8 * 8:] == 7.0)     # rows clipped exactly, columns in 16-byte chunks
     assert np.abs(kept[:n, :N].float().numpy() / E - 1).max() < 2 ** -8 + 1e-5
 
 
@@ -387,7 +390,7 @@ def test_emulated_panel_kernels(tc, rows, N, d, grow0, variant, sms):
     want[idx, grow0 + idx] -= dg.double().numpy()
     got = Wz.double().numpy()
     assert np.allclose(got[:, :N], want, rtol=2.0 ** -7, atol=1e-6)            # bf16 storage
-    assert np.all(got[:, N:] == 7.0)                                           # TMA stores clip the columns beyond N
+    assert np.all(got[:, (N + 7) // 8 * 8:] == 7.0)                            # TMA stores clip whole 16-byte chunks beyond N
 
 
 @pytest.mark.parametrize("n,N,d", [(300, 300, 72), (256, 512, 128)])

@@ -63,6 +63,23 @@ def main():
                 ms = timed(fn, flush)
                 gbs = nbytes / (ms * 1e-3) / 1e9
                 res["kernels"][f"{name} {str(dt).split('.')[-1]}"] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": gbs, "frac": gbs / peak}
+        # the epilogue in front of the loss: L2-normalise (+ logit scale) and the plain scale, d = 1024
+        d = 1024
+        x = torch.randn(rows, d, device=dev).to(dt)
+        gy = torch.randn(rows, d, device=dev).to(dt)
+        y = torch.empty_like(x); gx = torch.empty_like(x)
+        inv = torch.empty(rows, device=dev); dsp = torch.empty(rows, device=dev)
+        sc = torch.full((1,), 1 / 0.07, device=dev)
+        K.l2norm_scale_fwd(x, y, inv, sc)
+        cases = {
+            f"l2norm_scale_fwd d={d}": (lambda: K.l2norm_scale_fwd(x, y, inv, sc), 2 * rows * d * esz),
+            f"l2norm_scale_bwd d={d}": (lambda: K.l2norm_scale_bwd(x, gy, inv, gx, dsp, sc), 3 * rows * d * esz),
+            f"scale_rows d={d}": (lambda: K.scale_rows(x, y, sc), 2 * rows * d * esz),
+        }
+        for name, (fn, nbytes) in cases.items():
+            ms = timed(fn, flush)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res["kernels"][f"{name} {str(dt).split('.')[-1]}"] = {"ms": ms, "algorithmic_bytes": nbytes, "gbs": gbs, "frac": gbs / peak}
         Bt, L, D = 64, 1024, 1280
         f = torch.randn(Bt, L, D, device=dev).to(dt)
         mask = (torch.arange(L, device=dev)[None, :] < torch.randint(L // 2, L + 1, (Bt, 1), device=dev)).float()

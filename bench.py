@@ -581,6 +581,109 @@ def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, keep, reps=5)
     return {"kernels": out}
 
 
+# ----------------------------------------------------------------------------------------------
+# second configuration: BASELINE.json configs[2] - the sequence anchor against 5 modalities, 1024 rows per GPU
+# ----------------------------------------------------------------------------------------------
+def run_modalities5(args):
+    """`--config modalities5`: five independent (A_m, B_m) pairs of 1024 rows per GPU x 1024 bf16, the SHIPPED mode
+    ClipLoss(local_loss=True, gather_with_grad=True) (configs/model/oneprot.yaml:11-12), one fwd+bwd per pair in
+    sequence like the reference's training_step (oneprot_module.py:92-108; its optimizer step between the pairs is
+    what forbids a grouped launch there).  ~50 us of math per pair and rank: the regime is launch / exchange bound.
+    One step = the 5 pairs.  Prints one JSON line: samples/s over all pairs and GPUs, us per pair, and (baseline leg)
+    the unmodified reference ClipLoss run eagerly over NCCL on the same ranks and inputs."""
+    import torch
+    import torch.distributed as dist
+    from oneprot_b200 import ClipLoss, kernels
+    from tools.synthetic import synthetic_global_rows
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, P = 1024, DIM, 5
+    N = n * world
+    pairs = [synthetic_global_rows(rank * n, n, d, seed=1234, pair_id=p) for p in range(P)]
+    As = [a.to(dev).requires_grad_(True) for a, _ in pairs]
+    Bs = [b.to(dev).requires_grad_(True) for _, b in pairs]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps, warmup = max(1, args.steps), max(3, args.warmup) * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_step(loss_fn):
+        def step():
+            out = None
+            for A, B in zip(As, Bs):
+                A.grad = None; B.grad = None
+                out = loss_fn(A, B)
+                out.backward()
+            return out
+        return step
+
+    def measure(step):
+        gc.collect()
+        barrier()
+        for _ in range(warmup):
+            step()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item())
+
+    variants = {}
+    mk = lambda **kw: ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world, **kw)   # noqa: E731
+    mods = {"python host": mk(host_sequencer=False), "C step sequencer": mk(host_sequencer=True)}
+    if world == 1:
+        mods["CUDA graph replay"] = mk(graph=True)
+    kernels.launch_count_reset()
+    for name, m in mods.items():
+        variants[name] = measure(make_step(m))
+    launches = kernels.launch_count()
+    loss_val = float(next(iter(mods.values())).last_loss_fp32.item())
+    best = min(variants, key=variants.get)
+    ms = variants[best]
+    line = {"metric": METRIC, "value": P * N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"ClipLoss fwd+bwd, {P} modality pairs in sequence, {n} rows per GPU x {d} bf16 (global {N}), "
+                                   "local_loss=True, gather_with_grad=True (BASELINE configs[2])",
+                       "pairs": P, "rows_per_gpu": n, "global_batch": N, "dim": d, "us_per_pair": 1e3 * ms / P, "host": best,
+                       "ms_per_step_by_host": variants, "loss_last_pair_rank0": loss_val,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)"},
+            "gpu_launches": launches}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle.make_ref import import_reference
+            ref = import_reference()
+            if ref is None:
+                raise RuntimeError("oracle/_ref not built")
+            rm = ref[0].ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+            t_ref = measure(make_step(lambda A, B: rm(A, B, 1.0)))
+            line["eager_b200"] = {"impl": "reference (oracle/_ref, unmodified loss.py) eager over NCCL", "ms_per_step": t_ref,
+                                  "us_per_pair": 1e3 * t_ref / P, "value": P * N / (t_ref * 1e-3), "speedup": t_ref / ms}
+        except Exception as e:
+            line["eager_b200"] = {"unavailable": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -588,9 +691,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="metric", choices=["metric", "modalities5"],
+                    help="metric: BASELINE.json's headline (global 32768 x 1024); modalities5: configs[2], 5 pairs x 1024 rows per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "modalities5":
+        run_modalities5(args)
     else:
         run_ours(args)
 

@@ -207,7 +207,6 @@ struct SParams {
   int nI, nJ;      // row blocks (128), column blocks (256)
   int CI;          // row blocks per work item
   int nChunks;     // ceil(nI / CI)
-  int SC;          // chunks per chunk group: consecutive items sweep all column blocks of SC row chunks (L2 locality)
   int grow0;       // global row index of row 0 (diagonal)
   const float* scale;   // device scalar
   const float* stats;   // [maxA2, maxB2]
@@ -252,19 +251,15 @@ __device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int ep
 }
 #endif
 
-// Work item -> (logical column block, row chunk).  Items are dealt round-robin to one persistent CTA per SM, so the
-// ~#SM consecutive items in flight at a time should share operands through L2: they cover SC row chunks x
-// (#SM / SC) column blocks - a roughly square super-tile - and the row operand of a chunk group (SC * CI * 128 rows)
-// stays hot while all column blocks sweep past it.  SC = nChunks is the plain column-major order (one column block x
-// all row chunks at a time), which the fused all-gather needs (columns in arrival order).  Measured with ncu on B200,
-// N = 32768 (round 2): the plain order re-streams the whole row operand per wave - 0.97 GB of DRAM reads for 0.13 GB of
-// operands in FWD, 2.49 GB in FWD_E where the streamed panel evicts them, 73 % L2 hit rate, 73 % tensor-pipe activity.
+// Work item -> (logical column block, row chunk): column-major - the ~#SM items in flight cover ~#SM / nChunks column
+// blocks x ALL row chunks, so every row-operand tile is shared by ~9 CTAs at a time (N = 32768).  A "square" order
+// (SC row chunks x #SM / SC column blocks per wave, to keep a smaller working set hot in L2) was measured on B200 in
+// round 2 and is monotonically SLOWER the more CTAs share a row tile: FWD_E 1.745 / 1.785 / 1.828 / 1.875 / 1.908 ms for
+// 9 / 18 / 37 / 74 / 148 sharers, FWD and DZ alike - although ncu shows the plain order re-streaming the row operand
+// once per wave (0.97 GB of DRAM reads for 0.13 GB of operands).  DRAM is not the limiter; lock-step sharers are.
 __device__ __forceinline__ void item_to_jc(const SParams& p, int item, int& jl, int& ch) {
-  const int per_group = p.nJ * p.SC;
-  const int cg = item / per_group, r = item - cg * per_group;
-  const int sc_here = min(p.SC, p.nChunks - cg * p.SC);
-  jl = r / sc_here;
-  ch = cg * p.SC + (r - jl * sc_here);
+  jl = item / p.nChunks;
+  ch = item - jl * p.nChunks;
 }
 
 // logical column-block index -> actual column block: chunk-major (arrival order), own rank first
@@ -1024,13 +1019,6 @@ void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
   }
   p.CI = std::max(1, best_ci);
   p.nChunks = cdiv(p.nI, p.CI);
-  // chunk group: SC row chunks x (#SM / SC) column blocks in flight at a time, roughly square in operand bytes:
-  // SC * CI * 128 rows = (#SM / SC) * 256 columns
-  int sc = static_cast<int>(std::lround(std::sqrt(2.0 * sms / p.CI)));
-  if (const char* e = getenv("ONEPROT_SC")) {   // A/B knob of round 2 (removed once measured)
-    if (atoi(e) > 0) sc = atoi(e);
-  }
-  p.SC = std::max(1, std::min(sc, p.nChunks));
 }
 
 }  // namespace
@@ -1115,7 +1103,6 @@ int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, i
       return fail(ONEPROT_ERR_ARG, "fwd_sums_ag: null pointer in oneprot_ag_t");
     if (W <= 0 || W > 8 || ag->rank < 0 || ag->rank >= W || rows * W != N || CH <= 0 || rows % (CH * op::BN))
       return fail(ONEPROT_ERR_ARG, "fwd_sums_ag: need N = world * rows_per_rank and rows_per_rank a multiple of chunks * 256");
-    p.SC = p.nChunks;                // the fused all-gather consumes column blocks in arrival order: plain order
     p.ag_src = static_cast<const uint4*>(ag->src);
     p.ag_dst_mc = static_cast<uint4*>(ag->dst_mc);
     p.ag_counters = ag->counters;

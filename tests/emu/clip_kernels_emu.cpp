@@ -29,8 +29,6 @@ void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
   }
   p.CI = std::max(1, best_ci);
   p.nChunks = cdiv(p.nI, p.CI);
-  p.SC = std::max(1, std::min(static_cast<int>(std::lround(std::sqrt(2.0 * g_sms / p.CI))), p.nChunks));   // chunk groups, as the library
-  if (const char* e = getenv("ONEPROT_SC")) { if (atoi(e) > 0) p.SC = std::max(1, std::min(atoi(e), p.nChunks)); }
 }
 
 template <int EPI>

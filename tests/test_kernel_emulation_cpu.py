@@ -318,12 +318,9 @@ def _unit(rng, n, d, scale=1.0):
 SHAPES = [(300, 300, 72, 0), (256, 512, 128, 256), (130, 700, 64, 400)]       # (n, N, d, row offset): ragged tiles, K tails, panels
 
 
-@pytest.mark.parametrize("n,N,d,off,sms,sc", [(*sh, sms, 0) for sh in SHAPES for sms in (3, 1)] +
-                         [(640, 512, 64, 0, 3, 2), (900, 300, 64, 0, 2, 3)])    # chunk groups: 2 of 3 (5) row chunks per group
-def test_emulated_forward_sums(tc, n, N, d, off, sms, sc, monkeypatch):
+@pytest.mark.parametrize("n,N,d,off,sms", [(*sh, sms) for sh in SHAPES for sms in (3, 1)] + [(640, 512, 64, 0, 3)])   # + 3 row chunks
+def test_emulated_forward_sums(tc, n, N, d, off, sms):
     tc.emu_set_sms(sms)
-    if sc:
-        monkeypatch.setenv("ONEPROT_SC", str(sc))
     rng = np.random.default_rng(n + N)
     A, Av = _unit(rng, n, d)
     B, Bv = _unit(rng, N, d, 1 / 0.07)

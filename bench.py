@@ -285,7 +285,10 @@ def run_ours(args):
     a_pin, b_pin = a.pin_memory(), b.pin_memory()
     A = a.to(dev).requires_grad_(True)
     B = b.to(dev).requires_grad_(True)
-    loss_mod = ClipLoss(local_loss=False, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    # ONEPROT_BENCH_HOST=python: A/B switch of this bench only (the library default is the C step sequencer)
+    py_host = os.environ.get("ONEPROT_BENCH_HOST") == "python"
+    loss_mod = ClipLoss(local_loss=False, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world,
+                        host_sequencer=not py_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 2x the 126 MB L2
 
     def barrier():
@@ -418,7 +421,7 @@ def run_ours(args):
                                      "last10_ms_per_step": sus_last10_ms, "value": GLOBAL_N / (sus_ms * 1e-3),
                                      "frac_of_burst_peak": 6.0 * GLOBAL_N * GLOBAL_N * DIM / world / (sus_ms * 1e-3) / 1e12 / _peaks()["bf16_tflops"]},
                        "backward": "stored exponentials (keep_exp)" if loss_mod.keep_exp else "recompute",
-                       "host": "C step sequencer (ONEPROT_SEQ=1)" if os.environ.get("ONEPROT_SEQ") == "1" else "python",
+                       "host": "python" if py_host else "C step sequencer",
                        "knobs": {k: v for k, v in os.environ.items() if k.startswith("ONEPROT_") and k not in ("ONEPROT_BENCH_N", "ONEPROT_BENCH_D")}},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": dk["tflops"], "peak": peaks["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": dk["tflops"] / peaks["bf16_tflops"], "traffic": traffic,

@@ -551,8 +551,11 @@ class ClipLoss(nn.Module):
                    (bf16 in -> bf16 out).  The fp32 value is always kept in ``last_loss_fp32``.
       panel_bytes  bound of the bf16 dL/dZ panel workspace used by the backward.
       group        process group for the collectives (default: the world group).
-      host_sequencer  enqueue each phase of the step from one C call (sequencer.py; opt-in, also
-                   ONEPROT_SEQ=1) instead of kernel by kernel from Python.
+      host_sequencer  (default True) enqueue each phase of the step from one C call (sequencer.py, csrc/clip_sequence.cu)
+                   instead of kernel by kernel from Python wherever that path covers the call (bf16 features, logit_scale
+                   without gradient, one-pass conventions, NVLS exchange); the results are bit-identical, the host cost
+                   of a small step drops by a third (B200, 5 pairs x 1024 rows: 1.10 vs 1.78 ms on one GPU, 1.81 vs
+                   3.16 ms on two).  False forces the Python host.
       graph        replay the forward / backward launch sequences as CUDA graphs (world_size == 1);
                    removes the ~0.4 ms of host enqueue per step that dominates at OneProt's batch sizes.
       keep_exp     stored-exponentials backward (default True): the forward keeps the n x N exponentials as a
@@ -576,7 +579,7 @@ class ClipLoss(nn.Module):
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
                  use_horovod=False, *, loss_dtype: Optional[torch.dtype] = None,
-                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = False,
+                 panel_bytes: int = DEFAULT_PANEL_BYTES, group=None, host_sequencer: bool = True,
                  robust: Optional[str] = None, graph: bool = False, keep_exp: bool = True,
                  keep_bytes: int = DEFAULT_KEEP_BYTES, check_rows: str = "first"):
         super().__init__()
@@ -688,6 +691,7 @@ class ClipLoss(nn.Module):
             cfg["robust"] = self.robust
         if self.graph and A.is_cuda:
             from .graphed import GraphedClipFunction, GraphedStep
+            cfg["host_sequencer"] = False      # launch cost is paid once, at capture: the plain host order is captured
             needs = (bool(A.requires_grad and torch.is_grad_enabled()), bool(B.requires_grad and torch.is_grad_enabled()))
             key = (tuple(A.shape), A.dtype, needs, bool(scale_t.requires_grad), A.device.index)
             step = self._graphs.get(key)

@@ -998,6 +998,31 @@ int prep_kernel(K kernel, int smem_bytes) {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// The fused all-gather forward spins on flags that are raised only after EVERY CTA of the grid has pushed its slice:
+// the whole grid must be resident at once.  A cooperative launch makes the driver guarantee that (it fails instead of
+// starting a grid it cannot place, e.g. beside another kernel that holds an SM) - a plain launch only happens to work.
+template <typename Kern>
+int launch_coresident(Kern kern, int grid, int smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& w,
+                      const op::SParams& p) {
+#ifdef ONEPROT_HOST_EMULATION
+  (void)kern; (void)grid; (void)smem; (void)st; (void)a; (void)b; (void)w; (void)p;
+  return fail(ONEPROT_ERR_ARG, "the fused all-gather forward is not emulated");
+#else
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(op::NUM_THREADS);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  OP_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, w, p));
+  return ONEPROT_OK;
+#endif
+}
+
 // Row-chunk length CI of an S-kernel work item (item = one 256-column block x CI row blocks).
 // Items are dealt round-robin to one persistent CTA per SM, so the makespan is about
 // ceil(items / SMs) * CI tiles; pick the CI in [ci_min, 16] that minimises it (ties: longer
@@ -1148,9 +1173,11 @@ int oneprot_clip_fwd_sums_keep(const void* A, const void* B_all, int n, int N, i
   if (E) {
     constexpr int smem_e = op::SCfg<op::EPI_FWD_E>::SMEM;
     if ((rc = prep_kernel(op::clip_s_kernel<op::EPI_FWD_E>, smem_e))) return rc;
-    op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
+    if (ag) { if ((rc = launch_coresident(op::clip_s_kernel<op::EPI_FWD_E>, grid, smem_e, st, mapA, mapB, mapE, p))) return rc; }
+    else op::clip_s_kernel<op::EPI_FWD_E><<<grid, op::NUM_THREADS, smem_e, st>>>(mapA, mapB, mapE, p);
   } else {
-    op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
+    if (ag) { if ((rc = launch_coresident(op::clip_s_kernel<op::EPI_FWD>, grid, smem, st, mapA, mapB, mapA, p))) return rc; }
+    else op::clip_s_kernel<op::EPI_FWD><<<grid, op::NUM_THREADS, smem, st>>>(mapA, mapB, mapA /*unused*/, p);
   }
   ++g_launches;
   OP_CUDA(cudaGetLastError());

@@ -40,6 +40,7 @@ class GraphedStep:
         self.A_s.copy_(A.detach()); self.B_s.copy_(B.detach())
         self.scale_s.copy_(scale_t.detach().to(device=dev, dtype=torch.float32).reshape(1))
         self.scale_needs_grad = bool(scale_t.requires_grad)
+        self.generation = 0          # bumped by every replayed forward: a backward must belong to the latest one
 
         # warm-up on a side stream (torch.cuda.graphs contract), then capture
         cur = torch.cuda.current_stream()
@@ -81,9 +82,15 @@ class GraphedStep:
         self.A_s.copy_(A.detach()); self.B_s.copy_(B.detach())
         self.scale_s.copy_(scale_t.detach().to(device=self.A_s.device, dtype=torch.float32).reshape(1))
         self.fwd_graph.replay()
+        self.generation += 1
         return self.loss_out.clone(), self.loss_f32.clone(), self.flag.clone()
 
-    def backward(self, g):
+    def backward(self, g, generation):
+        if generation != self.generation:
+            # the static buffers (operands, saved sums, kept panel) hold a LATER forward's state: replaying would
+            # return that call's gradients silently (e.g. loss = m(A1, B1) + m(A2, B2) on one graphed module)
+            raise RuntimeError("ClipLoss(graph=True): backward of a forward that is no longer the latest one on this module; "
+                               "call backward before the next forward of the same shape, or use graph=False")
         self.g_s.copy_(g.detach().to(dtype=torch.float32).reshape(()))
         self.bwd_graph.replay()
         gA = self.gA.clone() if self.gA is not None else None
@@ -100,6 +107,7 @@ class GraphedClipFunction(torch.autograd.Function):
         ctx.step = step
         ctx.set_materialize_grads(False)
         loss_out, loss_f32, flag = step.forward(A, B, scale_t)
+        ctx.generation = step.generation
         ctx.mark_non_differentiable(loss_f32, flag)
         return loss_out, loss_f32, flag
 
@@ -107,6 +115,6 @@ class GraphedClipFunction(torch.autograd.Function):
     def backward(ctx, g_loss, _g32, _gflag):
         if g_loss is None:
             return None, None, None, None
-        gA, gB, gS = ctx.step.backward(g_loss)
+        gA, gB, gS = ctx.step.backward(g_loss, ctx.generation)
         need = ctx.needs_input_grad
         return (gA if need[0] else None), (gB if need[1] else None), (gS if need[2] else None), None

@@ -7,8 +7,8 @@ NVLS exchange provider.  The C side issues the same launches in the same order o
 as ``_ClipLossFunction._forward_impl/_backward_impl`` (``tests/test_sequencer_cpu.py`` compares the
 two launch traces), so the numerics are those of the Python path.
 
-Opt-in while it has not been validated on hardware: ``ONEPROT_SEQ=1`` or ``ClipLoss(...,
-host_sequencer=True)``.  Scope (everything else stays on the Python path): bf16 features with
+Default since round 2 (``ClipLoss(host_sequencer=True)``; validated on B200 at 1, 2 and 8 GPUs: bit-identical to
+the Python host).  Scope (everything else stays on the Python path): bf16 features with
 d % 8 == 0, ``logit_scale`` without gradient, one pass over both softmax directions (world 1;
 ``local_loss=False``; ``local_loss=True`` with ``gather_with_grad=True``), and for world > 1 the NVLS
 provider with the all-gather fused into the forward kernel and a side stream for the exchanges.
@@ -29,7 +29,7 @@ FLAG_AT = 8         # ONEPROT_SAVED_FLAG_AT
 
 
 def enabled(cfg) -> bool:
-    return bool(cfg.get("host_sequencer")) or os.environ.get("ONEPROT_SEQ") == "1"
+    return bool(cfg.get("host_sequencer"))
 
 
 def eligible(cfg, ops, comm, scale_requires_grad: bool) -> bool:
@@ -52,6 +52,7 @@ def forward(ctx, ops, scale_dev, cfg, comm, K, keep=None):
     """-> (loss32 view, flag view); fills ctx.seq.  keep: bf16 panel that receives the exponentials
     (stored-exponentials backward, clip_loss.py) or None."""
     lib = _lib.load()
+    K._need_cuda(ops.A, ops.B)        # no CPU fallback: fail like every kernel wrapper does
     W, rank = cfg["world_size"], cfg["rank"]
     n, d = ops.n, ops.d
     N, off = W * n, rank * n

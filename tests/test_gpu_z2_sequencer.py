@@ -37,7 +37,7 @@ def test_single_gpu_bit_identical_to_python_host(n, d, panel_rows, need):
     if panel_rows:
         kw["panel_bytes"] = 2 * ((n + 63) // 64 * 64) * panel_rows
         kw["keep_exp"] = False                       # several dL/dZ panels: the recompute backward
-    l0, ga0, gb0, k0 = _step(a, b, need=need, **kw)
+    l0, ga0, gb0, k0 = _step(a, b, need=need, host_sequencer=False, **kw)
     l1, ga1, gb1, k1 = _step(a, b, need=need, host_sequencer=True, **kw)
     assert l0.item() == l1.item()
     assert k0 == k1 and k1 > 0                       # same number of kernel launches

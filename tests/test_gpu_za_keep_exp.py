@@ -142,7 +142,8 @@ def _worker(rank, world, port, n, d, results):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from oneprot_b200 import ClipLoss
     a, b = oc.synthetic_pair(n, d, seed=77, rank=rank)
-    variants = {"default": dict(keep_exp=False), "keep": dict(keep_exp=True), "keep_seq": dict(keep_exp=True, host_sequencer=True)}
+    variants = {"default": dict(keep_exp=False, host_sequencer=False), "keep": dict(keep_exp=True, host_sequencer=False),
+                "keep_seq": dict(keep_exp=True, host_sequencer=True)}
     rec = {}
     for ll, gwg in ((False, True), (False, False), (True, True), (True, False)):     # the last one falls back to the recompute
         for name, kw in variants.items():

@@ -22,7 +22,7 @@ a, b = oc.synthetic_pair(n, d, seed=1)
 A = a.cuda().requires_grad_(True)
 B = b.cuda().requires_grad_(True)
 ref = None
-for name, kw in (("python", {}), ("seq", dict(host_sequencer=True)), ("graph", dict(graph=True))):
+for name, kw in (("python", dict(host_sequencer=False)), ("seq", dict(host_sequencer=True)), ("graph", dict(graph=True))):
     try:
         m = ClipLoss(loss_dtype=torch.float32, **kw)
 

@@ -9,10 +9,10 @@ run() { name=$1; shift; echo "=== $name"; timeout ${T:-300} "$@" > gpurun_out/$n
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1"
 T=600 run mg_tests python -m pytest tests/test_gpu_zb_configs.py tests/test_gpu_multirank.py tests/test_gpu_z2_sequencer.py tests/test_gpu_z4_siglip.py tests/test_gpu_za_keep_exp.py -q -m gpu -s -p no:cacheprovider -k "zb_configs or multi_gpu or two_gpu"
 S="--steps 100 --warmup 5"
-run mg_bench_py   $TR --master-port 29511 bench.py --gpus $G $S
-ONEPROT_SEQ=1 run mg_bench_seq $TR --master-port 29512 bench.py --gpus $G $S
-run mg_bench_py2  $TR --master-port 29513 bench.py --gpus $G $S
-ONEPROT_SEQ=1 run mg_bench_seq2 $TR --master-port 29514 bench.py --gpus $G $S
+ONEPROT_BENCH_HOST=python run mg_bench_py   $TR --master-port 29511 bench.py --gpus $G $S
+run mg_bench_seq $TR --master-port 29512 bench.py --gpus $G $S
+ONEPROT_BENCH_HOST=python run mg_bench_py2  $TR --master-port 29513 bench.py --gpus $G $S
+run mg_bench_seq2 $TR --master-port 29514 bench.py --gpus $G $S
 run mg_bench_1    python bench.py --gpus 1 $S --no-cpu-baseline
 run mg_eager      $TR --master-port 29515 tests/perf_eager_bar.py --world --sizes 8192,32768 --reps 5 --out gpurun_out/eager_bar_w$G.json
 grep -h '"metric"' gpurun_out/mg_bench_py.log gpurun_out/mg_bench_seq.log gpurun_out/mg_bench_py2.log gpurun_out/mg_bench_seq2.log gpurun_out/mg_bench_1.log > gpurun_out/r2_mg${G}_bench_lines.json

@@ -310,14 +310,19 @@ def run_ours(args):
         host_loss.copy_(loss.detach().float(), non_blocking=True)
         return Ad.grad
 
-    def timed(fn, k):
+    host_ms = {}     # leg -> host time to ENQUEUE one step (no sync inside): a leg is host-bound when this reaches its ms/step
+
+    def timed(fn, k, leg=None):
         """k steps, each bracketed by its own event pair; the L2 flush sits between the pairs."""
         evs = []
+        t0 = time.perf_counter()
         for _ in range(k):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             evs.append((e0, e1))
+        if leg is not None:
+            host_ms[leg] = 1e3 * (time.perf_counter() - t0) / k
         torch.cuda.synchronize()
         return [e0.elapsed_time(e1) for e0, e1 in evs]
 
@@ -337,7 +342,7 @@ def run_ours(args):
         step_device()
     kernels.launch_count_reset()
     barrier()
-    ms = timed(step_device, steps)
+    ms = timed(step_device, steps, "device_resident")
     barrier()
     launches = kernels.launch_count()
     ms_steps_rank0 = [round(x, 4) for x in ms]
@@ -371,18 +376,18 @@ def run_ours(args):
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
     k_e2e = max(3, steps // 2)
 
-    def measure(fn):
+    def measure(fn, leg):
         for _ in range(max(3, world)):
             fn()
         barrier()
-        t = timed(fn, k_e2e)
+        t = timed(fn, k_e2e, leg)
         barrier()
         m = torch.tensor([sum(t) / len(t)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(m, op=dist.ReduceOp.MAX)
         return float(m.item())
 
-    e2e_serial_ms = measure(lambda: step_e2e(host_loss))
+    e2e_serial_ms = measure(lambda: step_e2e(host_loss), "e2e_serial")
 
     # ---- roofline: the four tensor-core kernels timed alone (rank-local panel), CUDA events
     roof = (kernel_roofline(torch, kernels, A.detach(), B.detach(), n, GLOBAL_N, world, rank, dev, flush, loss_mod.keep_exp)
@@ -497,9 +502,10 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(pipe_ok, op=dist.ReduceOp.MIN)
     if int(pipe_ok.item()):
-        e2e_ms = measure(step_e2e_pipelined)
+        e2e_ms = measure(step_e2e_pipelined, "e2e_pipelined")
         if rank == 0:
             line["e2e"]["pipelined_ms_per_step"] = e2e_ms
+            line["config"]["host_enqueue_ms_per_step_rank0"] = host_ms
             if e2e_ms <= e2e_serial_ms:
                 line["e2e"].update(value=GLOBAL_N / (e2e_ms * 1e-3), ms_per_step=e2e_ms,
                                    mode=("pipelined: PinnedPairPrefetcher copies the next step's pair on a copy stream inside "

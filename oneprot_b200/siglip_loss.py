@@ -24,7 +24,6 @@ parameters later).  Exchanges go through torch.distributed (all-gather / reduce-
 """
 from __future__ import annotations
 
-import os
 from typing import Optional
 
 import torch
@@ -184,12 +183,12 @@ class SigLipLoss(nn.Module):
 
     Extra keyword-only arguments: ``loss_dtype`` (dtype of the returned scalar, default = input dtype
     like the reference), ``panel_bytes`` (bound of the bf16 dL/dZ panel), ``group`` (process group),
-    ``keep_exp`` / ``keep_bytes`` (opt-in, also ONEPROT_KEEP_EXP=1: the forward keeps sigma(z) - [i == j] as a
-    bf16 n x N panel and the backward is the two GEMMs on it - no recompute, no panel kernel)."""
+    ``keep_exp`` / ``keep_bytes`` (default True / 8 GiB: the forward keeps sigma(z) - [i == j] as a bf16 n x N panel and
+    the backward is the two GEMMs on it - no recompute, no panel kernel; False or a larger panel: recompute backward)."""
 
     def __init__(self, cache_labels=False, rank=0, world_size=1, bidir=True, use_horovod=False, *,
                  loss_dtype: Optional[torch.dtype] = None, panel_bytes: int = _cl.DEFAULT_PANEL_BYTES, group=None,
-                 keep_exp: Optional[bool] = None, keep_bytes: int = _cl.DEFAULT_KEEP_BYTES):
+                 keep_exp: bool = True, keep_bytes: int = _cl.DEFAULT_KEEP_BYTES):
         super().__init__()
         self.cache_labels = cache_labels
         self.rank = rank
@@ -200,7 +199,7 @@ class SigLipLoss(nn.Module):
         self.loss_dtype = loss_dtype
         self.panel_bytes = int(panel_bytes)
         self.group = group
-        self.keep_exp = (os.environ.get("ONEPROT_KEEP_EXP") == "1") if keep_exp is None else bool(keep_exp)
+        self.keep_exp = bool(keep_exp)
         self.keep_bytes = int(keep_bytes)
         self.prev_num_logits = 0
         self.labels = {}

@@ -389,6 +389,24 @@ def run_ours(args):
 
     e2e_serial_ms = measure(lambda: step_e2e(host_loss), "e2e_serial")
 
+    # H2D probe: the copy of one step's pair alone, all ranks at the same time (barrier-aligned) - the floor of any
+    # end-to-end step from host memory on this box (8 GPUs share the host's memory / PCIe bandwidth)
+    Ad_probe, Bd_probe = torch.empty_like(A), torch.empty_like(B)
+    barrier()
+    pe = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Ad_probe.copy_(a_pin, non_blocking=True); Bd_probe.copy_(b_pin, non_blocking=True)
+        e1.record()
+        pe.append((e0, e1))
+    torch.cuda.synchronize()
+    h2d_ms = torch.tensor([sum(x.elapsed_time(y) for x, y in pe) / len(pe)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_ms, op=dist.ReduceOp.MAX)
+    h2d_ms = float(h2d_ms.item())
+    del Ad_probe, Bd_probe
+
     # ---- roofline: the four tensor-core kernels timed alone (rank-local panel), CUDA events
     roof = (kernel_roofline(torch, kernels, A.detach(), B.detach(), n, GLOBAL_N, world, rank, dev, flush, loss_mod.keep_exp)
             if rank == 0 else None)
@@ -440,7 +458,9 @@ def run_ours(args):
             "e2e": {"value": GLOBAL_N / (e2e_serial_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_serial_ms,
                     "h2d_bytes_per_step": 2 * n * DIM * 2, "d2h_bytes_per_step": 4,
                     "mode": "serial (copy, then compute, on one stream); dA / dB stay on the device (they feed the encoder backward there), only the loss is read back",
-                    "serial_value": GLOBAL_N / (e2e_serial_ms * 1e-3), "serial_ms_per_step": e2e_serial_ms},
+                    "serial_value": GLOBAL_N / (e2e_serial_ms * 1e-3), "serial_ms_per_step": e2e_serial_ms,
+                    "h2d_alone_ms_per_step": h2d_ms, "h2d_alone_gbs_per_gpu": 2 * n * DIM * 2 / (h2d_ms * 1e-3) / 1e9,
+                    "h2d_alone_gbs_all_gpus": world * 2 * n * DIM * 2 / (h2d_ms * 1e-3) / 1e9},
             "gpu_launches": launches,
             "clocks": clocks,
         }

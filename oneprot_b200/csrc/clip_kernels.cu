@@ -1026,7 +1026,9 @@ int launch_coresident(Kern kern, int grid, int smem, cudaStream_t st, const CUte
 // Row-chunk length CI of an S-kernel work item (item = one 256-column block x CI row blocks).
 // Items are dealt round-robin to one persistent CTA per SM, so the makespan is about
 // ceil(items / SMs) * CI tiles; pick the CI in [ci_min, 16] that minimises it (ties: longer
-// chunks, fewer column flushes; beyond 16 the cold-L2 start gets measurably worse).
+// chunks, fewer column flushes; beyond 16 the cold-L2 start gets measurably worse).  Shorter chunks with the same
+// makespan (fewer CTAs sharing a streamed row tile) were measured in round 2 at N = 32768 and are slower: FWD_E
+// 1.806 / 1.867 / 1.956 ms and 5.89 / 5.96 / 6.14 ms per step for CI = 16 / 8 / 4 (profiles/r2f_ci_ab.txt).
 void s_schedule(int rows, int N, int ci_min, op::SParams& p) {
   p.nI = cdiv(rows, op::BM);
   p.nJ = cdiv(N, op::BN);

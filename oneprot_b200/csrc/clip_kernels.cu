@@ -91,15 +91,22 @@ __device__ __forceinline__ void load_stage(uint8_t* sa, uint8_t* sb, const CUten
   }
 }
 
+// The four UMMAs of one 64-deep stage.  Only the 14-bit start-address field of the shared-memory descriptors moves
+// from one K = 16 step to the next (+32 B K-major, +2048 B MN-major; no carry: the stage lies below 256 KiB), so the
+// descriptors of a stage are built once and stepped by one 32-bit add each.  The MMA warp is the pacing warp of the
+// S-kernels (ncu, round 2: ~105 instructions per stage took ~700 cycles beside two busy epilogue warps on its
+// scheduler against 512 cycles of tensor work; the warp never waited for operands or accumulators) - every
+// instruction taken out of this loop is tensor-pipe time.
 template <int A_MN, int B_MN>
 __device__ __forceinline__ void mma_stage(uint32_t sa, uint32_t sb, uint32_t tmem_d, bool first) {
   constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+  constexpr uint32_t step_a = (A_MN ? 2048 : 32) >> 4, step_b = (B_MN ? 2048 : 32) >> 4;
+  const uint64_t da = A_MN ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
+  const uint64_t db = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 16, 1024);
 #pragma unroll
-  for (int k = 0; k < BK / 16; ++k) {
-    const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-    const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-    umma_bf16(tmem_d, da, db, idesc, (first && k == 0) ? 0u : 1u);
-  }
+  for (int k = 0; k < BK / 16; ++k)
+    umma_bf16(tmem_d, da + static_cast<uint64_t>(k * step_a), db + static_cast<uint64_t>(k * step_b), idesc,
+              (first && k == 0) ? 0u : 1u);
 }
 
 template <int NS>
@@ -399,11 +406,14 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------ UMMA issuer
+    // All 32 lanes walk the loop in lock step (uniform control flow keeps the descriptors in uniform registers); the
+    // lane elect.sync picks - the same one every time - issues the UMMAs and their commits.
     reg_dealloc<56>();
-    if (lane_id() == 0) {
+    {
       PipeState<NS> ps;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t stages_s = smem_u32(s.stages);
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int jl, ch;
         item_to_jc(p, item, jl, ch);
@@ -415,12 +425,16 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           for (int kb = 0; kb < p.nK; ++kb) {
             mbar_wait(&s.tail->full[ps.stage], ps.phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(s.stages + ps.stage * STAGE_BYTES);
-            mma_stage<0, 0>(sa, sa + A_STAGE_BYTES, tmem_d, kb == 0);
-            umma_commit(&s.tail->empty[ps.stage]);
+            if (elect_one()) {
+              const uint32_t sa = stages_s + ps.stage * STAGE_BYTES;
+              mma_stage<0, 0>(sa, sa + A_STAGE_BYTES, tmem_d, kb == 0);
+              umma_commit(&s.tail->empty[ps.stage]);
+            }
+            __syncwarp();
             ps.advance();
           }
-          umma_commit(&s.tail->tfull[acc]);
+          if (elect_one()) umma_commit(&s.tail->tfull[acc]);
+          __syncwarp();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -771,10 +785,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     reg_dealloc<40>();
-    if (lane_id() == 0) {
+    {   // all lanes in lock step, the elected lane issues (see clip_s_kernel)
       PipeState<GEMM_NS> ps;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t stages_s = smem_u32(s.stages);
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         mbar_wait(&s.tail->tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -782,12 +797,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         for (int kb = 0; kb < p.nK; ++kb) {
           mbar_wait(&s.tail->full[ps.stage], ps.phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(s.stages + ps.stage * STAGE_BYTES);
-          mma_stage<A_MN, B_MN>(sa, sa + A_STAGE_BYTES, tmem_d, kb == 0);
-          umma_commit(&s.tail->empty[ps.stage]);
+          if (elect_one()) {
+            const uint32_t sa = stages_s + ps.stage * STAGE_BYTES;
+            mma_stage<A_MN, B_MN>(sa, sa + A_STAGE_BYTES, tmem_d, kb == 0);
+            umma_commit(&s.tail->empty[ps.stage]);
+          }
+          __syncwarp();
           ps.advance();
         }
-        umma_commit(&s.tail->tfull[acc]);
+        if (elect_one()) umma_commit(&s.tail->tfull[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -237,7 +237,9 @@ class NvlsComm(DistComm):
                 h.snap = h.view.clone()       # stream-ordered before this call's exchanges
 
     # ---- forward -------------------------------------------------------------------------
-    def begin_forward(self, ops, rank, world):
+    def begin_forward(self, ops, rank, world, fused=True):
+        """fused=False: always gather with the separate multicast kernel (callers whose forward kernel does not
+        carry the all-gather: SigLipLoss)."""
         K = self.K
         n, dk = ops.n, ops.dk
         N = world * n
@@ -251,7 +253,7 @@ class NvlsComm(DistComm):
         small.zero_()
         st = dict(B_all=Bg, sums=small[self.SUMS_AT:self.SUMS_AT + 3 * N], stats=small[self.STATS_AT:self.STATS_AT + 4],
                   stats_rows=ops.B, stats_off=0, token=(p, self.calls), p=p, N=N, ag=None)
-        chunks = next((c for c in (8, 4, 2, 1) if n % (c * 256) == 0), 0)
+        chunks = next((c for c in (8, 4, 2, 1) if n % (c * 256) == 0), 0) if fused else 0
         if chunks:
             # the gather is fused into the forward kernel: nothing to launch here
             base = int(self.hdl.buffer_ptrs[rank]) + self._off_ctl()
@@ -265,6 +267,12 @@ class NvlsComm(DistComm):
             # second operand: one multimem.st pass puts this rank's rows into every GPU's Bg[p]
             K.mc_store(ops.B, self.mc + self._off_bg(p) + rank * n * dk * 2, n * dk * 2)
         return st
+
+    def gather_rows(self, ops, rank, world):
+        """All-gather of the second operand alone (one multimem.st pass + barrier) -> (B_all view, token)."""
+        st = self.begin_forward(ops, rank, world, fused=False)
+        self._barrier()                           # every rank's rows are in place
+        return st["B_all"], st["token"]
 
     def global_stats(self, st):
         # (the caller ran rowstats on the LOCAL rows: stats holds this rank's maxima)

@@ -69,7 +69,21 @@ class _SigLipFunction(torch.autograd.Function):
             ops = _cl._Operands(A, B)
             n, off = ops.n, rank * ops.n
             dev = A.device
-            B_all = ops.B if W == 1 else _all_gather_rows(ops.B, W, group)
+            # exchange provider of the ClipLoss path (comm.py): on one NVSwitch node the second operand is gathered by one
+            # multimem.st pass and the partial dB reduced by multimem.ld_reduce (the reference's ring of W - 1 neighbour
+            # exchanges, loss.py:116-201, carries the same rows); torch.distributed collectives otherwise
+            ctx.comm = ctx.token = ctx.bhold = None
+            if W == 1:
+                B_all = ops.B
+            else:
+                comm = _cl._get_comm(W, rank, group, dev)
+                if comm.name == "nvls" and not ops.split:
+                    B_all, ctx.token = comm.gather_rows(ops, rank, W)
+                    ctx.comm = comm
+                    if any(ctx.needs_input_grad[:4]):
+                        ctx.bhold = comm.hold_for_backward(B_all)
+                else:
+                    B_all = _all_gather_rows(ops.B, W, group)
             diag = torch.empty(n, dtype=torch.float32, device=dev)
             stats = torch.zeros(4, dtype=torch.float32, device=dev)
             K.rowstats(ops.A, B_all, off, diag, stats)                  # diag[i] = <a_i, b_{off+i}>: the label logits
@@ -105,6 +119,8 @@ class _SigLipFunction(torch.autograd.Function):
             n, d = ops.n, ops.d
             N, off = W * n, rank * n
             dev = ops.A.device
+            if ctx.comm is not None:
+                B_all = ctx.comm.b_all_for_backward(ops, B_all, ctx.token, rank, W, hold=ctx.bhold)
             need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
             need_s = ctx.needs_input_grad[2]
             need_bias = ctx.bias_dev is not None and ctx.needs_input_grad[3]
@@ -119,7 +135,7 @@ class _SigLipFunction(torch.autograd.Function):
                 # kept panel: S already is dL/dz / (logit_scale g / n); the constant goes into the GEMM epilogues' row scale
                 S = ctx.S[:n]
                 dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
-                dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
+                dBp = _SigLipFunction._db_buffer(ctx, N, d, grad_dtype, dev) if want_b else None
                 if want_b:
                     coef_N = (ctx.scale_dev * g32 / n).expand(N).contiguous()
                     _cl._GemmChain(N, d, dBp, coef_N, 1).add(S, True, ops.A, True, n)
@@ -140,7 +156,7 @@ class _SigLipFunction(torch.autograd.Function):
             Wz = torch.empty(min(rows_cap, (n + 127) // 128 * 128), ldw, dtype=torch.bfloat16, device=dev)
             n_bp = 2 if ops.split else 1
             dA = torch.empty(n, d, dtype=grad_dtype, device=dev) if want_a else None
-            dBp = torch.empty(N, d, dtype=grad_dtype, device=dev) if want_b else None
+            dBp = _SigLipFunction._db_buffer(ctx, N, d, grad_dtype, dev) if want_b else None
             chain_b = _cl._GemmChain(N, d, dBp, None, len(panels) * n_bp) if want_b else None
             b_pieces = ops.b_pieces(B_all)
             sig = torch.empty(n, dtype=torch.float32, device=dev) if need_bias else None     # row sums of sigma(z)
@@ -159,13 +175,23 @@ class _SigLipFunction(torch.autograd.Function):
             return _SigLipFunction._finish(ctx, K, dA, dBp, sig, g32, need_a, need_b, need_s, need_bias)
 
     @staticmethod
+    def _db_buffer(ctx, N, d, dtype, dev):
+        """Where the partial dB is written: the symmetric workspace under the NVLS provider (its owner pulls the sum)."""
+        if ctx.comm is not None and dtype == torch.bfloat16:
+            return ctx.comm.db_buffer(N, d, dtype, dev)
+        return torch.empty(N, d, dtype=dtype, device=dev)
+
+    @staticmethod
     def _finish(ctx, K, dA, dBp, sig, g32, need_a, need_b, need_s, need_bias):
         """Exchange of the partial dB, scalar gradients, final dtypes (shared by the panel and the kept-panel backward)."""
         cfg, ops = ctx.cfg, ctx.ops
         W, rank, group = cfg["world_size"], cfg["rank"], cfg["group"]
         n, dev = ops.n, ops.A.device
         if dBp is not None and W > 1:
-            dBp = _reduce_scatter_rows(dBp, rank, W, group)
+            if ctx.comm is not None and dBp.dtype == torch.bfloat16:
+                dBp = ctx.comm.reduce_scatter_db(dBp, rank, W)        # barrier + multimem.ld_reduce pull of this rank's rows
+            else:
+                dBp = _reduce_scatter_rows(dBp, rank, W, group)
         grad_s = grad_bias = None
         if need_s:      # d loss / d scale = sum_ij dL/dz_ij <a_i, b_j> = (1 / scale) sum_i <a_i, dA_i>
             sdt, sdev, sshape = ctx.scalar_meta[0]

@@ -152,11 +152,16 @@ class NvlsComm(DistComm):
     name = "nvls"
     G_AT, STATS_AT, SUMS_AT = 0, 16, 32      # float offsets inside a small buffer: [g | maxima | sums]
 
-    def __init__(self, K, group, world, rank, dev):
+    def __init__(self, K, group, world, rank, dev, static=False):
         super().__init__(K, group)
         import torch.distributed._symmetric_memory as symm
         self.symm = symm
         self.world, self.rank, self.dev = world, rank, dev
+        # static = the CUDA-graph variant (graphed.py): every address, barrier channel and kernel argument of a step must
+        # be the same at every replay, so there is ONE buffer set (no parity), no epoch-flagged fused gather, no side
+        # stream, and a leading barrier per forward gives the write-after-read protection the double buffering gives
+        # the eager provider (5 barriers per step instead of 3: meant for the launch-bound batch sizes)
+        self.static = bool(static)
         self.cap = None          # (n, dk, d) capacity the workspace was sized for
         self.calls = 0
         self.gen = [0, 0]        # generation of the data held in Bg[p]
@@ -197,6 +202,8 @@ class NvlsComm(DistComm):
         self.chan = (self.chan + 1) % 8
 
     def side_stream(self, dev):
+        if self.static:
+            return None
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
         return self._side
@@ -226,6 +233,8 @@ class NvlsComm(DistComm):
         __slots__ = ("view", "snap", "__weakref__")
 
     def hold_for_backward(self, B_all):
+        if self.static:
+            return None               # a graphed step refuses a backward that is not the latest forward's (graphed.py)
         h = NvlsComm._Hold()
         h.view, h.snap = B_all, None
         self._pending.add(h)
@@ -244,10 +253,16 @@ class NvlsComm(DistComm):
         n, dk = ops.n, ops.dk
         N = world * n
         self._ensure(n, dk, ops.d)
-        self._snapshot_pending()
-        p = self.calls & 1
-        self.calls += 1
-        self.gen[p] = self.calls
+        if self.static:
+            fused = False
+            self._barrier()           # every rank has finished the previous step's reads of the single buffer set
+            p, self.gen[0] = 0, 1
+            self.calls = 1
+        else:
+            self._snapshot_pending()
+            p = self.calls & 1
+            self.calls += 1
+            self.gen[p] = self.calls
         Bg = self._view(self._off_bg(p), (N, dk), torch.bfloat16)
         small = self._view(self._off_small(p), (self.SUMS_AT + 3 * N,), torch.float32)
         small.zero_()
@@ -352,6 +367,8 @@ class NvlsComm(DistComm):
     def b_all_for_backward(self, ops, B_all, token, rank, world, hold=None):
         """The gathered operand for the backward of the forward `token`: the symmetric buffer when that backward
         directly follows its forward, else the snapshot begin_forward took (see the class docstring)."""
+        if self.static:
+            return B_all
         if hold is not None:
             self._pending.discard(hold)
             if hold.snap is not None:
@@ -386,6 +403,8 @@ def make_comm(K, world, rank, group, device, prefer=None):
     if world == 1:
         return LocalComm(K)
     mode = (prefer or os.environ.get("ONEPROT_COMM", "auto")).lower()
+    if mode.startswith("nvls-static"):   # "nvls-static/<shape tag>": one workspace per graphed step shape; CUDA-graph replay (graphed.py): no fallback, the torch.distributed provider is not captured
+        return NvlsComm(K, group, world, rank, device, static=True)
     want_nvls = mode == "nvls" or (mode == "auto" and device.type == "cuda" and dist.get_backend(group) == "nccl"
                                    and hasattr(K, "mc_store") and world <= torch.cuda.device_count())
     if want_nvls:

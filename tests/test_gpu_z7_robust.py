@@ -1,5 +1,5 @@
 """GPU: two-reference (robust) ClipLoss path - per-row / per-column references for inputs outside the
-single-reference fp32 window - against the float64 oracle.  Not yet run on hardware."""
+single-reference fp32 window - against the float64 oracle.  Green on B200 since round 2."""
 import math
 
 import numpy as np

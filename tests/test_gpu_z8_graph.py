@@ -1,5 +1,5 @@
 """GPU: ClipLoss(graph=True) - CUDA-graph replay of the forward / backward launch sequences (world_size 1) -
-against the eager path, bit for bit.  Not yet run on hardware."""
+against the eager path, bit for bit.  Green on B200 since round 2."""
 import math
 
 import numpy as np

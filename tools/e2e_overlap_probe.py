@@ -13,7 +13,7 @@ from tools.synthetic import synthetic_global_rows
 world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0)); lr = int(os.environ.get("LOCAL_RANK", 0))
 dev = torch.device("cuda", lr); torch.cuda.set_device(dev)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
-N, d = 32768, 1024; n = N // world
+N, d = int(os.environ.get("PROBE_N", 32768)), 1024; n = N // world
 a, b = synthetic_global_rows(rank * n, n, d)
 a_pin, b_pin = a.pin_memory(), b.pin_memory()
 A = a.to(dev).requires_grad_(True); B = b.to(dev).requires_grad_(True)

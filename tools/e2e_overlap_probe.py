@@ -17,7 +17,7 @@ N, d = int(os.environ.get("PROBE_N", 32768)), 1024; n = N // world
 a, b = synthetic_global_rows(rank * n, n, d)
 a_pin, b_pin = a.pin_memory(), b.pin_memory()
 A = a.to(dev).requires_grad_(True); B = b.to(dev).requires_grad_(True)
-m = ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world)
+m = ClipLoss(local_loss=False, gather_with_grad=True, rank=rank, world_size=world, graph=bool(os.environ.get("PROBE_GRAPH")))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 K = 60
 def barrier():

@@ -420,38 +420,6 @@ __device__ __forceinline__ float gelu_grad_f(float v) {
   return fmaf(v, pdf, cdf);
 }
 
-// bf16 in / bf16 out: the exact erff costs ~35 instructions per element and made the bf16 kernels ISSUE-bound (56 % of
-// the HBM copy bandwidth where the fp32 ones reach 91 - 95 %, round-2 measurement).  Abramowitz & Stegun 7.1.26
-// (|error| <= 1.5e-7 absolute; one reciprocal, one exponential, five FMAs) keeps GELU within 9.3e-4 relative of the
-// exact value for v > -4 - half a bf16 ulp is 1.95e-3 - and the exponential is the one the gradient's pdf needs anyway;
-// the far negative tail (v < -3.5, where the result is ~1e-4 |v| and smaller) takes the exact erfc.
-__device__ __forceinline__ void gelu_fast_parts(float v, float& cdf, float& e) {     // cdf = Phi(v), e = exp(-v^2 / 2)
-  const float a = fabsf(v) * 0.70710678118654752f;
-  e = __expf(-a * a);
-  if (v < -3.5f) { cdf = 0.5f * erfcf(a); return; }
-  const float t = __fdividef(1.f, fmaf(0.3275911f, a, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float half_erfc = 0.5f * p * t * e;              // 0.5 erfc(|v| / sqrt 2)
-  cdf = v >= 0.f ? 1.f - half_erfc : half_erfc;
-}
-template <bool FP32>
-__device__ __forceinline__ float gelu_fwd_t(float v) {
-  if (FP32) return gelu_f(v);
-  float cdf, e;
-  gelu_fast_parts(v, cdf, e);
-  return v * cdf;
-}
-template <bool FP32>
-__device__ __forceinline__ float gelu_grad_t(float v) {
-  if (FP32) return gelu_grad_f(v);
-  float cdf, e;
-  gelu_fast_parts(v, cdf, e);
-  return fmaf(v, 0.3989422804014327f * e, cdf);
-}
-
 // 4 independent 16-byte vectors per thread and step: all loads are issued before the first erf (bytes in flight)
 template <bool FP32, bool BWD>
 __global__ void __launch_bounds__(256) gelu_kernel(const void* __restrict__ x, const void* __restrict__ gy, void* __restrict__ out,
@@ -478,10 +446,10 @@ __global__ void __launch_bounds__(256) gelu_kernel(const void* __restrict__ x, c
           float g[8];
           vg[j].unpack(g);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) o[u] = g[u] * gelu_grad_t<FP32>(f[u]);
+          for (int u = 0; u < 8; ++u) o[u] = g[u] * gelu_grad_f(f[u]);
         } else {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) o[u] = gelu_fwd_t<FP32>(f[u]);
+          for (int u = 0; u < 8; ++u) o[u] = gelu_f(f[u]);
         }
         store8<FP32>(out, i * 8, o);
       }

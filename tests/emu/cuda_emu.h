@@ -112,9 +112,6 @@ inline uint32_t float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); ret
 #define __float_as_uint(f) emu::float_as_uint(f)
 #define __int_as_float(i) emu::uint_as_float(static_cast<uint32_t>(i))
 #define __expf(x) expf(x)
-#ifndef __fdividef
-#define __fdividef(a, b) ((a) / (b))
-#endif
 #define __log2f(x) log2f(x)
 #define rsqrtf(x) (1.0f / sqrtf(x))
 #define __ldg(p) (*(p))

@@ -454,19 +454,3 @@ def test_emulated_gemm_all_layouts_and_epilogues(tc, a_mn, b_mn, M, Nc, K):
     assert np.allclose(acc_out.numpy(), val * rs.double().numpy()[:, None], rtol=1e-5, atol=1e-4)
     assert np.allclose(out.double().numpy(), val * rs.double().numpy()[:, None], rtol=2.0 ** -7, atol=1e-2)
     assert np.allclose(rd.double().numpy()[:, :M].sum(0), (val * dotv).sum(1), rtol=1e-4, atol=1e-3)      # row dots of the unscaled value
-
-
-def test_bf16_gelu_fast_erf_stays_within_one_bf16_ulp(emu):
-    """The bf16 GELU kernels use a 12-instruction erf (Abramowitz & Stegun 7.1.26, exact erfc in the far negative tail):
-    over a dense grid of inputs the result is within one bf16 ulp of the correctly rounded float64 value, forward
-    and backward."""
-    x = torch.linspace(-9.0, 9.0, 8 * 4096).to(torch.bfloat16)
-    xv = x.double().numpy()
-    gy = torch.ones_like(x)
-    y = torch.empty_like(x); gx = torch.empty_like(x)
-    emu.emu_gelu(_p(x), None, _p(y), C.c_size_t(x.numel()), 0)
-    emu.emu_gelu(_p(x), _p(gy), _p(gx), C.c_size_t(x.numel()), 0)
-    for got, want in ((y, ho.gelu_fwd(xv)), (gx, ho.gelu_bwd(np.ones_like(xv), xv))):
-        w = torch.from_numpy(want)
-        ulp = torch.maximum(2.0 ** (torch.floor(torch.log2(w.abs().clamp_min(1e-30))) - 7), torch.tensor(2.0 ** -40, dtype=torch.float64))
-        assert float(((got.double() - w).abs() / ulp).max()) <= 1.0

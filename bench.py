@@ -570,7 +570,7 @@ def kernel_roofline(torch, K, A, B, n, N, world, rank, dev, flush, keep, reps=5)
     off = rank * n
     B_all = B if world == 1 else B.repeat(world, 1)       # same shape/values class as the gathered operand
     scale = torch.ones(1, dtype=torch.float32, device=dev)
-    stats = torch.zeros(2, dtype=torch.float32, device=dev)
+    stats = torch.zeros(4, dtype=torch.float32, device=dev)      # [max|a|^2, max|b|^2, exact max logit, its valid flag]
     diag = torch.empty(n, dtype=torch.float32, device=dev)
     rowsum = torch.empty(n, dtype=torch.float32, device=dev)
     colsum = torch.empty(N, dtype=torch.float32, device=dev)

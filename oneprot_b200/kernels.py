@@ -117,11 +117,18 @@ def launch_count_reset():
     _lib.load().oneprot_launch_count_reset()
 
 
+def _need_stats(stats):
+    """[max |a|^2, max |b|^2, exact maximum logit, its valid flag]: the forward / panel kernels read all four floats."""
+    _need(stats, torch.float32, "stats")
+    if stats.numel() < 4:
+        raise ValueError("stats must hold 4 floats: [max|a|^2, max|b|^2, exact max logit, valid flag]")
+
+
 def rowstats(A, B_all, row_offset: int, diag, stats):
     """diag[i] = <a_i, b_{row_offset+i}>, stats[0:2] = max |a|^2, max |b|^2 (atomic max)."""
     _need_cuda(A, B_all, diag, stats)
     _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
-    _need(diag, torch.float32, "diag"); _need(stats, torch.float32, "stats")
+    _need(diag, torch.float32, "diag"); _need_stats(stats)
     n, d = A.shape
     N = B_all.shape[0]
     check(_lib.load().oneprot_clip_rowstats(ptr(A), ptr(B_all), n, N, d, row_offset, ptr(diag), ptr(stats),
@@ -138,7 +145,7 @@ def fwd_sums(A, B_all, scale_dev, stats, rowsum, colsum, scratch=None, ag=None, 
     keep: optional bf16 tensor (>= n rows, row pitch >= N, multiple of 8) that receives the exponentials
     e_ij for dz_from_exp (stored-exponentials backward)."""
     _need_cuda(A, B_all, scale_dev, stats, rowsum, colsum)
-    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all")
+    _need(A, torch.bfloat16, "A"); _need(B_all, torch.bfloat16, "B_all"); _need_stats(stats)
     n, d = A.shape
     N = B_all.shape[0]
     need = fwd_scratch_bytes(n, N)
@@ -227,6 +234,7 @@ def dz_panel(A_rows, B_all, grow0: int, scale_dev, stats, wr, wc, dg, Wz):
     """Wz[i, j] = e_ij (wr[i] + wc[j]) - [grow0+i == j] dg[i]  (bf16 panel, rows x ldw)."""
     _need_cuda(A_rows, B_all, wr, wc, dg, Wz)
     _need(A_rows, torch.bfloat16, "A_rows"); _need(B_all, torch.bfloat16, "B_all"); _need(Wz, torch.bfloat16, "Wz")
+    _need_stats(stats)
     rows, d = A_rows.shape
     N = B_all.shape[0]
     if Wz.shape[0] < rows:

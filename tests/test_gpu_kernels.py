@@ -61,7 +61,7 @@ def test_fwd_sums_match_fp64(n, N, d, off):
     A = (_rand_bf16(n, d, 12, 1.0 / math.sqrt(d)).float() + 0.5 * B_all[off:off + n].float()).to(torch.bfloat16)
     s = 14.2857
     scale = torch.tensor([s], dtype=torch.float32, device="cuda")
-    stats = torch.zeros(2, dtype=torch.float32, device="cuda")
+    stats = torch.zeros(4, dtype=torch.float32, device="cuda")
     diag = torch.empty(n, dtype=torch.float32, device="cuda")
     rowsum = torch.empty(n, dtype=torch.float32, device="cuda")
     colsum = torch.empty(N, dtype=torch.float32, device="cuda")
@@ -89,7 +89,7 @@ def test_dz_panel_matches_fp64(rows, N, d, grow0):
     A = _rand_bf16(rows, d, 22, 1.0 / math.sqrt(d))
     s = 10.0
     scale = torch.tensor([s], dtype=torch.float32, device="cuda")
-    stats = torch.zeros(2, dtype=torch.float32, device="cuda")
+    stats = torch.zeros(4, dtype=torch.float32, device="cuda")
     diag = torch.empty(rows, dtype=torch.float32, device="cuda")
     k.rowstats(A, B_all, grow0, diag, stats)
     g = torch.Generator(device="cpu").manual_seed(5)

@@ -21,7 +21,7 @@ dev = torch.device("cuda")
 a, b = oc.synthetic_pair(N, d, seed=1)
 A, B = a.to(dev), b.to(dev)
 scale = torch.ones(1, device=dev)
-stats = torch.zeros(2, device=dev)
+stats = torch.zeros(4, device=dev)
 diag = torch.empty(N, device=dev)
 K.rowstats(A, B, 0, diag, stats)
 rowsum = torch.empty(rows, device=dev); colsum = torch.empty(N, device=dev)

@@ -2,8 +2,8 @@
 """BASELINE.json configs[4]: end-to-end OneProt train step on B200 - random-init ESM-2 650M towers + projection heads +
 fused ClipLoss - and the loss path's share of it.
 
-    python tools/e2e_step.py [--batch 256] [--seq-len 128] [--steps 5]                       # one GPU
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/e2e_step.py
+    python tests/perf_e2e_step.py [--batch 256] [--seq-len 128] [--steps 5]                       # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tests/perf_e2e_step.py
 
 What is timed (CUDA events, max over ranks), mirroring the reference's training_step for ONE modality pair
 (oneprot_module.py:92-108) with the shipped configuration (configs/model/oneprot.yaml, components/sequence.yaml:
@@ -20,8 +20,8 @@ gradient-norm clipping at 1.0):
 
 and the same step with the loss (and only the loss) swapped for the unmodified reference ClipLoss from oracle/_ref run
 eagerly - the reference's own arrangement.  The encoders are not this repository's product: the number that matters
-here is the share of the step the loss path takes and how the swap changes the step.  Test/measurement tool: it may
-import oracle/ (checker) - nothing under oneprot_b200/ does."""
+here is the share of the step the loss path takes and how the swap changes the step.  Lives under tests/ because it
+executes oracle/ (the reference classes of oracle/_ref as the comparison arm) - nothing under oneprot_b200/ does."""
 import argparse
 import json
 import os

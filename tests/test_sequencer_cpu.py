@@ -403,3 +403,39 @@ def test_sequencer_workspace_regions_do_not_overlap(streams, n, d, panel_rows):
         assert a0 + sz <= b0, (na, nb)
     assert regs[-1][1] + regs[-1][2] <= endb
     assert all(_addr(a["Wz"]) == _addr(dz[0]["Wz"]) for a in dz) and all(int(a["ldw"]) == ldw for a in dz)
+
+
+# ---------------------------------------------------------------------------------------------
+# static NVLS provider (CUDA-graph replay with world_size > 1): a step must be the SAME command list at every call
+# ---------------------------------------------------------------------------------------------
+class FakeStaticNvlsComm(FakeNvlsComm):
+    def __init__(self, world, rank, streams):
+        comm_mod.NvlsComm.__init__(self, K, object(), world, rank, torch.device("cpu"), static=True)
+        self.symm = FakeSymm(world, streams)
+        self.streams = streams
+
+    def side_stream(self, dev):
+        return comm_mod.NvlsComm.side_stream(self, dev)      # static: None (no side stream inside a captured step)
+
+
+@pytest.mark.parametrize("ll,gwg", [(False, True), (True, True), (False, False)])
+def test_static_provider_repeats_one_command_list(streams, ll, gwg):
+    """What graphed.py captures at world_size > 1: every step starts with a barrier (write-after-read protection of the
+    single buffer set), gathers with the separate multicast kernel (no epoch-flagged fused gather), stays on one stream,
+    runs 5 barriers, and - addresses included - is identical from one call to the next."""
+    world, n, d = 2, 512, 64                      # n % 256 == 0: the eager provider would fuse the gather here
+    A, B, scale = _pair(n, d)
+    comm = FakeStaticNvlsComm(world, 0, streams)
+    cfg = dict(_cfg(world, 0, ll, gwg, cl.DEFAULT_PANEL_BYTES, False, True))
+    runs = []
+    for _ in range(3):
+        lines, reg = _run(streams, A, B, scale, cfg, comm)
+        runs.append(_canon(lines, reg + _sym_regions(comm), drop=()))
+    sym_only = [[ln for ln in r if "sym+" in ln or "mc+" in ln or ln.startswith("barrier")] for r in runs]
+    assert sym_only[1] == sym_only[2]             # same symmetric-memory addresses, same order (run 0 allocates the workspace)
+    ln = runs[2]
+    kinds = [x.split()[0] for x in ln]
+    assert kinds.count("barrier") == 5 and kinds[0] == "barrier"
+    assert "mc_store" in kinds and kinds.index("mc_store") < kinds.index("fwd_sums")
+    assert not any(x.startswith("  ag ") for x in ln)                           # no fused gather
+    assert not any(x.endswith(f"st={SIDE:#x}") or x.endswith("st=side") for x in ln)   # one stream

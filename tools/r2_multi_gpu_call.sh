@@ -19,6 +19,6 @@ run mg_bench_1    python bench.py --gpus 1 $S --no-cpu-baseline
 run mg_m5         $TR --master-port 29516 bench.py --gpus $G --config modalities5 --steps 50 --warmup 5
 run mg_eager      $TR --master-port 29515 tests/perf_eager_bar.py --world --sizes 8192,32768 --reps 5 --out gpurun_out/eager_bar_w$G.json
 run mg_timeline   $TR --master-port 29517 tools/timeline.py
-T=400 run mg_e2e  $TR --master-port 29518 tools/e2e_step.py --batch 256 --seq-len 128 --out gpurun_out/e2e_w$G.json
+T=400 run mg_e2e  $TR --master-port 29518 tests/perf_e2e_step.py --batch 256 --seq-len 128 --out gpurun_out/e2e_w$G.json
 grep -h '"metric"' gpurun_out/mg_bench_seq.log gpurun_out/mg_bench_py.log gpurun_out/mg_bench_seq2.log gpurun_out/mg_bench_1.log gpurun_out/mg_m5.log > gpurun_out/r2_mg${G}_bench_lines.json
 echo done

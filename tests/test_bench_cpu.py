@@ -80,3 +80,21 @@ def test_reference_arm_prints_one_line():
     ln = lines[0]
     assert ln["impl"] == "reference" and ln["e2e"]["h2d_bytes_per_step"] == 0 and ln["cpu_baseline"]["kind"] == "port"
     assert ln["e2e"]["value"] == ln["value"] == ln["cpu_baseline"]["value"]
+
+
+def test_global_synthetic_pair_does_not_depend_on_the_sharding():
+    """bench.py draws rows [rank n, (rank + 1) n) of ONE global pair: any sharding concatenates to the same matrices, so
+    the global loss is comparable across GPU counts (different data per world size)."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from tools.synthetic import GLOBAL_BLOCK, synthetic_global_rows
+    N, d = 4 * GLOBAL_BLOCK, 16
+    a, b = synthetic_global_rows(0, N, d)
+    for world in (2, 4, 8):
+        n = N // world
+        parts = [synthetic_global_rows(r * n, n, d) for r in range(world)]
+        assert torch.equal(torch.cat([p[0] for p in parts]), a) and torch.equal(torch.cat([p[1] for p in parts]), b)
+    a2, b2 = synthetic_global_rows(300, 1000, d)                       # unaligned windows are slices of the same pair
+    assert torch.equal(a2, a[300:1300]) and torch.equal(b2, b[300:1300])
+    a3, _ = synthetic_global_rows(0, N, d, pair_id=1)
+    assert not torch.equal(a3, a)

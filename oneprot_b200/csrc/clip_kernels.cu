@@ -419,11 +419,11 @@ clip_s_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         item_to_jc(p, item, jl, ch);
         const int ib1 = min(p.nI, (ch + 1) * p.CI);
         for (int ib = ch * p.CI; ib < ib1; ++ib) {
-          mbar_wait(&s.tail->tempty[acc], acc_phase ^ 1);
+          mbar_wait_warp(&s.tail->tempty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * BN;
           for (int kb = 0; kb < p.nK; ++kb) {
-            mbar_wait(&s.tail->full[ps.stage], ps.phase);
+            mbar_wait_warp(&s.tail->full[ps.stage], ps.phase);
             tc_fence_after();
             if (elect_one()) {
               const uint32_t sa = stages_s + ps.stage * STAGE_BYTES;
@@ -791,11 +791,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
       uint32_t acc_phase = 0;
       const uint32_t stages_s = smem_u32(s.stages);
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        mbar_wait(&s.tail->tempty[acc], acc_phase ^ 1);
+        mbar_wait_warp(&s.tail->tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.nK; ++kb) {
-          mbar_wait(&s.tail->full[ps.stage], ps.phase);
+          mbar_wait_warp(&s.tail->full[ps.stage], ps.phase);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = stages_s + ps.stage * STAGE_BYTES;

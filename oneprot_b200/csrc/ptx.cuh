@@ -75,6 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait of a whole warp that walks a loop in lock step (the UMMA-issuing warp): every lane polls.  The CPU emulation of
+// the tests (independent OS threads per lane) lets ONE lane wait and joins the others at a warp barrier - a lane that
+// wakes late could otherwise find the barrier already one phase further and wait for ever.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -40,8 +40,11 @@ inline bool elect_one() { return lane_id() == 0; }
 struct MBarState { int init = 0, pending = 0; long tx = 0; uint32_t phase = 0; };
 inline std::mutex& mbar_mu() { static std::mutex m; return m; }
 inline std::map<const void*, MBarState>& mbar_tab() { static std::map<const void*, MBarState> t; return t; }
+// Waiters BLOCK on this condition variable (a yield-spin of several hundred emulated threads on one mutex melts down
+// as soon as the host is loaded: round 2 saw the CPU suite go from 4 to > 40 minutes); every phase flip wakes them.
+inline std::condition_variable& mbar_cv() { static std::condition_variable c; return c; }
 inline void mbar_check(MBarState& s) {
-  if (s.pending == 0 && s.tx == 0) { s.phase ^= 1u; s.pending = s.init; }
+  if (s.pending == 0 && s.tx == 0) { s.phase ^= 1u; s.pending = s.init; mbar_cv().notify_all(); }
 }
 inline void mbar_init(uint64_t* bar, uint32_t count) {
   std::lock_guard<std::mutex> lk(mbar_mu());
@@ -70,7 +73,14 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return mbar_tab()[bar].phase != parity;      // the phase with this parity has completed
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) std::this_thread::yield();
+  std::unique_lock<std::mutex> lk(mbar_mu());
+  MBarState& s = mbar_tab()[bar];                      // (std::map: references stay valid across insertions)
+  mbar_cv().wait(lk, [&] { return s.phase != parity; });
+}
+
+inline void mbar_wait_warp(uint64_t* bar, uint32_t parity) {      // see ptx.cuh: one lane waits, the warp joins
+  if (lane_id() == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ---- TMA -------------------------------------------------------------------------------------------------

@@ -85,6 +85,9 @@ int oneprot_clip_fwd_sums(const void* A, const void* B_all, int n, int N, int d,
  * way; their global maximum is written to stats_out[0..1] for the later kernels.
  * flags/flags_mc: u32[world][chunks + 1]; stats_all/stats_mc: float[world][4]; counters:
  * u32[chunks], zero-initialised once.  All *_mc pointers alias symmetric memory.
+ * The flags of a chunk are raised only after EVERY CTA of the grid has pushed its slice, so the whole grid must be
+ * resident at once: with `ag` the kernel is launched cooperatively (the launch fails instead of starting a grid that
+ * cannot be placed) and every flag wait is a bounded spin that traps (ONEPROT_WAIT_TRAP_CYCLES).
  * Replaces gather_features (loss.py:19-46) for the forward, overlapped with get_logits. */
 typedef struct {
   const void* src;

@@ -4,7 +4,7 @@ exists.  Test infrastructure (started by tests/test_bench_cpu.py in a subprocess
 events / pinned memory are stubs, the kernels are the float64 emulation of tests/fake_kernels.py and
 the problem is tiny (ONEPROT_BENCH_N / _D).  The numbers it prints mean nothing.
 
-    python tests/bench_cpu_harness.py [pipelined|fallback|lib-pipelined|lib-fallback]
+    python tests/bench_cpu_harness.py [pipelined|fallback|m5|lib-pipelined|lib-fallback]
 
 The lib-* modes replace the float64 stand-ins by the library itself compiled for the CPU (tests/emu), so
 bench.py's calls go through the real kernels.py wrappers, ctypes signatures and C entry points.
@@ -111,4 +111,6 @@ if world > 1:      # launched by torch.distributed.run: NCCL -> gloo
     _init = dist.init_process_group
     dist.init_process_group = lambda backend=None, device_id=None, **k: _init("gloo", **k)
 sys.argv = ["bench.py", "--gpus", str(world), "--steps", "2" if "ONEPROT_LIB" in os.environ else "3", "--warmup", "3"]
+if mode == "m5":      # BASELINE cfg 3: five pairs in sequence (tiny here), host variants that cannot run on the CPU are skipped
+    sys.argv += ["--config", "modalities5", "--no-cpu-baseline"]
 bench.main()

@@ -98,3 +98,18 @@ def test_global_synthetic_pair_does_not_depend_on_the_sharding():
     assert torch.equal(a2, a[300:1300]) and torch.equal(b2, b[300:1300])
     a3, _ = synthetic_global_rows(0, N, d, pair_id=1)
     assert not torch.equal(a3, a)
+
+
+def test_modalities5_config_control_flow():
+    """`bench.py --config modalities5` (BASELINE cfg 3) through the stand-ins: one JSON line, per-host-variant times, the
+    CUDA-graph variant reported as unavailable on the CPU without taking the line down."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_cpu_harness.py"), "m5"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = _json_lines(p.stdout)
+    assert len(lines) == 1, p.stdout
+    ln = lines[0]
+    c = ln["config"]
+    assert c["pairs"] == 5 and c["rows_per_gpu"] == 1024 and ln["scaling"] == "weak" and ln["n_gpus"] == 1
+    assert "python host" in c["ms_per_step_by_host"] and abs(c["us_per_pair"] - 1e3 * ln["ms_per_step"] / 5) < 1e-6
+    assert ln["value"] == pytest.approx(5 * 1024 / (ln["ms_per_step"] * 1e-3))
